@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Bifrost hot path.
+
+Metric (BASELINE.json): Msamples/s through the FDMT on a synthetic 4096-chan
+int8 filterbank (config 2: max_dm=100 -> max_delay=794, 131072 output samples
+per gulp), plus % of the HBM roofline.  One "step" = one gulp through
+bfFdmtExecute.  `value` is timed with the input resident in HBM; `e2e` is the
+same call made from HOST buffers (pinned) with the H2D copy of the gulp and
+the D2H read of the dispersion bank inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (under torchrun): rank g processes its own 4096-channel sub-band (weak
+scaling, no data-path collective -- SURVEY 8e); time = max over ranks.
+`--impl reference` times the CPU restatement of the reference algorithm
+(oracle/) on the host cores of this box on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NCHAN = 4096
+NTIME_OUT = 131072
+F0_MHZ = 1000.0
+BW_MHZ = 400.0
+DT_S = 256e-6
+MAX_DM = 100.0
+KDM = 4.148741601e3
+
+
+def max_delay_for(f0, df, nchan, dt, max_dm):
+    """blocks/fdmt.py:79-81 of the reference."""
+    rel = (f0 ** -2 - (f0 + nchan * df) ** -2)
+    return int(np.ceil(abs(KDM / dt * max_dm * rel)))
+
+
+def workload(rank=0):
+    df = BW_MHZ / NCHAN
+    f0 = F0_MHZ + rank * NCHAN * df
+    md = max_delay_for(F0_MHZ, df, NCHAN, DT_S, MAX_DM)      # same bank depth on every rank
+    return dict(nchan=NCHAN, ntime=NTIME_OUT + md, max_delay=md, f0=f0, df=df)
+
+
+def make_input(w, seed, ntime=None):
+    """round(N(0,20)) clipped to int8 plus three dispersed pulses (BASELINE.md cfg 2)."""
+    ntime = ntime or w['ntime']
+    rng = np.random.default_rng(seed)
+    x = np.empty((w['nchan'], ntime), np.int8)
+    step = 256
+    for c0 in range(0, w['nchan'], step):
+        blk = rng.normal(0, 20, size=(step, ntime)).astype(np.float32)
+        np.rint(blk, out=blk)
+        np.clip(blk, -127, 127, out=blk)
+        x[c0:c0 + step] = blk.astype(np.int8)
+    f = w['f0'] + w['df'] * np.arange(w['nchan'])
+    fmax = f[-1]
+    rel = (f ** -2 - fmax ** -2) / (f[0] ** -2 - fmax ** -2)
+    for frac_dm, t0 in ((0.2, ntime // 5), (0.5, ntime // 2), (0.9, (3 * ntime) // 4)):
+        tt = t0 + np.rint(rel * frac_dm * (w['max_delay'] - 1)).astype(np.int64)
+        ok = tt < ntime
+        x[np.arange(w['nchan'])[ok], tt[ok]] = 100
+    return x
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smmax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smmax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(np.max(smmax)) if smmax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), 'measured'
+        except Exception:
+            pass
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), 'fallback'
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_fdmt_sample(w, ntime_sample, threads=None):
+    """Times the oracle (CPU restatement of the reference algorithm) on a
+    bounded sample: the full 4096 channels, `ntime_sample` time samples.
+    Returns (Msamples/s, kind, cores, seconds)."""
+    x = make_input(w, 4321, ntime=ntime_sample + w['max_delay'])
+    try:
+        from oracle import fdmt_c
+        have_c = fdmt_c.available()
+    except Exception:
+        have_c = False
+    nsamp = w['nchan'] * ntime_sample
+    if have_c:
+        from oracle import fdmt_c
+        cores = threads or os.cpu_count()
+        plan = fdmt_c.Plan(w['nchan'], w['max_delay'], w['f0'], w['df'])
+        out = np.zeros((w['max_delay'], x.shape[1]), np.float32)
+        plan.execute(x, out, threads=cores)            # warm (page-in, thread pool)
+        t0 = time.perf_counter()
+        plan.execute(x, out, threads=cores)
+        dt = time.perf_counter() - t0
+        return nsamp / dt / 1e6, 'port', cores, dt
+    from oracle import fdmt as ofdmt
+    plan = ofdmt.FdmtPlan(w['nchan'], w['max_delay'], w['f0'], w['df'])
+    t0 = time.perf_counter()
+    ofdmt.fdmt(x, w['max_delay'], w['f0'], w['df'], plan=plan)
+    dt = time.perf_counter() - t0
+    return nsamp / dt / 1e6, 'port', 1, dt
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    w = workload(0)
+    ntime_sample = 8192
+    vals, secs = [], []
+    cores = 1
+    for i in range(args.warmup + args.steps):
+        v, kind, cores, dt = cpu_fdmt_sample(w, ntime_sample)
+        if i >= args.warmup:
+            vals.append(v)
+            secs.append(dt)
+    value = float(np.mean(vals))
+    sample = (f"oracle CPU FDMT on {w['nchan']} chan x {ntime_sample} samples "
+              f"(1/{NTIME_OUT // ntime_sample} of the gulp) per step, {cores} threads")
+    line = dict(impl='reference', metric='FDMT throughput, 4096-chan int8 filterbank, max_delay=%d'
+                % w['max_delay'], value=value, unit='Msamples/s', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=float(np.mean(secs) * 1e3),
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic',
+                config=dict(workload='BASELINE config 2: FDMT max_dm=100 on 4096-chan x 128k-sample '
+                                     'int8 filterbank (bounded sample, see cpu_baseline.sample)'),
+                cpu_baseline=dict(value=value, unit='Msamples/s', cores=cores, kind='port',
+                                  sample=sample),
+                e2e=dict(value=value, unit='Msamples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import bifrost_b200 as bf
+    from bifrost_b200.fdmt import Fdmt
+
+    torch.cuda.set_device(local_rank)
+    bf.device.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    stream = torch.cuda.current_stream()
+    bf.device.set_stream(stream.cuda_stream)
+
+    w = workload(rank)
+    nchan, ntime, md = w['nchan'], w['ntime'], w['max_delay']
+    x_host = make_input(w, 1234 + rank)
+    pinned_in = bf.empty((nchan, ntime), dtype='i8', space='cuda_host')
+    np.copyto(np.asarray(pinned_in), x_host)
+    pinned_out = bf.empty((md, ntime), dtype='f32', space='cuda_host')
+    d_in = bf.empty((nchan, ntime), dtype='i8', space='cuda')
+    d_out = bf.empty((md, ntime), dtype='f32', space='cuda')
+    bf.copy_array(d_in, pinned_in)
+    bf.memset_array(d_out, 0)
+    plan = Fdmt()
+    plan.init(nchan, md, w['f0'], w['df'])
+    ws_size = plan.get_workspace_size(d_in, d_out)
+    ws = bf.empty((ws_size,), dtype='u8', space='cuda')
+
+    def step_resident():
+        plan.execute_workspace(d_in, d_out, ws.ctypes.data, ws_size)
+
+    def step_e2e():
+        bf.copy_array(d_in, pinned_in)            # H2D of this gulp (pinned, async on the stream)
+        plan.execute_workspace(d_in, d_out, ws.ctypes.data, ws_size)
+        bf.copy_array(pinned_out, d_out)          # D2H of the dispersion bank (+ stream sync)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nwarm, nstep, sampler=None):
+        for _ in range(nwarm):
+            fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = bf.launch_count()
+        ev0.record(stream)
+        for _ in range(nstep):
+            fn()
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = ev0.elapsed_time(ev1)
+        launches = bf.launch_count() - launches0
+        if world > 1:
+            t = torch.tensor([ms], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, launches, clocks = timed(step_resident, args.warmup, args.steps, sampler)
+    ms_step = ms_total / args.steps
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e_total, _, _ = timed(step_e2e, 2, e2e_steps)
+    ms_e2e = ms_e2e_total / e2e_steps
+
+    samples_per_step = nchan * NTIME_OUT * world            # pol not counted
+    value = samples_per_step / (ms_step * 1e-3) / 1e6
+    e2e_value = samples_per_step / (ms_e2e * 1e-3) / 1e6
+
+    # Roofline of the op (all kernels of one bfFdmtExecute): compulsory bytes
+    # ntime*(nchan*1 + max_delay*4) per gulp, per GPU.
+    peaks, peak_kind = measured_peaks()
+    alg_bytes = ntime * (nchan * 1 + md * 4)
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    roofline = dict(bound='hbm', kernel='bfFdmtExecute (all launches of one call)',
+                    achieved=achieved, peak=peaks['hbm_gbs'], peak_source=peak_kind,
+                    unit='GB/s', frac=achieved / peaks['hbm_gbs'],
+                    algorithmic_bytes=alg_bytes, traffic=None)
+    prof = os.path.join(ROOT, 'profiles', 'fdmt_traffic.json')
+    if os.path.exists(prof):
+        try:
+            roofline['traffic'] = json.load(open(prof)).get('dram_bytes_per_call')
+        except Exception:
+            pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, kind, cores, dt = cpu_fdmt_sample(w, 8192)
+        cpu = dict(value=v, unit='Msamples/s', cores=cores, kind=kind,
+                   sample=f"{nchan} chan x 8192 samples (1/16 of the gulp), {dt:.2f} s, "
+                          f"{cores} thread(s) of {os.cpu_count()} host cores")
+
+    line = dict(metric='FDMT throughput, 4096-chan int8 filterbank, max_delay=%d' % md,
+                value=value, unit='Msamples/s', n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='BASELINE config 2: bfFdmtExecute, max_dm=100 '
+                                     f'(max_delay={md}) on {nchan}-chan x {NTIME_OUT}(+{md})-sample '
+                                     'int8 filterbank per GPU; f0=1000 MHz, bw=400 MHz, dt=256 us',
+                            sharding='one 4096-chan sub-band per GPU, no collective' if world > 1
+                                     else 'single GPU',
+                            l2='input 537 MB + output 419 MB per step exceed the 126 MB L2'),
+                roofline=roofline, cpu_baseline=cpu,
+                e2e=dict(value=e2e_value, unit='Msamples/s', ms_per_step=ms_e2e,
+                         h2d_bytes_per_step=int(nchan * ntime), d2h_bytes_per_step=int(md * ntime * 4)),
+                gpu_launches=int(launches), clocks=clocks)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,316 @@
+/* bifrost_b200.h -- C ABI of the B200-native Bifrost hot path.
+ *
+ * One consolidated header for the drop-in boundary.  Every type, enum value
+ * and entry point below is what the reference's ctypes FFI binds for the
+ * per-gulp DSP path; names, argument order and status codes are kept so that
+ * `libbifrost_b200.so` can be loaded in place of `libbifrost.so` for this
+ * path.  Each declaration cites the reference interface it replaces
+ * (paths relative to the reference tree).
+ *
+ * The per-topic headers under include/bifrost/ (fdmt.h, fft.h, ...) simply
+ * include this file, so C/C++ callers that `#include <bifrost/fdmt.h>` keep
+ * compiling.
+ */
+#ifndef BIFROST_B200_H_
+#define BIFROST_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ *
+ * Scalars and status codes            (ref: src/bifrost/common.h:40-84)
+ * ------------------------------------------------------------------ */
+typedef int                BFbool;
+typedef float              BFcomplex[2];
+typedef float              BFreal;
+typedef unsigned long      BFsize;
+typedef unsigned long long BFoffset;
+typedef signed long long   BFdelta;
+
+typedef enum BFstatus_ {
+	BF_STATUS_SUCCESS              = 0,
+	BF_STATUS_END_OF_DATA          = 1,
+	BF_STATUS_WOULD_BLOCK          = 2,
+	BF_STATUS_INVALID_POINTER      = 8,
+	BF_STATUS_INVALID_HANDLE       = 9,
+	BF_STATUS_INVALID_ARGUMENT     = 10,
+	BF_STATUS_INVALID_STATE        = 11,
+	BF_STATUS_INVALID_SPACE        = 12,
+	BF_STATUS_INVALID_SHAPE        = 13,
+	BF_STATUS_INVALID_STRIDE       = 14,
+	BF_STATUS_INVALID_DTYPE        = 15,
+	BF_STATUS_MEM_ALLOC_FAILED     = 32,
+	BF_STATUS_MEM_OP_FAILED        = 33,
+	BF_STATUS_UNSUPPORTED          = 48,
+	BF_STATUS_UNSUPPORTED_SPACE    = 49,
+	BF_STATUS_UNSUPPORTED_SHAPE    = 50,
+	BF_STATUS_UNSUPPORTED_STRIDE   = 51,
+	BF_STATUS_UNSUPPORTED_DTYPE    = 52,
+	BF_STATUS_FAILED_TO_CONVERGE   = 64,
+	BF_STATUS_INSUFFICIENT_STORAGE = 65,
+	BF_STATUS_DEVICE_ERROR         = 66,
+	BF_STATUS_INTERNAL_ERROR       = 99
+} BFstatus;
+
+const char* bfGetStatusString(BFstatus status);   /* common.h:81 */
+BFbool      bfGetDebugEnabled(void);              /* common.h:82 */
+BFstatus    bfSetDebugEnabled(BFbool enabled);    /* common.h:83 */
+BFbool      bfGetCudaEnabled(void);               /* common.h:84 */
+
+/* ------------------------------------------------------------------ *
+ * Memory spaces                       (ref: src/bifrost/memory.h:43-82)
+ * ------------------------------------------------------------------ */
+typedef enum BFspace_ {
+	BF_SPACE_AUTO         = 0,
+	BF_SPACE_SYSTEM       = 1,
+	BF_SPACE_CUDA         = 2,
+	BF_SPACE_CUDA_HOST    = 3,
+	BF_SPACE_CUDA_MANAGED = 4
+} BFspace;
+
+BFstatus    bfMalloc(void** ptr, BFsize size, BFspace space);
+BFstatus    bfFree(void* ptr, BFspace space);
+BFstatus    bfGetSpace(const void* ptr, BFspace* space);
+const char* bfGetSpaceString(BFspace space);
+/* Synchronous w.r.t. the host, asynchronous w.r.t. the device (memory.h:59) */
+BFstatus    bfMemcpy(void* dst, BFspace dst_space,
+                     const void* src, BFspace src_space, BFsize count);
+BFstatus    bfMemcpy2D(void* dst, BFsize dst_stride, BFspace dst_space,
+                       const void* src, BFsize src_stride, BFspace src_space,
+                       BFsize width, BFsize height);
+BFstatus    bfMemset(void* ptr, BFspace space, int value, BFsize count);
+BFstatus    bfMemset2D(void* ptr, BFsize stride, BFspace space, int value,
+                       BFsize width, BFsize height);
+BFsize      bfGetAlignment(void);
+
+/* ------------------------------------------------------------------ *
+ * Array descriptor                    (ref: src/bifrost/array.h:38-234)
+ * The dtype word is a bit-field: low byte = bits per real component,
+ * 0xF00 = kind, 0xFF000 = vector length - 1, 0x100000 = complex.
+ * sizeof(BFarray) == 168 and the field order is ABI.
+ * ------------------------------------------------------------------ */
+enum { BF_MAX_DIMS = 8 };
+
+typedef enum BFdtype_ {
+	BF_DTYPE_NBIT_BITS    = 0x0000FF,
+	BF_DTYPE_TYPE_BITS    = 0x000F00,
+	BF_DTYPE_VECTOR_BITS  = 0x0FF000,
+	BF_DTYPE_VECTOR_BIT0  = 12,
+	BF_DTYPE_COMPLEX_BIT  = 0x100000,
+
+	BF_DTYPE_INT_TYPE     = 0x0000,
+	BF_DTYPE_UINT_TYPE    = 0x0100,
+	BF_DTYPE_FLOAT_TYPE   = 0x0200,
+	BF_DTYPE_STRING_TYPE  = 0x0300,
+	BF_DTYPE_STORAGE_TYPE = 0x0400,
+
+	BF_DTYPE_I1   =  1 | BF_DTYPE_INT_TYPE,
+	BF_DTYPE_I2   =  2 | BF_DTYPE_INT_TYPE,
+	BF_DTYPE_I4   =  4 | BF_DTYPE_INT_TYPE,
+	BF_DTYPE_I8   =  8 | BF_DTYPE_INT_TYPE,
+	BF_DTYPE_I16  = 16 | BF_DTYPE_INT_TYPE,
+	BF_DTYPE_I32  = 32 | BF_DTYPE_INT_TYPE,
+	BF_DTYPE_I64  = 64 | BF_DTYPE_INT_TYPE,
+
+	BF_DTYPE_U1   =  1 | BF_DTYPE_UINT_TYPE,
+	BF_DTYPE_U2   =  2 | BF_DTYPE_UINT_TYPE,
+	BF_DTYPE_U4   =  4 | BF_DTYPE_UINT_TYPE,
+	BF_DTYPE_U8   =  8 | BF_DTYPE_UINT_TYPE,
+	BF_DTYPE_U16  = 16 | BF_DTYPE_UINT_TYPE,
+	BF_DTYPE_U32  = 32 | BF_DTYPE_UINT_TYPE,
+	BF_DTYPE_U64  = 64 | BF_DTYPE_UINT_TYPE,
+
+	BF_DTYPE_F16  = 16 | BF_DTYPE_FLOAT_TYPE,
+	BF_DTYPE_F32  = 32 | BF_DTYPE_FLOAT_TYPE,
+	BF_DTYPE_F64  = 64 | BF_DTYPE_FLOAT_TYPE,
+
+	BF_DTYPE_CI1  =  1 | BF_DTYPE_INT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CI2  =  2 | BF_DTYPE_INT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CI4  =  4 | BF_DTYPE_INT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CI8  =  8 | BF_DTYPE_INT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CI16 = 16 | BF_DTYPE_INT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CI32 = 32 | BF_DTYPE_INT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CI64 = 64 | BF_DTYPE_INT_TYPE | BF_DTYPE_COMPLEX_BIT,
+
+	BF_DTYPE_CF16 = 16 | BF_DTYPE_FLOAT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CF32 = 32 | BF_DTYPE_FLOAT_TYPE | BF_DTYPE_COMPLEX_BIT,
+	BF_DTYPE_CF64 = 64 | BF_DTYPE_FLOAT_TYPE | BF_DTYPE_COMPLEX_BIT
+} BFdtype;
+
+typedef struct BFarray_ {
+	void*   data;
+	BFspace space;
+	BFdtype dtype;
+	int     ndim;
+	long    shape[BF_MAX_DIMS];    /* elements */
+	long    strides[BF_MAX_DIMS];  /* bytes    */
+	BFbool  immutable;
+	BFbool  big_endian;
+	BFbool  conjugated;
+} BFarray;
+
+/* In: space, dtype, ndim, shape.  Out: data, strides.  (array.h:226-234) */
+BFstatus bfArrayMalloc(BFarray* array);
+BFstatus bfArrayFree(const BFarray* array);
+BFstatus bfArrayCopy(const BFarray* dst, const BFarray* src);
+BFstatus bfArrayMemset(const BFarray* array, int value);
+
+/* ------------------------------------------------------------------ *
+ * Device / stream glue                  (ref: src/bifrost/cuda.h:38-45)
+ * All compute entry points enqueue on the calling thread's stream
+ * (default: cudaStreamPerThread, ref src/cuda.cpp:34) and return without
+ * waiting for the device.
+ * ------------------------------------------------------------------ */
+BFstatus bfStreamGet(void* stream);        /* cudaStream_t* out */
+BFstatus bfStreamSet(void const* stream);  /* cudaStream_t const* in */
+BFstatus bfStreamSynchronize(void);
+BFstatus bfDeviceGet(int* device);
+BFstatus bfDeviceSet(int device);
+BFstatus bfDeviceSetById(const char* pci_bus_id);
+BFstatus bfDevicesSetNoSpinCPU(void);
+
+/* ------------------------------------------------------------------ *
+ * Transpose                         (ref: src/bifrost/transpose.h:40-42)
+ * out = in.transpose(axes); elements are opaque 1..16-byte words.
+ * ------------------------------------------------------------------ */
+BFstatus bfTranspose(BFarray const* in, BFarray const* out, int const* axes);
+
+/* ------------------------------------------------------------------ *
+ * Reduce                              (ref: src/bifrost/reduce.h:44-57)
+ * Exactly one axis of `out` is shorter than in `in` by an integer factor.
+ * ------------------------------------------------------------------ */
+typedef enum BFreduce_op_ {
+	BF_REDUCE_SUM,
+	BF_REDUCE_MEAN,
+	BF_REDUCE_MIN,
+	BF_REDUCE_MAX,
+	BF_REDUCE_STDERR,
+	BF_REDUCE_POWER_SUM,
+	BF_REDUCE_POWER_MEAN,
+	BF_REDUCE_POWER_MIN,
+	BF_REDUCE_POWER_MAX,
+	BF_REDUCE_POWER_STDERR
+} BFreduce_op;
+
+BFstatus bfReduce(BFarray const* in, BFarray const* out, BFreduce_op op);
+
+/* ------------------------------------------------------------------ *
+ * FDMT                                (ref: src/bifrost/fdmt.h:48-126)
+ * in  [..., nchan, ntime]  (i8/i16/i32/u8/u16/u32/f32, time fastest)
+ * out [..., max_delay, ntime] f32; row d holds the transform at delay d,
+ * aligned to the arrival time at the highest frequency; the last d samples
+ * of row d are left untouched (ref: src/fdmt.cu:120-124,702-708).
+ * Storage protocol for plan_storage / exec_storage (fdmt.h:71-78,108-115):
+ *   (NULL, NULL)  library-managed;  (NULL, &size) query only;
+ *   (ptr,  &size) caller-provided.
+ * ------------------------------------------------------------------ */
+typedef struct BFfdmt_impl* BFfdmt;
+
+BFstatus bfFdmtCreate(BFfdmt* plan);
+BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
+                    double f0, double df, double exponent, BFspace space,
+                    void* plan_storage, BFsize* plan_storage_size);
+BFstatus bfFdmtSetStream(BFfdmt plan, void const* stream);
+BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
+                       BFbool negative_delays,
+                       void* exec_storage, BFsize* exec_storage_size);
+BFstatus bfFdmtDestroy(BFfdmt plan);
+
+/* ------------------------------------------------------------------ *
+ * FFT                                   (ref: src/bifrost/fft.h:39-60)
+ * complex->complex: [i]fft; real->complex: rfft; complex->real: irfft.
+ * Unnormalised in both directions.  Integer inputs are scaled to [-1,1)
+ * on load (ci8/i8: x/128, ci16/i16: x/32768, ci4: nibble<<4 then /128;
+ * ref: src/fft_kernels.cu:96-197).  apply_fftshift centres DC on output
+ * for forward transforms and un-centres the input for inverse ones.
+ * ------------------------------------------------------------------ */
+typedef struct BFfft_impl* BFfft;
+
+BFstatus bfFftCreate(BFfft* plan);
+BFstatus bfFftInit(BFfft plan, BFarray const* in, BFarray const* out,
+                   int rank, int const* axes, BFbool apply_fftshift,
+                   size_t* tmp_storage_size);
+BFstatus bfFftExecute(BFfft plan, BFarray const* in, BFarray const* out,
+                      BFbool inverse, void* tmp_storage,
+                      size_t tmp_storage_size);
+BFstatus bfFftDestroy(BFfft plan);
+
+/* ------------------------------------------------------------------ *
+ * LinAlg                              (ref: src/bifrost/linalg.h:43-54)
+ * c = alpha*a.b + beta*c;  b==NULL: a.a^H;  a==NULL: b^H.b.
+ * The a.a^H / b^H.b forms write the lower triangle only.
+ * ------------------------------------------------------------------ */
+typedef struct BFlinalg_impl* BFlinalg;
+
+BFstatus bfLinAlgCreate(BFlinalg* handle);
+BFstatus bfLinAlgDestroy(BFlinalg handle);
+BFstatus bfLinAlgMatMul(BFlinalg handle, double alpha,
+                        BFarray const* a, BFarray const* b,
+                        double beta, BFarray const* c);
+
+/* ------------------------------------------------------------------ *
+ * Unpack                              (ref: src/bifrost/unpack.h:55-57)
+ * 1/2/4-bit i/u/ci -> 8-bit (or wider) of the same kind.
+ * ------------------------------------------------------------------ */
+BFstatus bfUnpack(BFarray const* in, BFarray const* out, BFbool align_msb);
+
+/* ------------------------------------------------------------------ *
+ * Map                                  (ref: src/bifrost/map.h:82-94)
+ * The reference JIT-compiles `func` with NVRTC.  This build ships fixed
+ * sm_100a kernels for the expressions the hot-path blocks emit (detect:
+ * python/bifrost/blocks/detect.py:87-136; accumulate:
+ * python/bifrost/blocks/accumulate.py:67) and returns
+ * BF_STATUS_UNSUPPORTED for any other expression.
+ * ------------------------------------------------------------------ */
+BFstatus bfMap(int ndim, long const* shape, char const* const* axis_names,
+               int narg, BFarray const* const* args,
+               char const* const* arg_names,
+               char const* func_name, char const* func,
+               char const* extra_code,
+               int const* block_shape, int const* block_axes);
+BFstatus bfMapClearCache(void);
+
+/* ------------------------------------------------------------------ *
+ * B200 extensions (no reference counterpart).  Same conventions: borrowed
+ * BFarrays, asynchronous on the thread's stream, BFstatus returns.
+ * ------------------------------------------------------------------ */
+
+/* Stokes / power detection as a fixed kernel.  mode: 0 scalar |x|^2,
+ * 1 jones (xx, yy, xy as cf32[.,2,2]...), 2 stokes (I,Q,U,V),
+ * 3 stokes_i, 4 coherence.  `axis` is the polarisation axis of `in`
+ * (ignored for mode 0).  Semantics of blocks/detect.py:86-138. */
+BFstatus bfDetect(BFarray const* in, BFarray const* out, int mode, int axis);
+
+/* b = beta*b + a  (blocks/accumulate.py:63-74) */
+BFstatus bfAccumulate(BFarray const* a, BFarray const* b, double beta);
+
+/* Fused GUPPI spectrometer gulp: for ci8 voltages laid out as the raw
+ * GUPPI block [nchan][ntime][npol=2] (ntime = nframe*nfft), compute per
+ * frame the nfft-point forward FFT with fftshift of both polarisations,
+ * Stokes IQUV, sum of f_avg adjacent fine channels, and
+ * out = beta*out + sum over the nframe frames.
+ * out: f32 [4][nchan*nfft/f_avg].  Equivalent to the reference chain
+ * transpose -> fft -> detect('stokes') -> reduce('freq', f_avg) ->
+ * accumulate(nframe) (testbench/gpuspec_simple.py:44-55). */
+BFstatus bfSpectrometerFused(BFarray const* in, BFarray const* out,
+                             int nfft, int f_avg, double beta);
+
+/* Host-only introspection of the FDMT plan bfFdmtInit would build (no device
+ * needed).  step < 0: writes the number of steps to *nrow.  Otherwise writes
+ * the row count of `step` to *nrow and, if rows != NULL, nrow triples
+ * (src_row0, src_row1, delay) for step >= 1, or (row0, ndelay, 0) per channel
+ * for step 0 (nchan triples). */
+BFstatus bfFdmtPlanQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+                         double exponent, int step, int* nrow, int* rows);
+
+/* Number of kernels this library has launched since load (all threads). */
+BFstatus bfGetLaunchCount(unsigned long long* count);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* BIFROST_B200_H_ */

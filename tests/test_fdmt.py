@@ -1,0 +1,215 @@
+"""FDMT parity.  CPU: the oracle against the golden outputs of the reference's
+own CUDA code.  GPU: libbifrost_b200 against the oracle (bit-exact -- the FDMT
+is a fixed tree of fp32 operations), against the reference library when it
+travelled, plus the reference's own smoke checks (test/test_fdmt.py:38-65) and
+size-independent properties at large sizes."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import bifrost_b200 as bf
+from bifrost_b200.fdmt import Fdmt
+from oracle import fdmt as ofdmt
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from golden.make_fdmt_golden import CASES as GOLDEN_CASES, SENTINEL  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'fdmt_ref_golden.npz')
+
+
+def assert_same_bits(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    assert a.shape == b.shape
+    mism = a.view(np.uint32) != b.view(np.uint32)
+    both_nan = np.isnan(a) & np.isnan(b)
+    mism &= ~both_nan
+    assert not mism.any(), f"{mism.sum()} of {mism.size} values differ; first at {np.argwhere(mism)[0]}"
+
+
+# ------------------------------------------------------------------ CPU ----
+@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="golden file not generated yet")
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+def test_oracle_matches_reference_golden(case):
+    """Pins oracle/fdmt.py against outputs of the reference CUDA library."""
+    name, ntime, nchan, md, f0, df, dtype, batch = case
+    g = np.load(GOLDEN)
+    x = g[name + '/in']
+    x = x.astype(np.float32) if dtype == 'f32' else x
+    out = np.full(batch + (md, ntime), SENTINEL, np.float32)
+    ofdmt.fdmt(x, md, f0, df, out=out)
+    assert_same_bits(out, g[name + '/out'])
+
+
+def test_oracle_dispersed_pulse_peaks_at_its_dm():
+    """A pulse following the nu^-2 law sums to (about) nchan in row d."""
+    nchan, ntime, md = 64, 512, 60
+    f0, df = 1000., 400. / nchan
+    plan = ofdmt.FdmtPlan(nchan, md, f0, df)
+    x = np.zeros((nchan, ntime), np.float32)
+    d_true, t0 = 41, 100
+    fmin, fmax = f0, f0 + (nchan - 1) * df
+    for c in range(nchan):
+        rel = ((f0 + c * df) ** -2 - fmax ** -2) / (fmin ** -2 - fmax ** -2)
+        x[c, t0 + int(round(rel * d_true))] = 1.0
+    out = ofdmt.fdmt(x, md, f0, df, plan=plan)
+    r, t = np.unravel_index(np.nanargmax(out), out.shape)
+    assert abs(r - d_true) <= 1 and abs(t - t0) <= 1
+    assert out[r, t] > 0.6 * nchan
+
+
+# ------------------------------------------------------------------ GPU ----
+def run_gpu(x, md, f0, df, batch=(), negative_delays=False, sentinel=SENTINEL, workspace=False):
+    nchan, ntime = x.shape[-2:]
+    plan = Fdmt()
+    plan.init(nchan, md, f0, df, -2.0, 'cuda')
+    d_in = bf.asarray(x, space='cuda')
+    d_out = bf.asarray(np.full(x.shape[:-2] + (md, ntime), sentinel, np.float32), space='cuda')
+    if workspace:
+        size = plan.get_workspace_size(d_in, d_out)
+        ws = bf.empty((size,), dtype='u8', space='cuda')
+        plan.execute_workspace(d_in, d_out, ws.ctypes.data, size, negative_delays)
+    else:
+        plan.execute(d_in, d_out, negative_delays)
+    bf.device.stream_synchronize()
+    return np.asarray(d_out.copy('system'))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+def test_gpu_matches_oracle_bit_exact(case):
+    from golden.make_fdmt_golden import make_input
+    name, ntime, nchan, md, f0, df, dtype, batch = case
+    i = [c[0] for c in GOLDEN_CASES].index(name)
+    x = make_input(name, batch + (nchan, ntime), dtype, 1234 + i)
+    x = x.astype(np.float32) if dtype == 'f32' else x
+    got = run_gpu(x, md, f0, df)
+    want = np.full(batch + (md, ntime), SENTINEL, np.float32)
+    ofdmt.fdmt(x, md, f0, df, out=want)
+    assert_same_bits(got, want)
+    if os.path.exists(GOLDEN):
+        assert_same_bits(got, np.load(GOLDEN)[name + '/out'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ntime,nchan,md,batch", [
+    (1024, 128, 200, ()), (1024, 2, 20, ()), (1024, 32, 2, ()), (1024, 32, 1, ()),
+    (1024, 33, 65, ()), (17, 33, 65, ()),
+    (1024, 128, 200, (7,)), (1024, 2, 20, (7,)), (1024, 33, 65, (7,)), (17, 33, 65, (7,)),
+    (256, 32, 20, (3, 2, 5)), (17, 33, 65, (3, 2, 5)),
+])
+def test_reference_smoke_semantics(ntime, nchan, md, batch):
+    """test/test_fdmt.py:38-65: untouched cells keep the sentinel, values stay
+    bounded, execute == execute_workspace bit for bit."""
+    rng = np.random.default_rng(1234)
+    x = rng.normal(size=batch + (nchan, ntime)).astype(np.float32)
+    f0, df = 1000., 400. / nchan
+    o1 = run_gpu(x, md, f0, df)
+    if md > 1:
+        assert o1.min() == SENTINEL
+    assert o1.max() < 100.
+    o2 = run_gpu(x, md, f0, df, workspace=True)
+    np.testing.assert_equal(o1, o2)
+    want = np.full(batch + (md, ntime), SENTINEL, np.float32)
+    ofdmt.fdmt(x, md, f0, df, out=want)
+    assert_same_bits(o1, want)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_library():
+    """Same call sequence through both C ABIs on the same device buffers."""
+    import reflib
+    ref = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/libbifrost_ref.so not present")
+    from bifrost_b200.libbifrost import _check
+    rng = np.random.default_rng(7)
+    for (ntime, nchan, md, dtype) in [(2000, 256, 300, np.float32), (1500, 100, 64, np.int8),
+                                     (4096, 512, 130, np.int8), (333, 17, 40, np.uint16)]:
+        if dtype == np.float32:
+            x = rng.normal(size=(nchan, ntime)).astype(np.float32)
+        else:
+            info = np.iinfo(dtype)
+            x = rng.integers(max(info.min, -127), min(info.max, 127) + 1, size=(nchan, ntime)).astype(dtype)
+        f0, df = 1000., 400. / nchan
+        got = run_gpu(x, md, f0, df)
+        d_in = bf.asarray(x, space='cuda')
+        d_out = bf.asarray(np.full((md, ntime), SENTINEL, np.float32), space='cuda')
+        plan = ctypes.c_void_p()
+        _check(ref.bfFdmtCreate(ctypes.byref(plan)))
+        _check(ref.bfFdmtInit(plan, nchan, md, f0, df, -2.0, 2, None, None))
+        _check(ref.bfFdmtExecute(plan, d_in.as_BFarray(), d_out.as_BFarray(), 0, None, None))
+        _check(ref.bfStreamSynchronize())
+        want = np.asarray(d_out.copy('system'))
+        _check(ref.bfFdmtDestroy(plan))
+        assert_same_bits(got, want)
+
+
+@pytest.mark.gpu
+def test_ring_style_padded_strides():
+    """Input rows with a pitch >> ntime and a batch (pol) axis, as handed over
+    by a ring span (SURVEY 8b layout fact 1)."""
+    rng = np.random.default_rng(3)
+    npol, nchan, ntime, pitch, md = 2, 48, 500, 1024, 30
+    base = rng.integers(-100, 100, size=(npol, nchan, pitch)).astype(np.int8)
+    d_base = bf.asarray(base, space='cuda')
+    d_in = d_base[:, :, 7:7 + ntime]
+    obase = bf.asarray(np.full((npol, md, pitch), SENTINEL, np.float32), space='cuda')
+    d_out = obase[:, :, :ntime]
+    f0, df = 1200., 2.0
+    plan = Fdmt()
+    plan.init(nchan, md, f0, df)
+    plan.execute(d_in, d_out)
+    bf.device.stream_synchronize()
+    got = np.asarray(obase.copy('system'))
+    want = np.full((npol, md, ntime), SENTINEL, np.float32)
+    ofdmt.fdmt(base[:, :, 7:7 + ntime], md, f0, df, out=want)
+    assert_same_bits(got[:, :, :ntime], want)
+    assert (got[:, :, ntime:] == SENTINEL).all()
+
+
+@pytest.mark.gpu
+def test_large_gulp_properties():
+    """Size-independent checks at a BASELINE-like size (oracle too slow here):
+    (1) a dispersed pulse lands in its DM row with ~nchan amplitude,
+    (2) linearity: fdmt(a + b) == fdmt(a) + fdmt(b) for integer-valued data
+        small enough that every partial sum is exact in fp32 before scaling,
+    (3) time-shift covariance away from the edges."""
+    nchan, ntime, md = 1024, 32768, 400
+    f0, df = 1000., 400. / nchan
+    fmax = f0 + (nchan - 1) * df
+    x = np.zeros((nchan, ntime), np.int8)
+    d_true, t0 = 333, 5000
+    for c in range(nchan):
+        rel = ((f0 + c * df) ** -2 - fmax ** -2) / (f0 ** -2 - fmax ** -2)
+        x[c, t0 + int(round(rel * d_true))] = 1
+    out = run_gpu(x, md, f0, df, sentinel=0.0)
+    r, t = np.unravel_index(np.argmax(out), out.shape)
+    assert abs(r - d_true) <= 1 and abs(t - t0) <= 1
+    assert out[r, t] > 0.5 * nchan
+    x2 = np.roll(x, 1000, axis=1)
+    out2 = run_gpu(x2, md, f0, df, sentinel=0.0)
+    np.testing.assert_array_equal(out2[:, 2000:ntime - md], out[:, 1000:ntime - md - 1000])
+
+
+@pytest.mark.gpu
+def test_status_codes():
+    from bifrost_b200.libbifrost import _bf
+    plan = Fdmt()
+    plan.init(16, 8, 1000., 10.)
+    bad_in = bf.empty((15, 64), dtype='f32', space='cuda')
+    out = bf.empty((8, 64), dtype='f32', space='cuda')
+    assert _bf.bfFdmtExecute(plan.obj, bad_in.as_BFarray(), out.as_BFarray(), 0, None, None) == \
+        _bf.BF_STATUS_INVALID_SHAPE
+    good_in = bf.empty((16, 64), dtype='f32', space='cuda')
+    small = _bf.BFsize(16)
+    ws = bf.empty((16,), dtype='u8', space='cuda')
+    assert _bf.bfFdmtExecute(plan.obj, good_in.as_BFarray(), out.as_BFarray(), 0,
+                             ws.ctypes.data, ctypes.byref(small)) == \
+        _bf.BF_STATUS_INSUFFICIENT_STORAGE
+    host_in = bf.empty((16, 64), dtype='f32', space='system')
+    assert _bf.bfFdmtExecute(plan.obj, host_in.as_BFarray(), out.as_BFarray(), 0, None, None) == \
+        _bf.BF_STATUS_UNSUPPORTED_SPACE
