@@ -56,11 +56,13 @@ def make_input(w, seed, ntime=None):
     rng = np.random.default_rng(seed)
     x = np.empty((w['nchan'], ntime), np.int8)
     step = 256
-    for c0 in range(0, w['nchan'], step):
-        blk = rng.normal(0, 20, size=(step, ntime)).astype(np.float32)
-        np.rint(blk, out=blk)
-        np.clip(blk, -127, 127, out=blk)
-        x[c0:c0 + step] = blk.astype(np.int8)
+    blk = rng.normal(0, 20, size=(step, ntime)).astype(np.float32)
+    np.rint(blk, out=blk)
+    np.clip(blk, -127, 127, out=blk)
+    blk = blk.astype(np.int8)
+    for i, c0 in enumerate(range(0, w['nchan'], step)):
+        # one noise block reused with a different cyclic time shift per block
+        x[c0:c0 + step] = np.roll(blk, 7919 * i, axis=1)[:min(step, w['nchan'] - c0)]
     f = w['f0'] + w['df'] * np.arange(w['nchan'])
     fmax = f[-1]
     rel = (f ** -2 - fmax ** -2) / (f[0] ** -2 - fmax ** -2)
@@ -193,6 +195,11 @@ def run_reference_arm(args, rank, world):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def log(*a):
+    if os.environ.get('BENCH_VERBOSE'):
+        print('[bench]', *a, file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -223,6 +230,7 @@ def main():
     stream = torch.cuda.current_stream()
     bf.device.set_stream(stream.cuda_stream)
 
+    log('torch/bf imported, device set')
     w = workload(rank)
     nchan, ntime, md = w['nchan'], w['ntime'], w['max_delay']
     x_host = make_input(w, 1234 + rank)
@@ -233,6 +241,7 @@ def main():
     d_out = bf.empty((md, ntime), dtype='f32', space='cuda')
     bf.copy_array(d_in, pinned_in)
     bf.memset_array(d_out, 0)
+    log('buffers ready')
     plan = Fdmt()
     plan.init(nchan, md, w['f0'], w['df'])
     ws_size = plan.get_workspace_size(d_in, d_out)
@@ -273,13 +282,16 @@ def main():
             ms = float(t.item())
         return ms, launches, clocks
 
+    log('workspace', ws_size)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_total, launches, clocks = timed(step_resident, args.warmup, args.steps, sampler)
     ms_step = ms_total / args.steps
+    log('resident ms/step', ms_step)
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e_total, _, _ = timed(step_e2e, 2, e2e_steps)
     ms_e2e = ms_e2e_total / e2e_steps
 
+    log('e2e ms/step', ms_e2e)
     samples_per_step = nchan * NTIME_OUT * world            # pol not counted
     value = samples_per_step / (ms_step * 1e-3) / 1e6
     e2e_value = samples_per_step / (ms_e2e * 1e-3) / 1e6

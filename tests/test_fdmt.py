@@ -127,7 +127,7 @@ def test_gpu_matches_reference_library():
         pytest.skip("oracle/_ref/libbifrost_ref.so not present")
     from bifrost_b200.libbifrost import _check
     rng = np.random.default_rng(7)
-    for (ntime, nchan, md, dtype) in [(2000, 256, 300, np.float32), (1500, 100, 64, np.int8),
+    for (ntime, nchan, md, dtype) in [(2000, 256, 301, np.float32), (1500, 100, 64, np.int8),
                                      (4096, 512, 130, np.int8), (333, 17, 40, np.uint16)]:
         if dtype == np.float32:
             x = rng.normal(size=(nchan, ntime)).astype(np.float32)
@@ -193,6 +193,16 @@ def test_large_gulp_properties():
     x2 = np.roll(x, 1000, axis=1)
     out2 = run_gpu(x2, md, f0, df, sentinel=0.0)
     np.testing.assert_array_equal(out2[:, 2000:ntime - md], out[:, 1000:ntime - md - 1000])
+
+
+def test_plan_that_leaves_its_parent_band_is_rejected():
+    """nchan=256, max_delay=300 at 1000-1400 MHz makes a source row index fall
+    outside its parent band (step 7); the reference hits assert() and aborts
+    (src/fdmt.cu:513-514).  Here it is a status, not a crash."""
+    from bifrost_b200.libbifrost import _bf
+    n = ctypes.c_int()
+    assert _bf.bfFdmtPlanQuery(256, 300, 1000., 400. / 256, -2.0, -1, ctypes.byref(n), None) == \
+        _bf.BF_STATUS_INTERNAL_ERROR
 
 
 @pytest.mark.gpu

@@ -120,6 +120,7 @@ def test_errors():
     assert _bf.bfTranspose(a.as_BFarray(), b.as_BFarray(), axes) == _bf.BF_STATUS_INVALID_SHAPE
     c = bf.empty((6, 4), dtype='i32', space='cuda')
     assert _bf.bfTranspose(a.as_BFarray(), c.as_BFarray(), axes) == _bf.BF_STATUS_INVALID_DTYPE
-    d = bf.empty((6, 4), dtype='f32', space='cuda')
+    e = bf.empty((5, 5), dtype='f32', space='cuda')
+    d = bf.empty((5, 5), dtype='f32', space='cuda')
     bad = (ctypes.c_int * 2)(0, 0)
-    assert _bf.bfTranspose(a.as_BFarray(), d.as_BFarray(), bad) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert _bf.bfTranspose(e.as_BFarray(), d.as_BFarray(), bad) == _bf.BF_STATUS_INVALID_ARGUMENT
