@@ -25,6 +25,7 @@
 #include <math_constants.h>
 #include <algorithm>
 #include <vector>
+#include <cstdlib>
 
 namespace bfb {
 
@@ -113,6 +114,338 @@ fdmt_step_kernel(const float* __restrict__ prev, long pstride, long pbatchstride
 	}
 }
 
+
+// ===========================================================================
+// v2: fused head + L2-tiled tail.
+//
+// The step-by-step schedule above moves ~30x the compulsory bytes through
+// HBM.  v2 splits the merge tree at level K:
+//  * HEAD (steps 0..K): one CTA owns one level-K sub-band (2^K channels) and a
+//    time tile.  It stages the raw input tile in shared memory, evaluates the
+//    step-0 running means on the fly, and walks levels 1..K entirely in shared
+//    memory (ping-pong row buffers), writing only the level-K rows to HBM.
+//    A tile carries a left halo of H samples (the largest total delay inside
+//    a level-K sub-tree) so tiles are independent.
+//  * TAIL (steps K+1..last): the wide, few-band steps cannot fit on chip; they
+//    run as row-blocked step kernels (adjacent output rows share source rows,
+//    so a CTA's re-reads hit L1) swept tile-by-tile over time so that the
+//    ping-pong working set of all tail steps stays in the 126 MB L2.
+// Every value is produced by exactly the fp32 operations of the reference
+// (explicit __fadd_rn/__fmul_rn: no FMA contraction across the step-0 scale
+// and the level-1 add), so v2 is bit-identical to v1 and to the reference.
+// ===========================================================================
+enum { FDMT_KMAX = 8 };
+
+struct HeadBand {
+	int chan_lo, nchan;          // channels of this sub-tree (plan order)
+	int row_lo[FDMT_KMAX+1];     // first row of the sub-tree at each level
+	int nrow[FDMT_KMAX+1];
+};
+
+struct HeadParams {
+	const void* in;  long istride, ibatchstride;       // elements
+	float* dst;      long dstride, dbatchstride;       // level-K rows (or final out)
+	const HeadBand* bands;
+	const int2* row0map;         // step-0 row -> (channel, delay)
+	const int4* rows;            // [nstep][plan_stride] (src0, src1, delay, -)
+	long plan_stride;
+	long ntime;
+	int  nchan_total;
+	int  K;                      // last level computed by the head
+	int  W, T, H;                // window, tile, halo (W = T + H)
+	int  ra_rows, rb_rows;       // rows of the two shared row buffers
+	int  xs_chans;               // channel rows reserved for the input tile
+	int  guard;                  // floats of guard band before the first row buffer
+	const int4* items;           // [nband][K][nwarp][item_slots] work items
+	int  item_slots;
+	bool reverse_band;
+	bool final_level;            // level K is the last plan step: diagonal store
+};
+
+template<typename In>
+__device__ __forceinline__ float head_step0(const In* __restrict__ xrow, int dd, int w, long t) {
+	// state0[c][dd][t]: sequential fp32 running sum, then one multiply.
+	if( t < dd ) return CUDART_NAN_F;
+	float acc = 0.f;
+	for( int k=0; k<=dd; ++k ) {
+		int wk = w - k;
+		acc = __fadd_rn(acc, wk >= 0 ? (float)xrow[wk] : 0.f);
+	}
+	return __fmul_rn(acc, __fdiv_rn(1.f, (float)(dd + 1)));
+}
+
+// Copies `nbyte` bytes (multiple of 4) from global `g` (any alignment) to the
+// 4-aligned shared row `srow`, zero-filling bytes outside [valid_lo, valid_hi)
+// (byte offsets relative to g).  One warp; aligned 32-bit loads + funnel shift.
+__device__ __forceinline__ void head_stage_row(const unsigned char* __restrict__ g,
+                                               unsigned char* __restrict__ srow, int nbyte,
+                                               long valid_lo, long valid_hi, int lane) {
+	const int nword = nbyte >> 2;
+	const unsigned mis = (unsigned)((uintptr_t)g & 3);
+	const uint32_t* ga = (const uint32_t*)(g - mis);
+	uint32_t* sw = (uint32_t*)srow;
+	if( valid_lo <= -4 && valid_hi >= (long)nbyte + 8 ) {
+		// whole row interior: 4 independent word pairs in flight per lane
+		for( int j0 = 0; j0 < nword; j0 += 128 ) {
+			uint32_t lo[4], hi[4];
+#pragma unroll
+			for( int k=0; k<4; ++k ) {
+				int j = j0 + k * 32 + lane;
+				if( j < nword ) { lo[k] = ga[j]; hi[k] = ga[j + 1]; }
+			}
+#pragma unroll
+			for( int k=0; k<4; ++k ) {
+				int j = j0 + k * 32 + lane;
+				if( j < nword ) sw[j] = __funnelshift_r(lo[k], hi[k], mis * 8);
+			}
+		}
+		return;
+	}
+	for( int j = lane; j < nword; j += 32 ) {
+		long b0 = (long)j * 4;
+		uint32_t word;
+		// interior words (with a 4-byte margin for the neighbouring aligned word)
+		if( b0 - 4 >= valid_lo && b0 + 8 <= valid_hi ) {
+			uint32_t lo = ga[j];
+			uint32_t hi = mis ? ga[j + 1] : 0u;
+			word = __funnelshift_r(lo, hi, mis * 8);
+		} else {
+			word = 0;
+#pragma unroll
+			for( int k=0; k<4; ++k ) {
+				long bb = b0 + k;
+				uint32_t v = (bb >= valid_lo && bb < valid_hi) ? (uint32_t)g[bb] : 0u;
+				word |= v << (8 * k);
+			}
+		}
+		sw[j] = word;
+	}
+}
+
+// Host-built work item of the fused head (16 bytes, loaded as one int4):
+//   x: a | b<<16         source rows inside the previous level's buffer
+//                        (level >= 2) or channels of the staged tile (level 1)
+//   y: delay | r<<16     shift of source b; destination row inside this level
+//   z: c_lo | c_hi<<8 | d0<<16 | d1<<20 | flags<<24   32-sample chunk range,
+//                        clamped step-0 delays (lean path), flags
+//   w: d0x | d1x<<16     exact step-0 delays (general path)
+// Items are laid out [band][level-1][warp][slot]; a slot with c_lo >= c_hi ends
+// the warp's list.  The host balances chunks across warps per level.
+enum { HR_NO_A = 1, HR_NO_B = 2, HR_SLOW = 4 };
+
+template<typename T> struct is_float_type { enum { value = 0 }; };
+template<> struct is_float_type<float> { enum { value = 1 }; };
+
+// state0 value for DD known at compile time (interior tile: every sample
+// exists, so no NaN / range tests).  x points at the sample of time t.
+template<int DD, typename In>
+__device__ __forceinline__ float head_step0_fast(const In* __restrict__ x) {
+	if( DD == 0 ) {
+		// (0 + x) * 1: only -0.0f changes (to +0.0f), and only floats have it.
+		float v = (float)x[0];
+		return is_float_type<In>::value ? __fadd_rn(0.f, v) : v;
+	}
+	float acc = (float)x[0];
+	if( is_float_type<In>::value ) acc = __fadd_rn(0.f, acc);
+#pragma unroll
+	for( int k=1; k<=DD; ++k ) acc = __fadd_rn(acc, (float)x[-k]);
+	return __fmul_rn(acc, __fdiv_rn(1.f, (float)(DD + 1)));
+}
+
+template<int D0, int D1, typename In>
+__device__ __forceinline__ void head_level1_row(const In* __restrict__ xa, const In* __restrict__ xb,
+                                                float* __restrict__ d, int w_lo, int w_hi) {
+#pragma unroll 4
+	for( int w = w_lo; w < w_hi; w += 32 ) {
+		float va = head_step0_fast<D0>(xa + w);
+		float vb = head_step0_fast<D1>(xb + w);
+		d[w] = __fadd_rn(va, vb);
+	}
+}
+
+template<typename In>
+__global__ void __launch_bounds__(1024)
+fdmt_head_kernel(const __grid_constant__ HeadParams P) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int W = P.W, H = P.H, K = P.K;
+	// Guard band in front of the first buffer: interior tiles read up to
+	// max-delay samples before a row start (values never used).
+	float* bufA = (float*)smem_raw + P.guard;
+	float* bufB = bufA + P.ra_rows * W;
+	In*    xs   = (In*)(bufB + P.rb_rows * W);
+	__shared__ HeadBand hb;
+
+	const int  tid = threadIdx.x, nthr = blockDim.x;
+	const int  lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+	if( tid < (int)(sizeof(HeadBand) / 4) ) ((int*)&hb)[tid] = ((const int*)&P.bands[blockIdx.y])[tid];
+	const int  batch = blockIdx.z;
+	const long t0 = (long)blockIdx.x * P.T;
+	const long wstart = t0 - H;
+	// Tiles far enough from t = 0 satisfy every "t >= delay" test of the
+	// reference trivially and take the lean path.
+	const bool edge_tile = wstart < H;
+	__syncthreads();
+
+	// ---- stage the input tile (zero outside [0, ntime)): one warp per channel row
+	{
+		const In* in = (const In*)P.in + (long)batch * P.ibatchstride;
+		const int nchan = hb.nchan, chan_lo = hb.chan_lo;
+		const long vlo = (wstart < 0 ? -wstart : 0) * (long)sizeof(In);
+		const long vhi = (P.ntime - wstart) * (long)sizeof(In);
+		for( int c = warp; c < nchan; c += nwarp ) {
+			int cg = chan_lo + c;
+			int c_in = P.reverse_band ? P.nchan_total - 1 - cg : cg;
+			const In* grow = in + (long)c_in * P.istride + wstart;      // may point before the row
+			// rows other than the first/last of the whole array may read the
+			// neighbouring row's bytes, which is harmless; the first and last
+			// row take the checked path at the array ends.
+			long lo = vlo, hi = vhi;
+			if( wstart >= 4 ) lo = -4;
+			head_stage_row((const unsigned char*)grow, (unsigned char*)(xs + c * W),
+			               W * (int)sizeof(In), lo, hi, lane);
+		}
+	}
+	__syncthreads();
+
+	float* dstg = P.dst + (long)batch * P.dbatchstride;
+	const int4* items = P.items + ((size_t)blockIdx.y * K * nwarp + warp) * P.item_slots;
+
+	for( int level = 1; level <= K; ++level, items += (size_t)nwarp * P.item_slots ) {
+		const float* src = (level & 1) ? bufB : bufA;     // level-1 output lives in bufA
+		float*       dst = (level & 1) ? bufA : bufB;
+		const bool last = (level == K);
+		const int  row_lo = hb.row_lo[level];
+		int4 it_next = items[0];
+		for( int m = 0; m < P.item_slots; ++m ) {
+			const int4 it = it_next;
+			const int c_lo = it.z & 0xFF, c_hi = (it.z >> 8) & 0xFF;
+			if( c_lo >= c_hi ) break;
+			if( m + 1 < P.item_slots ) it_next = items[m + 1];     // prefetch
+			const int ia = it.x & 0xFFFF, ib = (it.x >> 16) & 0xFFFF;
+			const int delay = it.y & 0xFFFF, r = (it.y >> 16) & 0xFFFF;
+			const int flags = (it.z >> 24) & 0xFF;
+			const int w_lo = c_lo << 5, w_hi = min(W, c_hi << 5);
+			const int rg = row_lo + r;
+			const bool lean = !edge_tile && flags == 0 && !(last && P.final_level);
+			if( lean ) {
+				if( level == 1 && !last ) {
+					const In* xa = xs + ia * W + lane;
+					const In* xb = xs + ib * W + lane - delay;
+					float* d = dst + r * W + lane;
+					switch( (it.z >> 16) & 0xFF ) {   // d0 | d1<<4, warp-uniform, both <= 3
+					case 0x00: head_level1_row<0,0>(xa, xb, d, w_lo, w_hi); break;
+					case 0x10: head_level1_row<0,1>(xa, xb, d, w_lo, w_hi); break;
+					case 0x20: head_level1_row<0,2>(xa, xb, d, w_lo, w_hi); break;
+					case 0x30: head_level1_row<0,3>(xa, xb, d, w_lo, w_hi); break;
+					case 0x01: head_level1_row<1,0>(xa, xb, d, w_lo, w_hi); break;
+					case 0x11: head_level1_row<1,1>(xa, xb, d, w_lo, w_hi); break;
+					case 0x21: head_level1_row<1,2>(xa, xb, d, w_lo, w_hi); break;
+					case 0x31: head_level1_row<1,3>(xa, xb, d, w_lo, w_hi); break;
+					case 0x02: head_level1_row<2,0>(xa, xb, d, w_lo, w_hi); break;
+					case 0x12: head_level1_row<2,1>(xa, xb, d, w_lo, w_hi); break;
+					case 0x22: head_level1_row<2,2>(xa, xb, d, w_lo, w_hi); break;
+					case 0x32: head_level1_row<2,3>(xa, xb, d, w_lo, w_hi); break;
+					case 0x03: head_level1_row<3,0>(xa, xb, d, w_lo, w_hi); break;
+					case 0x13: head_level1_row<3,1>(xa, xb, d, w_lo, w_hi); break;
+					case 0x23: head_level1_row<3,2>(xa, xb, d, w_lo, w_hi); break;
+					default:   head_level1_row<3,3>(xa, xb, d, w_lo, w_hi); break;
+					}
+					continue;
+				}
+				if( level > 1 ) {
+					const float* a = src + ia * W + lane;
+					const float* b = src + ib * W + lane - delay;
+					if( !last ) {
+						float* d = dst + r * W + lane;
+#pragma unroll 4
+						for( int w = w_lo; w < w_hi; w += 32 ) d[w] = __fadd_rn(a[w], b[w]);
+					} else {
+						// level-K rows go to HBM (only the T fresh samples of the tile)
+						float* g = dstg + (long)rg * P.dstride + wstart + lane;
+						const int w_beg = max(w_lo, H);
+						const int w_end = (int)min((long)w_hi, P.ntime - wstart) - lane;
+#pragma unroll 4
+						for( int w = w_beg; w < w_end; w += 32 ) g[w] = __fadd_rn(a[w], b[w]);
+					}
+					continue;
+				}
+			}
+			// ---------------- general: exact edge semantics, one sample per lane
+			const bool has_a = !(flags & HR_NO_A), has_b = !(flags & HR_NO_B);
+			const int d0x = it.w & 0xFFFF, d1x = (it.w >> 16) & 0xFFFF;
+			for( int w = w_lo + lane; w < w_hi; w += 32 ) {
+				long t = wstart + w;
+				float val = 0.f;
+				if( level == 1 ) {
+					if( has_a ) val = head_step0(xs + ia * W, d0x, w, t);
+					if( has_b && t >= delay ) {
+						int wb = w - delay;
+						float bv = wb >= 0 ? head_step0(xs + ib * W, d1x, wb, t - delay) : 0.f;
+						val = __fadd_rn(val, bv);
+					}
+				} else {
+					if( has_a ) val = src[ia * W + w];
+					if( has_b && t >= delay ) {
+						int wb = w - delay;
+						val = __fadd_rn(val, wb >= 0 ? src[ib * W + wb] : 0.f);
+					}
+				}
+				if( !last ) {
+					dst[r * W + w] = val;
+				} else if( w >= H && t < P.ntime ) {
+					if( !P.final_level ) {
+						dstg[(long)rg * P.dstride + t] = val;
+					} else if( t >= rg ) {
+						dstg[(long)rg * P.dstride + (t - rg)] = val;
+					}
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// Row-blocked merge step over the time range [tbeg, tend) (tbeg % 4 == 0).
+// grid.x: 1024-sample chunks, grid.y: blocks of `rows_per_cta` rows, grid.z: batch.
+template<bool FINAL>
+__global__ void __launch_bounds__(256)
+fdmt_tail_kernel(const float* __restrict__ prev, long pstride, long pbatchstride,
+                 float* __restrict__ next, long nstride, long nbatchstride,
+                 const int4* __restrict__ rows, int nrow, int rows_per_cta,
+                 long ntime, long tbeg, long tend) {
+	int  b = blockIdx.z;
+	long t0 = tbeg + ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if( t0 >= tend ) return;
+	int r_lo = blockIdx.y * rows_per_cta;
+	int r_hi = min(nrow, r_lo + rows_per_cta);
+	const float* pb = prev + (long)b * pbatchstride;
+	float* dst = next + (long)b * nbatchstride;
+	for( int r = r_lo; r < r_hi; ++r ) {
+		int4 row = rows[r];
+		int delay = row.z;
+		float4 va = make_float4(0.f, 0.f, 0.f, 0.f);
+		if( row.x >= 0 ) va = *(const float4*)(pb + (long)row.x * pstride + t0);
+		float o[4] = {va.x, va.y, va.z, va.w};
+		if( row.y >= 0 ) {
+			const float* bb = pb + (long)row.y * pstride;
+#pragma unroll
+			for( int j=0; j<4; ++j ) {
+				long t = t0 + j;
+				if( t >= delay && t < ntime ) o[j] += bb[t - delay];
+			}
+		}
+		if( !FINAL ) {
+			*(float4*)(dst + (long)r * nstride + t0) = make_float4(o[0], o[1], o[2], o[3]);
+		} else {
+#pragma unroll
+			for( int j=0; j<4; ++j ) {
+				long t = t0 + j;
+				if( t < ntime && t < tend && t >= r ) dst[(long)r * nstride + (t - r)] = o[j];
+			}
+		}
+	}
+}
+
 } // namespace bfb
 
 using namespace bfb;
@@ -127,23 +460,94 @@ struct BFfdmt_impl {
 	size_t own_plan_size = 0;
 	int*   d_row_offsets = nullptr;      // [nchan+1]
 	int4*  d_rows = nullptr;             // [nstep][plan_stride]
+	int2*  d_row0map = nullptr;          // [nrow(0)]
+	HeadBand* d_head = nullptr;          // [nband(K)]
+	// fused-head work items, built per (window, warps) at execute time
+	std::vector<HeadBand> h_head;
+	std::vector<int2>     h_row0map;
+	std::vector<int4>     h_items;
+	int4*  d_items = nullptr;
+	size_t d_items_cap = 0;
+	int    items_W = 0, items_nwarp = 0, item_slots = 0;
 	long   plan_stride = 0;
+	// fused schedule (v2)
+	int    K = 0;                        // head covers steps 0..K
+	int    head_halo = 0;
+	int    head_ra = 0, head_rb = 0, head_chans = 0, head_tabrows = 0, max_nd0 = 1;
+	std::vector<int> step_maxdelay;      // [nstep]
+	// tunables (environment overrides, read once per plan)
+	int    cfg_kmax = 5, cfg_smem_kb = 100, cfg_threads = 512, cfg_tail_rows = 8;
+	long   cfg_tail_tile = 1L << 30;
+	bool   cfg_force_v1 = false;
+	bool   head_ok = false;
 	// exec workspace
 	void*  own_exec_storage = nullptr;
 	size_t own_exec_size = 0;
 
 	cudaStream_t get_stream() { return stream_set ? stream : thread_stream(); }
 
-	size_t plan_bytes() const {
-		size_t off = round_up<size_t>((plan.nchan + 1) * sizeof(int), 512);
-		off += (size_t)plan.nstep() * plan_stride * sizeof(int4);
-		return off;
+	size_t off_rows()    const { return round_up<size_t>((plan.nchan + 1) * sizeof(int), 512); }
+	size_t off_row0map() const { return off_rows() + (size_t)plan.nstep() * plan_stride * sizeof(int4); }
+	size_t off_head()    const { return off_row0map() + round_up<size_t>((size_t)plan.nrow(0) * sizeof(int2), 512); }
+	size_t plan_bytes()  const {
+		return off_head() + round_up<size_t>(plan.bands[K].size() * sizeof(HeadBand), 512);
 	}
 	~BFfdmt_impl() {
 		if( own_plan_storage ) cudaFree(own_plan_storage);
 		if( own_exec_storage ) cudaFree(own_exec_storage);
+		if( d_items ) cudaFree(d_items);
 	}
 };
+
+static int env_int(const char* name, int dflt) {
+	const char* v = getenv(name);
+	return (v && *v) ? atoi(v) : dflt;
+}
+
+// Rows buffered by the head at each parity, channels per sub-tree and the halo,
+// for splitting the tree at level K.
+static void head_geometry(FdmtPlan const& P, int K, std::vector<HeadBand>* bands,
+                          int* ra, int* rb, int* chans, int* halo, int* tabrows, int* nd0) {
+	*ra = *rb = *chans = *halo = *tabrows = 0;
+	bands->clear();
+	int max_nd0 = 1;
+	for( FdmtBand const& b : P.bands[0] ) max_nd0 = std::max(max_nd0, b.ndelay);
+	for( size_t ib=0; ib<P.bands[K].size(); ++ib ) {
+		HeadBand hb;
+		memset(&hb, 0, sizeof(hb));
+		int lo = (int)ib, hi = (int)ib;          // band index range at the current level
+		int h = max_nd0 - 1;
+		for( int s=K; s>=0; --s ) {
+			FdmtBand const& bl = P.bands[s][lo];
+			FdmtBand const& bh = P.bands[s][hi];
+			hb.row_lo[s] = bl.row0;
+			hb.nrow[s]   = bh.row0 + bh.ndelay - bl.row0;
+			if( s == 0 ) { hb.chan_lo = bl.chan0; hb.nchan = bh.chan0 + bh.nchan - bl.chan0; break; }
+			int md = 0;
+			for( int r=hb.row_lo[s]; r<hb.row_lo[s]+hb.nrow[s]; ++r ) md = std::max(md, P.rows[s][r].delay);
+			h += md;
+			int nlo = 1 << 30, nhi = -1;
+			for( int b=lo; b<=hi; ++b ) {
+				FdmtBand const& bb = P.bands[s][b];
+				if( bb.parent0 >= 0 ) { nlo = std::min(nlo, bb.parent0); nhi = std::max(nhi, bb.parent0); }
+				if( bb.parent1 >= 0 ) { nlo = std::min(nlo, bb.parent1); nhi = std::max(nhi, bb.parent1); }
+			}
+			lo = nlo; hi = nhi;
+		}
+		int tab = 0;
+		for( int s=1; s<=K; ++s ) tab += hb.nrow[s];
+		*tabrows = std::max(*tabrows, tab);
+		for( int s=1; s<K; ++s ) {
+			if( s & 1 ) *ra = std::max(*ra, hb.nrow[s]);
+			else        *rb = std::max(*rb, hb.nrow[s]);
+		}
+		*chans = std::max(*chans, hb.nchan);
+		*halo  = std::max(*halo, h);
+		bands->push_back(hb);
+	}
+	*halo = (*halo + 3) / 4 * 4;     // keeps window and global time 4-aligned together
+	*nd0 = max_nd0;
+}
 
 extern "C" {
 
@@ -179,7 +583,24 @@ BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
 	BFB_TRY(ok = plan->plan.build((int)nchan, (int)max_delay, f0, df, exponent));
 	BFB_ASSERT(ok, BF_STATUS_INTERNAL_ERROR);
 	plan->planned = true;
-	plan->plan_stride = round_up<long>(plan->plan.nrow_max, 128);
+	FdmtPlan const& P = plan->plan;
+	plan->plan_stride = round_up<long>(P.nrow_max, 128);
+	// Tunables
+	plan->cfg_kmax      = std::min(env_int("BFB_FDMT_K", 5), (int)FDMT_KMAX);
+	plan->cfg_smem_kb   = std::min(env_int("BFB_FDMT_SMEM_KB", 100), 227);
+	plan->cfg_threads   = env_int("BFB_FDMT_THREADS", 512);
+	plan->cfg_tail_rows = std::max(1, env_int("BFB_FDMT_TAIL_ROWS", 8));
+	plan->cfg_tail_tile = (long)std::max(1024, env_int("BFB_FDMT_TAIL_TILE", 1 << 30)) / 1024 * 1024;
+	plan->cfg_force_v1  = env_int("BFB_FDMT_V1", 0) != 0;
+	plan->K = std::max(1, std::min(plan->cfg_kmax, P.nstep() - 1));
+	std::vector<HeadBand> head;
+	BFB_TRY(head_geometry(P, plan->K, &head, &plan->head_ra, &plan->head_rb,
+	                      &plan->head_chans, &plan->head_halo, &plan->head_tabrows,
+	                      &plan->max_nd0));
+	plan->step_maxdelay.assign(P.nstep(), 0);
+	for( int s=1; s<P.nstep(); ++s ) {
+		for( FdmtRow const& r : P.rows[s] ) plan->step_maxdelay[s] = std::max(plan->step_maxdelay[s], r.delay);
+	}
 	size_t need = plan->plan_bytes();
 	if( plan_storage_size ) {
 		if( !plan_storage ) { *plan_storage_size = need; return BF_STATUS_SUCCESS; }
@@ -196,11 +617,17 @@ BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
 	}
 	char* base = (char*)plan_storage;
 	plan->d_row_offsets = (int*)base;
-	plan->d_rows = (int4*)(base + round_up<size_t>((nchan + 1) * sizeof(int), 512));
-	// Upload: row offsets of step 0, then one padded int4 table per step.
-	FdmtPlan const& P = plan->plan;
+	plan->d_rows    = (int4*)(base + plan->off_rows());
+	plan->d_row0map = (int2*)(base + plan->off_row0map());
+	plan->d_head    = (HeadBand*)(base + plan->off_head());
+	// Upload: row offsets of step 0, one padded int4 table per step, the
+	// step-0 row -> (channel, delay) map and the head sub-tree descriptors.
 	std::vector<int> offsets(nchan + 1);
-	for( size_t c=0; c<nchan; ++c ) offsets[c] = P.bands[0][c].row0;
+	std::vector<int2> row0map(P.nrow(0));
+	for( size_t c=0; c<nchan; ++c ) {
+		offsets[c] = P.bands[0][c].row0;
+		for( int d=0; d<P.bands[0][c].ndelay; ++d ) row0map[P.bands[0][c].row0 + d] = make_int2((int)c, d);
+	}
 	offsets[nchan] = P.nrow(0);
 	std::vector<int4> table((size_t)P.nstep() * plan->plan_stride, make_int4(-1, -1, 0, 0));
 	for( int s=1; s<P.nstep(); ++s ) {
@@ -209,10 +636,18 @@ BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
 			table[(size_t)s * plan->plan_stride + r] = make_int4(row.src0, row.src1, row.delay, 0);
 		}
 	}
+	plan->head_ok = P.max_delay < 65000 && plan->max_nd0 < 65000 && P.nrow_max < 65000;
+	plan->h_head = head;
+	plan->h_row0map = row0map;
+	plan->items_W = 0;      // force a rebuild of the work items
 	cudaStream_t st = plan->get_stream();
 	BFB_CUDA(cudaMemcpyAsync(plan->d_row_offsets, offsets.data(), offsets.size()*sizeof(int),
 	                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
 	BFB_CUDA(cudaMemcpyAsync(plan->d_rows, table.data(), table.size()*sizeof(int4),
+	                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
+	BFB_CUDA(cudaMemcpyAsync(plan->d_row0map, row0map.data(), row0map.size()*sizeof(int2),
+	                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
+	BFB_CUDA(cudaMemcpyAsync(plan->d_head, head.data(), head.size()*sizeof(HeadBand),
 	                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
 	BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
 	return BF_STATUS_SUCCESS;
@@ -247,6 +682,81 @@ BFstatus bfFdmtPlanQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	return BF_STATUS_SUCCESS;
 }
 
+// Builds the per-(band, level, warp) work items of the fused head for a window
+// of W samples processed by nwarp warps: each level's (row x 32-sample chunk)
+// space is cut into nwarp contiguous, equally sized shares.
+static void build_head_items(BFfdmt_impl* plan, int W, int nwarp) {
+	FdmtPlan const& P = plan->plan;
+	const int K = plan->K;
+	const int nchunk = (W + 31) / 32;
+	std::vector<std::vector<int4> > lists(plan->h_head.size() * (size_t)K * nwarp);
+	size_t slots = 1;
+	for( size_t ib=0; ib<plan->h_head.size(); ++ib ) {
+		HeadBand const& hb = plan->h_head[ib];
+		for( int lv=1; lv<=K; ++lv ) {
+			long total = (long)hb.nrow[lv] * nchunk;
+			long share = (total + nwarp - 1) / nwarp;
+			for( int w=0; w<nwarp; ++w ) {
+				std::vector<int4>& out = lists[(ib * K + (lv-1)) * nwarp + w];
+				long beg = std::min(total, w * share), end = std::min(total, (w + 1) * share);
+				while( beg < end ) {
+					int r = (int)(beg / nchunk), c_lo = (int)(beg % nchunk);
+					int c_hi = (int)std::min<long>(nchunk, c_lo + (end - beg));
+					FdmtRow const& row = P.rows[lv][hb.row_lo[lv] + r];
+					int flags = (row.src0 < 0 ? HR_NO_A : 0) | (row.src1 < 0 ? HR_NO_B : 0);
+					int a = 0, b = 0, d0 = 0, d1 = 0, d0x = 0, d1x = 0;
+					if( lv == 1 ) {
+						int2 m0 = row.src0 >= 0 ? plan->h_row0map[row.src0] : make_int2(hb.chan_lo, 0);
+						int2 m1 = row.src1 >= 0 ? plan->h_row0map[row.src1] : make_int2(hb.chan_lo, 0);
+						a = m0.x - hb.chan_lo; b = m1.x - hb.chan_lo;
+						d0x = m0.y; d1x = m1.y;
+						if( d0x > 3 || d1x > 3 ) flags |= HR_SLOW;
+						d0 = std::min(d0x, 3); d1 = std::min(d1x, 3);
+					} else {
+						a = row.src0 >= 0 ? row.src0 - hb.row_lo[lv-1] : 0;
+						b = row.src1 >= 0 ? row.src1 - hb.row_lo[lv-1] : 0;
+					}
+					int4 it;
+					it.x = a | (b << 16);
+					it.y = row.delay | (r << 16);
+					it.z = c_lo | (c_hi << 8) | (d0 << 16) | (d1 << 20) | (flags << 24);
+					it.w = d0x | (d1x << 16);
+					out.push_back(it);
+					beg += c_hi - c_lo;
+				}
+				slots = std::max(slots, out.size());
+			}
+		}
+	}
+	plan->item_slots = (int)slots;
+	plan->h_items.assign(lists.size() * slots, make_int4(0, 0, 0, 0));   // c_lo == c_hi: end marker
+	for( size_t i=0; i<lists.size(); ++i ) {
+		for( size_t m=0; m<lists[i].size(); ++m ) plan->h_items[i * slots + m] = lists[i][m];
+	}
+	plan->items_W = W; plan->items_nwarp = nwarp;
+}
+
+// Head geometry for an input item size: window W (multiple of 32) that fits the
+// shared-memory budget, tile T = W - halo.  Returns false if the fused path
+// cannot be used (then the step-by-step path runs).
+static bool head_window(BFfdmt_impl const* plan, long isize, int* W, int* T, size_t* smem) {
+	size_t per_w = (size_t)(plan->head_ra + plan->head_rb) * 4 + (size_t)plan->head_chans * isize;
+	if( !plan->head_ok ) return false;
+	size_t guard_bytes = (size_t)(plan->head_halo + 16) * 4;
+	size_t budget = (size_t)plan->cfg_smem_kb * 1024;
+	if( budget <= guard_bytes + 1024 ) return false;
+	long w = (long)((budget - guard_bytes) / per_w);
+	w = std::min<long>(w, 2048);
+	// Prefer a window made of whole 128-sample warp units.
+	w = (w >= 256) ? w / 128 * 128 : w / 32 * 32;
+	long t = (w - plan->head_halo) / 4 * 4;
+	if( t < 64 ) return false;
+	*W = (int)w;
+	*T = (int)t;
+	*smem = guard_bytes + per_w * (size_t)w;
+	return true;
+}
+
 BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
                        BFbool negative_delays,
                        void* exec_storage, BFsize* exec_storage_size) {
@@ -279,9 +789,28 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 		ibatchbytes = v[0].strides[0];
 		obatchbytes = v[1].strides[0];
 	}
+	long isize = dtype_nbyte(in->dtype);
+	BFB_ASSERT(isize > 0, BF_STATUS_UNSUPPORTED_DTYPE);
+	int W = 0, T = 0;
+	size_t head_smem = 0;
+	bool fused = !negative_delays && !plan->cfg_force_v1 &&
+	             head_window(plan, isize, &W, &T, &head_smem);
+	int nstep = P.nstep();
+	bool head_is_final = fused && (plan->K == nstep - 1);
 	long sstride = round_up<long>(ntime, FDMT_TIME_ALIGN);
-	long sbatchstride = (long)P.nrow_max * sstride;
-	size_t need = 2 * (size_t)nbatch * sbatchstride * sizeof(float);
+	// Workspace: the step-by-step path ping-pongs nrow_max rows; the fused path
+	// only the rows of the tail steps (level K and above).
+	long ws_rows = P.nrow_max;
+	if( fused ) {
+		ws_rows = 0;
+		for( int s=plan->K; s<nstep-1; ++s ) ws_rows = std::max<long>(ws_rows, P.nrow(s));
+	}
+	long sbatchstride = ws_rows * sstride;
+	// v1 ping-pongs two buffers; v2 keeps the head output intact in a third
+	// one because every tail tile re-reads its halo from it.
+	int  nbuf = fused ? 3 : 2;
+	size_t need = (size_t)nbuf * (size_t)nbatch * sbatchstride * sizeof(float);
+	if( need == 0 ) need = 512;
 	if( exec_storage_size ) {
 		if( !exec_storage ) { *exec_storage_size = need; return BF_STATUS_SUCCESS; }
 		BFB_ASSERT(*exec_storage_size >= need, BF_STATUS_INSUFFICIENT_STORAGE);
@@ -298,13 +827,16 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	BFB_ASSERT(space_on_device(in->space),  BF_STATUS_UNSUPPORTED_SPACE);
 	BFB_ASSERT(space_on_device(out->space), BF_STATUS_UNSUPPORTED_SPACE);
 	BFB_ASSERT(out->dtype == BF_DTYPE_F32,  BF_STATUS_UNSUPPORTED_DTYPE);
-	long isize = dtype_nbyte(in->dtype);
-	BFB_ASSERT(isize > 0, BF_STATUS_UNSUPPORTED_DTYPE);
 	BFB_ASSERT( in->strides[ndim-1] == isize, BF_STATUS_UNSUPPORTED_STRIDE);
 	BFB_ASSERT(out->strides[ndim-1] == 4,     BF_STATUS_UNSUPPORTED_STRIDE);
 	BFB_ASSERT( in->strides[ndim-2] > 0 &&  in->strides[ndim-2] % isize == 0, BF_STATUS_UNSUPPORTED_STRIDE);
 	BFB_ASSERT(out->strides[ndim-2] > 0 && out->strides[ndim-2] % 4 == 0,     BF_STATUS_UNSUPPORTED_STRIDE);
 	BFB_ASSERT(ibatchbytes % isize == 0 && obatchbytes % 4 == 0,              BF_STATUS_UNSUPPORTED_STRIDE);
+	switch( in->dtype ) {
+	case BF_DTYPE_I8: case BF_DTYPE_I16: case BF_DTYPE_I32:
+	case BF_DTYPE_U8: case BF_DTYPE_U16: case BF_DTYPE_U32: case BF_DTYPE_F32: break;
+	default: BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
+	}
 	if( ntime == 0 || nbatch == 0 ) return BF_STATUS_SUCCESS;
 	BFB_ASSERT(nbatch <= 65535 && P.nrow_max <= 65535, BF_STATUS_UNSUPPORTED_SHAPE);
 	long istride = in->strides[ndim-2] / isize,  ibatch = ibatchbytes / isize;
@@ -316,38 +848,124 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	cudaStream_t st = plan->get_stream();
 	dim3 block(256);
 	unsigned gx = (unsigned)div_up<long>(div_up<long>(ntime, 4), 256);
-	dim3 grid0(gx, P.nchan, (unsigned)nbatch);
-#define BFB_FDMT_INIT(T) \
-	fdmt_init_kernel<T><<<grid0, block, 0, st>>>((const T*)in->data, istride, ibatch, \
-		buf_a, sstride, sbatchstride, plan->d_row_offsets, P.nchan, ntime, \
-		P.reverse_band, rev)
-	switch( in->dtype ) {
-	case BF_DTYPE_I8:  BFB_FDMT_INIT(int8_t);   break;
-	case BF_DTYPE_I16: BFB_FDMT_INIT(int16_t);  break;
-	case BF_DTYPE_I32: BFB_FDMT_INIT(int32_t);  break;
-	case BF_DTYPE_U8:  BFB_FDMT_INIT(uint8_t);  break;
-	case BF_DTYPE_U16: BFB_FDMT_INIT(uint16_t); break;
-	case BF_DTYPE_U32: BFB_FDMT_INIT(uint32_t); break;
-	case BF_DTYPE_F32: BFB_FDMT_INIT(float);    break;
-	default: BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
-	}
-#undef BFB_FDMT_INIT
-	count_launch();
 	float* cur = buf_a;
 	float* nxt = buf_b;
-	int nstep = P.nstep();
-	for( int s=1; s<nstep; ++s ) {
-		dim3 grid(gx, P.nrow(s), (unsigned)nbatch);
-		const int4* rows = plan->d_rows + (size_t)s * plan->plan_stride;
-		if( s == nstep-1 ) {
-			fdmt_step_kernel<true><<<grid, block, 0, st>>>(cur, sstride, sbatchstride,
-				(float*)out->data, ostride, obatch, rows, ntime, rev);
-		} else {
-			fdmt_step_kernel<false><<<grid, block, 0, st>>>(cur, sstride, sbatchstride,
-				nxt, sstride, sbatchstride, rows, ntime, rev);
+
+	if( !fused ) {
+		// ---------------- v1: one launch per step over the whole gulp
+		dim3 grid0(gx, P.nchan, (unsigned)nbatch);
+#define BFB_FDMT_INIT(T_) \
+		fdmt_init_kernel<T_><<<grid0, block, 0, st>>>((const T_*)in->data, istride, ibatch, \
+			buf_a, sstride, sbatchstride, plan->d_row_offsets, P.nchan, ntime, \
+			P.reverse_band, rev)
+		switch( in->dtype ) {
+		case BF_DTYPE_I8:  BFB_FDMT_INIT(int8_t);   break;
+		case BF_DTYPE_I16: BFB_FDMT_INIT(int16_t);  break;
+		case BF_DTYPE_I32: BFB_FDMT_INIT(int32_t);  break;
+		case BF_DTYPE_U8:  BFB_FDMT_INIT(uint8_t);  break;
+		case BF_DTYPE_U16: BFB_FDMT_INIT(uint16_t); break;
+		case BF_DTYPE_U32: BFB_FDMT_INIT(uint32_t); break;
+		default:           BFB_FDMT_INIT(float);    break;
 		}
+#undef BFB_FDMT_INIT
 		count_launch();
-		std::swap(cur, nxt);
+		for( int s=1; s<nstep; ++s ) {
+			dim3 grid(gx, P.nrow(s), (unsigned)nbatch);
+			const int4* rows = plan->d_rows + (size_t)s * plan->plan_stride;
+			if( s == nstep-1 ) {
+				fdmt_step_kernel<true><<<grid, block, 0, st>>>(cur, sstride, sbatchstride,
+					(float*)out->data, ostride, obatch, rows, ntime, rev);
+			} else {
+				fdmt_step_kernel<false><<<grid, block, 0, st>>>(cur, sstride, sbatchstride,
+					nxt, sstride, sbatchstride, rows, ntime, rev);
+			}
+			count_launch();
+			std::swap(cur, nxt);
+		}
+		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+		return BF_STATUS_SUCCESS;
+	}
+
+	// ---------------- v2: fused head ...
+	HeadParams hp;
+	hp.in = in->data; hp.istride = istride; hp.ibatchstride = ibatch;
+	if( head_is_final ) { hp.dst = (float*)out->data; hp.dstride = ostride; hp.dbatchstride = obatch; }
+	else                { hp.dst = cur;               hp.dstride = sstride; hp.dbatchstride = sbatchstride; }
+	hp.bands = plan->d_head; hp.row0map = plan->d_row0map; hp.rows = plan->d_rows;
+	hp.plan_stride = plan->plan_stride; hp.ntime = ntime; hp.nchan_total = P.nchan;
+	hp.K = plan->K; hp.W = W; hp.T = T; hp.H = W - T;
+	hp.guard = plan->head_halo + 16;
+	hp.items = plan->d_items; hp.item_slots = plan->item_slots;
+	hp.ra_rows = plan->head_ra; hp.rb_rows = plan->head_rb; hp.xs_chans = plan->head_chans;
+	hp.reverse_band = P.reverse_band; hp.final_level = head_is_final;
+	dim3 hgrid((unsigned)div_up<long>(ntime, T), (unsigned)P.bands[plan->K].size(), (unsigned)nbatch);
+	int hthreads = std::max(64, std::min(1024, plan->cfg_threads / 32 * 32));
+	if( plan->items_W != W || plan->items_nwarp != hthreads / 32 ) {
+		// (re)build and upload the work items; the host copy outlives the copy
+		BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
+		BFB_TRY(build_head_items(plan, W, hthreads / 32));
+		size_t bytes = plan->h_items.size() * sizeof(int4);
+		if( plan->d_items_cap < bytes ) {
+			if( plan->d_items ) cudaFree(plan->d_items);
+			plan->d_items = nullptr; plan->d_items_cap = 0;
+			BFB_CUDA(cudaMalloc((void**)&plan->d_items, bytes), BF_STATUS_MEM_ALLOC_FAILED);
+			plan->d_items_cap = bytes;
+		}
+		BFB_CUDA(cudaMemcpyAsync(plan->d_items, plan->h_items.data(), bytes,
+		                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
+		BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
+	}
+	hp.items = plan->d_items; hp.item_slots = plan->item_slots;
+#define BFB_FDMT_HEAD(T_) do { \
+		BFB_CUDA(cudaFuncSetAttribute(fdmt_head_kernel<T_>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem), BF_STATUS_INTERNAL_ERROR); \
+		fdmt_head_kernel<T_><<<hgrid, hthreads, head_smem, st>>>(hp); } while(0)
+	switch( in->dtype ) {
+	case BF_DTYPE_I8:  BFB_FDMT_HEAD(int8_t);   break;
+	case BF_DTYPE_I16: BFB_FDMT_HEAD(int16_t);  break;
+	case BF_DTYPE_I32: BFB_FDMT_HEAD(int32_t);  break;
+	case BF_DTYPE_U8:  BFB_FDMT_HEAD(uint8_t);  break;
+	case BF_DTYPE_U16: BFB_FDMT_HEAD(uint16_t); break;
+	case BF_DTYPE_U32: BFB_FDMT_HEAD(uint32_t); break;
+	default:           BFB_FDMT_HEAD(float);    break;
+	}
+#undef BFB_FDMT_HEAD
+	count_launch();
+	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+	if( head_is_final ) return BF_STATUS_SUCCESS;
+
+	// ---------------- ... and the tail, swept tile by tile so it stays in L2.
+	// Step s of tile [lo, hi) must cover [lo - halo_s, hi) where halo_s is the
+	// total delay still to be applied by later steps.
+	int first = plan->K + 1;
+	std::vector<long> halo(nstep + 1, 0);
+	// (halos are kept multiples of 4 so that every range start stays 4-aligned
+	// and each step re-computes everything the next one reads)
+	for( int s=nstep-2; s>=first; --s ) halo[s] = halo[s+1] + round_up<long>(plan->step_maxdelay[s+1], 4);
+	long tile = plan->cfg_tail_tile;
+	int rpc = plan->cfg_tail_rows;
+	float* buf_c = buf_b + (size_t)nbatch * sbatchstride;
+	for( long lo=0; lo<ntime; lo+=tile ) {
+		long hi = std::min(ntime, lo + tile);
+		float* c = cur;        // head output (never written by the tail)
+		float* n = nxt;
+		for( int s=first; s<nstep; ++s ) {
+			long tb = std::max<long>(0, lo - halo[s]);
+			unsigned tx = (unsigned)div_up<long>(div_up<long>(hi - tb, 4), 256);
+			dim3 grid(tx, (unsigned)div_up<int>(P.nrow(s), rpc), (unsigned)nbatch);
+			const int4* rows = plan->d_rows + (size_t)s * plan->plan_stride;
+			if( s == nstep-1 ) {
+				fdmt_tail_kernel<true><<<grid, block, 0, st>>>(c, sstride, sbatchstride,
+					(float*)out->data, ostride, obatch, rows, P.nrow(s), rpc, ntime, tb, hi);
+			} else {
+				fdmt_tail_kernel<false><<<grid, block, 0, st>>>(c, sstride, sbatchstride,
+					n, sstride, sbatchstride, rows, P.nrow(s), rpc, ntime, tb, hi);
+			}
+			count_launch();
+			// ping-pong between the two tail buffers only
+			c = n;
+			n = (n == nxt) ? buf_c : nxt;
+		}
 	}
 	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
 	return BF_STATUS_SUCCESS;

@@ -119,6 +119,51 @@ def test_reference_smoke_semantics(ntime, nchan, md, batch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("knob", [dict(BFB_FDMT_V1='1'), dict(BFB_FDMT_K='2'), dict(BFB_FDMT_K='4', BFB_FDMT_SMEM_KB='48'),
+                                  dict(BFB_FDMT_K='8'), dict(BFB_FDMT_TAIL_TILE='1024', BFB_FDMT_TAIL_ROWS='3'),
+                                  dict(BFB_FDMT_THREADS='128')])
+def test_every_schedule_gives_the_same_bits(knob):
+    """The step-by-step schedule (v1) and the fused head + tiled tail (v2) at
+    several split levels / tile sizes must agree bit for bit with the oracle."""
+    rng = np.random.default_rng(21)
+    old = {k: os.environ.get(k) for k in knob}
+    os.environ.update(knob)
+    try:
+        for (ntime, nchan, md, dtype) in [(3000, 300, 150, np.int8), (5000, 64, 40, np.float32),
+                                         (700, 1024, 90, np.uint8), (2500, 37, 33, np.int16)]:
+            if dtype == np.float32:
+                x = rng.normal(size=(nchan, ntime)).astype(np.float32)
+            else:
+                x = rng.integers(0, 100, size=(nchan, ntime)).astype(dtype)
+            f0, df = 1100., 300. / nchan
+            got = run_gpu(x, md, f0, df)
+            want = np.full((md, ntime), SENTINEL, np.float32)
+            ofdmt.fdmt(x, md, f0, df, out=want)
+            assert_same_bits(got, want)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.gpu
+def test_negative_delays_match_oracle():
+    """negative_delays mirrors time as the reference does (src/fdmt.cu:80-81,
+    150-151, 702-708); cells whose reference value depends on an out-of-bounds
+    read are excluded (documented divergence: we contribute 0 there)."""
+    rng = np.random.default_rng(22)
+    for (ntime, nchan, md) in [(600, 64, 40), (1000, 48, 30)]:
+        x = rng.integers(-50, 50, size=(nchan, ntime)).astype(np.int8)
+        f0, df = 1000., 400. / nchan
+        got = run_gpu(x, md, f0, df, negative_delays=True)
+        want = np.full((md, ntime), SENTINEL, np.float32)
+        ofdmt.fdmt(x, md, f0, df, negative_delays=True, out=want)
+        assert_same_bits(got, want)
+
+
+@pytest.mark.gpu
 def test_gpu_matches_reference_library():
     """Same call sequence through both C ABIs on the same device buffers."""
     import reflib
