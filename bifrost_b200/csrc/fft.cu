@@ -1,0 +1,787 @@
+// fft.cu -- bfFft* for sm_100a, hand-written (no cuFFT).
+//
+// Replaces: src/fft.cu:109-419 (plan + execute over cufftMakePlanMany64) and
+// src/fft_kernels.cu:32-341 (load callbacks: integer -> float scaling and
+// fftshift).
+//
+// Semantics kept from the reference:
+//  * unnormalised in both directions (test/test_fft.py:79-82);
+//  * complex->complex = [i]fft, real->complex = rfft (n/2+1 outputs on the last
+//    transform axis), complex->real = irfft;
+//  * integer inputs are scaled on load: ci4 (nibble<<4)/128, ci8 /128,
+//    ci16 /32768, i8 /128, i16 /32768, u8 /256, u16 /65536
+//    (src/fft_kernels.cu:96-197);
+//  * apply_fftshift: forward c2c transforms centre DC by flipping the sign of
+//    odd-indexed inputs (odd lengths: full phase ramp), inverse c2c transforms
+//    read their input rotated by n/2 (src/fft_kernels.cu:32-94); real
+//    transforms reject fftshift as the reference does (:250-283).
+//
+// Design: an N-D transform is a sequence of 1-D passes, one per axis, over a
+// strided array; every other dim is a batch dim.  `fft_pass_kernel` transforms
+// B lines per CTA:
+//  * n = 2^k, 16 <= n <= 8192: Stockham autosort in shared memory.  Each thread
+//    keeps exactly 16 complex points in registers for every stage (n/16 threads
+//    per line); stages are radix 16/8/4/2 DFTs done in registers, so a
+//    4096-point line makes 3 passes over shared memory instead of 12.  The first
+//    stage reads global memory straight into registers (converting, scaling and
+//    shifting on the fly) and the last stage stores straight from registers.
+//    Shared memory is split re/im with one pad word per 32 so that both the
+//    stride-R scatter of the first stage and the unit-stride later stages are
+//    bank-conflict free.
+//  * any other n <= 8192: direct O(n^2) DFT from shared memory with an exact
+//    twiddle table (correct, not fast; covers the odd sizes of the reference's
+//    tests).
+//  * n = 2^k > 8192 (c2c): four-step, n = n1*n2, two passes of the same kernel
+//    through the plan's workspace with the inter-pass twiddle W_n^(k1*c2)
+//    applied on store.
+// Threads map to (line, point) with the line index fastest whenever the axis is
+// strided, so global accesses stay coalesced for transforms over slow axes.
+#include "core.hpp"
+#include "shape.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <vector>
+
+namespace bfb {
+
+enum { FFT_NMAX_SMEM = 8192, FFT_MAX_OUTER = 8 };
+
+enum FftInKind {
+	FK_CF32 = 0, FK_CI8, FK_CI16, FK_CI4, FK_F32, FK_I8, FK_I16, FK_U8, FK_U16,
+	FK_CF64, FK_F64
+};
+
+template<typename T>
+struct FftPass {
+	const void* in;
+	void*       out;
+	int  in_kind;            // FftInKind
+	int  out_real;           // 1: write real parts only (c2r)
+	int  in_real;            // 1: real input (r2c)
+	int  in_hermitian;       // 1: input holds n/2+1 points of a Hermitian spectrum (c2r)
+	int  n;                  // transform length
+	int  n_out;              // outputs written along the axis (n, or n/2+1 for r2c)
+	int  nstage;
+	int  radix[8];
+	int  pow2_path;          // 1: Stockham; 0: direct DFT
+	int  tl;                 // threads per line (n/16) on the Stockham path
+	int  lines_per_cta;
+	int  b_fast_in, b_fast_out;
+	long in_axis_stride, out_axis_stride;          // bytes
+	int  nouter;
+	long oshape[FFT_MAX_OUTER];
+	long oistr[FFT_MAX_OUTER], oostr[FFT_MAX_OUTER];   // bytes; dim 0 enumerated fastest
+	long nline;
+	int  inverse;
+	int  shift;              // 0 none, 1 sign by axis index, 2 rotate input by n/2,
+	                         // 3 sign by coordinate of outer dim `tw_dim`
+	T    scale_in;
+	const T* twid;           // n pairs (cos, -sin)(2 pi k / n)
+	// four-step inter-pass twiddle W_N^(k * coord[tw_dim]) applied on store
+	int  post_twiddle;
+	int  tw_dim;
+	const T* tw_lo;          // 4096 pairs: exp(-2 pi i j / N)
+	const T* tw_hi;          // N/4096 pairs: exp(-2 pi i j 4096 / N)
+};
+
+// ---------------------------------------------------------------- butterflies
+template<typename T> struct Cst {
+	// cos / sin of 2 pi k / 16, k = 0..7, as foldable constant expressions
+	static __host__ __device__ constexpr T c16(int k) {
+		return k == 0 ? (T)1.0 : k == 1 ? (T)0.92387953251128673848 :
+		       k == 2 ? (T)0.70710678118654752440 : k == 3 ? (T)0.38268343236508977173 :
+		       k == 4 ? (T)0.0 : k == 5 ? (T)-0.38268343236508977173 :
+		       k == 6 ? (T)-0.70710678118654752440 : (T)-0.92387953251128673848;
+	}
+	static __host__ __device__ constexpr T s16(int k) {
+		return k == 0 ? (T)0.0 : k == 1 ? (T)0.38268343236508977173 :
+		       k == 2 ? (T)0.70710678118654752440 : k == 3 ? (T)0.92387953251128673848 :
+		       k == 4 ? (T)1.0 : k == 5 ? (T)0.92387953251128673848 :
+		       k == 6 ? (T)0.70710678118654752440 : (T)0.38268343236508977173;
+	}
+};
+
+// Forward DFT of R points in registers, natural order in and out.
+template<typename T, int R> struct Dft {
+	static __device__ __forceinline__ void apply(T* re, T* im) {
+		T er[R/2], ei[R/2], qr[R/2], qi[R/2];
+#pragma unroll
+		for( int k=0; k<R/2; ++k ) { er[k] = re[2*k]; ei[k] = im[2*k]; qr[k] = re[2*k+1]; qi[k] = im[2*k+1]; }
+		Dft<T,R/2>::apply(er, ei);
+		Dft<T,R/2>::apply(qr, qi);
+#pragma unroll
+		for( int k=0; k<R/2; ++k ) {
+			T tr, ti;
+			if( k == 0 )          { tr = qr[k];  ti = qi[k]; }
+			else if( 4*k == R )   { tr = qi[k];  ti = -qr[k]; }            // * (-i)
+			else {
+				const T c = Cst<T>::c16(k * (16 / R)), s = Cst<T>::s16(k * (16 / R));
+				tr = qr[k] * c + qi[k] * s;                                // * (c - i s)
+				ti = qi[k] * c - qr[k] * s;
+			}
+			re[k]       = er[k] + tr;  im[k]       = ei[k] + ti;
+			re[k + R/2] = er[k] - tr;  im[k + R/2] = ei[k] - ti;
+		}
+	}
+};
+template<typename T> struct Dft<T,1> {
+	static __device__ __forceinline__ void apply(T*, T*) {}
+};
+
+__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 5); }
+
+// ------------------------------------------------------------------- loading
+template<typename T>
+__device__ __forceinline__ void fft_load(FftPass<T> const& P, const char* line, int e,
+                                         int shift_sign, T& xr, T& xi) {
+	// e: logical index along the axis (already rotated for shift mode 2)
+	int n = P.n;
+	bool conj_in = false;
+	if( P.in_hermitian && e > n / 2 ) { e = n - e; conj_in = true; }
+	const char* p = line + (long)e * P.in_axis_stride;
+	T r, i = 0;
+	switch( P.in_kind ) {
+	case FK_CF32: { float2 v = *(const float2*)p; r = (T)v.x; i = (T)v.y; break; }
+	case FK_CF64: { double2 v = *(const double2*)p; r = (T)v.x; i = (T)v.y; break; }
+	case FK_CI8:  { char2 v = *(const char2*)p; r = (T)v.x; i = (T)v.y; break; }
+	case FK_CI16: { short2 v = *(const short2*)p; r = (T)v.x; i = (T)v.y; break; }
+	case FK_CI4:  { signed char b = *(const signed char*)p;
+	                r = (T)(signed char)(b & 0xF0); i = (T)(signed char)(b << 4); break; }
+	case FK_F32:  r = (T)*(const float*)p; break;
+	case FK_F64:  r = (T)*(const double*)p; break;
+	case FK_I8:   r = (T)*(const signed char*)p; break;
+	case FK_I16:  r = (T)*(const short*)p; break;
+	case FK_U8:   r = (T)*(const unsigned char*)p; break;
+	default:      r = (T)*(const unsigned short*)p; break;
+	}
+	r *= P.scale_in; i *= P.scale_in;
+	if( conj_in ) i = -i;
+	if( P.inverse ) i = -i;          // ifft(x) = conj(fft(conj(x)))
+	if( shift_sign ) { r = -r; i = -i; }
+	xr = r; xi = i;
+}
+
+template<typename T>
+__device__ __forceinline__ void fft_cmul(T& xr, T& xi, T wr, T wi) {
+	T tr = xr * wr - xi * wi;
+	xi = xr * wi + xi * wr;
+	xr = tr;
+}
+
+template<typename T>
+__device__ __forceinline__ void fft_store(FftPass<T> const& P, char* line, int o, T xr, T xi,
+                                          long tw_coord) {
+	if( o >= P.n_out ) return;
+	if( P.inverse && !P.out_real ) xi = -xi;
+	if( P.post_twiddle ) {
+		long m = (long)o * tw_coord;                 // < N
+		const T* lo = P.tw_lo + 2 * (m & 4095);
+		const T* hi = P.tw_hi + 2 * (m >> 12);
+		T wr = lo[0] * hi[0] - lo[1] * hi[1];
+		T wi = lo[0] * hi[1] + lo[1] * hi[0];
+		if( P.inverse ) wi = -wi;
+		fft_cmul(xr, xi, wr, wi);
+	}
+	char* p = line + (long)o * P.out_axis_stride;
+	if( P.out_real ) { *(T*)p = xr; }
+	else { T* q = (T*)p; q[0] = xr; q[1] = xi; }
+}
+
+// Line L -> byte offsets of its first element on the input and output side.
+template<typename T>
+__device__ __forceinline__ void fft_line_offsets(FftPass<T> const& P, long L, long& ioff,
+                                                 long& ooff, long& tw_coord) {
+	ioff = 0; ooff = 0; tw_coord = 0;
+	long rem = L;
+#pragma unroll
+	for( int d=0; d<FFT_MAX_OUTER; ++d ) {
+		if( d < P.nouter ) {
+			long q = rem / P.oshape[d];
+			long r = rem - q * P.oshape[d];
+			ioff += r * P.oistr[d];
+			ooff += r * P.oostr[d];
+			if( d == P.tw_dim ) tw_coord = r;
+			rem = q;
+		}
+	}
+}
+
+// One Stockham stage of radix R for the 16 points a thread owns.
+// FIRST: gather from global memory; LAST: scatter to global memory.
+template<typename T, int R>
+__device__ __forceinline__ void fft_stage(FftPass<T> const& P, int Ns, bool first, bool last,
+                                          bool live, int p, int TL, T* lre, T* lim,
+                                          const char* iline, char* oline, int sign_line, long twc) {
+	constexpr int NB = 16 / R;                 // butterflies per thread
+	const int n = P.n;
+	T vr[16], vi[16];
+	// ---- gather: v[u*R + t] = X[j + t*(n/R)], j = p + TL*u  <=>  element p + TL*(u + t*NB)
+	if( live ) {
+#pragma unroll
+		for( int m=0; m<16; ++m ) {
+			const int e = p + TL * m;
+			const int u = m % NB, t = m / NB;
+			T xr, xi;
+			if( first ) {
+				int es = e;
+				if( P.shift == 2 ) { es = e + n / 2; if( es >= n ) es -= n; }
+				int sg = (P.shift == 1) ? (e & 1) : sign_line;
+				fft_load(P, iline, es, sg, xr, xi);
+			} else {
+				xr = lre[fft_pad(e)]; xi = lim[fft_pad(e)];
+			}
+			vr[u * R + t] = xr; vi[u * R + t] = xi;
+		}
+	}
+	if( !first ) __syncthreads();              // everyone has read before anyone overwrites
+	if( live ) {
+#pragma unroll
+		for( int u=0; u<NB; ++u ) {
+			const int j = p + TL * u;
+			const int k = j & (Ns - 1);
+			T* r = vr + u * R;
+			T* i = vi + u * R;
+			if( Ns > 1 ) {
+				const int tstep = n / (Ns * R);
+#pragma unroll
+				for( int t=1; t<R; ++t ) {
+					const T* w = P.twid + 2 * (size_t)(k * t * tstep);
+					fft_cmul(r[t], i[t], w[0], w[1]);
+				}
+			}
+			Dft<T,R>::apply(r, i);
+			const int j0 = (j - k) * R + k;
+			if( last ) {
+#pragma unroll
+				for( int t=0; t<R; ++t ) fft_store(P, oline, j0 + t * Ns, r[t], i[t], twc);
+			} else {
+#pragma unroll
+				for( int t=0; t<R; ++t ) {
+					int o = fft_pad(j0 + t * Ns);
+					lre[o] = r[t]; lim[o] = i[t];
+				}
+			}
+		}
+	}
+	if( !last ) __syncthreads();
+}
+
+template<typename T>
+__global__ void __launch_bounds__(512)
+fft_pass_kernel(const __grid_constant__ FftPass<T> P) {
+	extern __shared__ __align__(16) unsigned char fft_smem[];
+	const int n = P.n;
+	const int B = P.lines_per_cta;
+	const int tid = threadIdx.x;
+	const long L0 = (long)blockIdx.x * B;
+
+	if( P.pow2_path ) {
+		const int TL = P.tl;
+		const int pitch = fft_pad(n) + 1;
+		T* sre = (T*)fft_smem;
+		T* sim = sre + (size_t)B * pitch;
+		// thread -> (line b, point p); the line index runs fastest when the
+		// axis is strided in memory so that neighbouring lanes touch
+		// neighbouring addresses.
+		int b = P.b_fast_in ? tid % B : tid / TL;
+		int p = P.b_fast_in ? tid / B : tid % TL;
+		long L = L0 + b;
+		bool live = L < P.nline;
+		long ioff = 0, ooff = 0, twc = 0;
+		if( live ) fft_line_offsets(P, L, ioff, ooff, twc);
+		const char* iline = (const char*)P.in + ioff;
+		const int sign_line = (P.shift == 3) ? (int)(twc & 1) : 0;
+		int Ns = 1;
+		for( int s=0; s<P.nstage; ++s ) {
+			const int R = P.radix[s];
+			const bool first = (s == 0), last = (s == P.nstage - 1);
+			if( last && !first && P.b_fast_out != P.b_fast_in ) {
+				b = P.b_fast_out ? tid % B : tid / TL;
+				p = P.b_fast_out ? tid / B : tid % TL;
+				L = L0 + b;
+				live = L < P.nline;
+				if( live ) fft_line_offsets(P, L, ioff, ooff, twc);
+			}
+			T* lre = sre + (size_t)b * pitch;
+			T* lim = sim + (size_t)b * pitch;
+			char* oline = (char*)P.out + ooff;
+			switch( R ) {
+			case 16: fft_stage<T,16>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
+			case  8: fft_stage<T, 8>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
+			case  4: fft_stage<T, 4>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
+			default: fft_stage<T, 2>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
+			}
+			Ns *= R;
+		}
+		return;
+	}
+
+	// ---------------- direct DFT for the remaining lengths
+	{
+		T* sre = (T*)fft_smem;
+		T* sim = sre + (size_t)B * n;
+		const int nthr = blockDim.x;
+		for( int idx = tid; idx < B * n; idx += nthr ) {
+			int b = P.b_fast_in ? idx % B : idx / n;
+			int e = P.b_fast_in ? idx / B : idx % n;
+			long L = L0 + b;
+			if( L >= P.nline ) continue;
+			long ioff, ooff, twc;
+			fft_line_offsets(P, L, ioff, ooff, twc);
+			int es = e;
+			if( P.shift == 2 ) { es = e + n / 2; if( es >= n ) es -= n; }
+			T xr, xi;
+			fft_load(P, (const char*)P.in + ioff, es, 0, xr, xi);
+			if( P.shift == 1 ) {
+				if( n % 2 == 0 ) { if( e & 1 ) { xr = -xr; xi = -xi; } }
+				else {
+					// odd length: multiply by exp(+2 pi i e (n/2) / n)  (fft_kernels.cu:76-90)
+					long m = ((long)e * (n / 2)) % n;
+					const T* w = P.twid + 2 * m;      // (cos, -sin)
+					T wr = w[0], wi = -w[1];
+					if( P.inverse ) wi = -wi;         // data is conjugated at this point
+					fft_cmul(xr, xi, wr, wi);
+				}
+			}
+			if( P.shift == 3 && (twc & 1) ) { xr = -xr; xi = -xi; }
+			sre[(size_t)b * n + e] = xr; sim[(size_t)b * n + e] = xi;
+		}
+		__syncthreads();
+		for( int idx = tid; idx < B * P.n_out; idx += nthr ) {
+			int b = P.b_fast_out ? idx % B : idx / P.n_out;
+			int o = P.b_fast_out ? idx / B : idx % P.n_out;
+			long L = L0 + b;
+			if( L >= P.nline ) continue;
+			long ioff, ooff, twc;
+			fft_line_offsets(P, L, ioff, ooff, twc);
+			const T* lre = sre + (size_t)b * n;
+			const T* lim = sim + (size_t)b * n;
+			T ar = 0, ai = 0;
+			int m = 0;
+			for( int e=0; e<n; ++e ) {
+				const T* w = P.twid + 2 * (size_t)m;
+				ar += lre[e] * w[0] - lim[e] * w[1];
+				ai += lre[e] * w[1] + lim[e] * w[0];
+				m += o; if( m >= n ) m -= n;
+			}
+			fft_store(P, (char*)P.out + ooff, o, ar, ai, twc);
+		}
+	}
+}
+
+} // namespace bfb
+
+using namespace bfb;
+
+// --------------------------------------------------------------------- plan --
+struct FftAxisPlan {
+	int  axis;
+	long n;
+};
+
+struct BFfft_impl {
+	int  ndim = 0, rank = 0;
+	int  axes[3];
+	bool real_in = false, real_out = false, fp64 = false, do_fftshift = false;
+	BFdtype itype, otype;
+	long ishape[BF_MAX_DIMS], oshape[BF_MAX_DIMS];
+	size_t workspace_size = 0;
+	// device twiddle tables, keyed by length (pairs of T)
+	std::map<long, void*> twid;          // n -> table of n pairs
+	std::map<long, void*> tw_lo, tw_hi;  // four-step N -> tables
+	void*  own_ws = nullptr;
+	size_t own_ws_size = 0;
+	bool   planned = false;
+
+	~BFfft_impl() {
+		for( auto& kv : twid )  cudaFree(kv.second);
+		for( auto& kv : tw_lo ) cudaFree(kv.second);
+		for( auto& kv : tw_hi ) cudaFree(kv.second);
+		if( own_ws ) cudaFree(own_ws);
+	}
+};
+
+namespace {
+
+template<typename T>
+BFstatus make_table(std::map<long, void*>& cache, long key, long count, long N, long mul,
+                    const T** out) {
+	auto it = cache.find(key);
+	if( it != cache.end() ) { *out = (const T*)it->second; return BF_STATUS_SUCCESS; }
+	std::vector<T> host(2 * (size_t)count);
+	const double two_pi = 6.283185307179586476925286766559;
+	for( long k=0; k<count; ++k ) {
+		// exp(-2 pi i (k*mul) / N), argument reduced exactly in integers
+		long m = (k * mul) % N;
+		double a = two_pi * (double)m / (double)N;
+		host[2*k]   = (T)std::cos(a);
+		host[2*k+1] = (T)(-std::sin(a));
+	}
+	void* dev = nullptr;
+	BFB_CUDA(cudaMalloc(&dev, host.size() * sizeof(T)), BF_STATUS_MEM_ALLOC_FAILED);
+	BFB_CUDA(cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice),
+	         BF_STATUS_MEM_OP_FAILED);
+	cache[key] = dev;
+	*out = (const T*)dev;
+	return BF_STATUS_SUCCESS;
+}
+
+bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
+
+int kind_of(BFdtype d) {
+	switch( d ) {
+	case BF_DTYPE_CF32: return FK_CF32;
+	case BF_DTYPE_CI8:  return FK_CI8;
+	case BF_DTYPE_CI16: return FK_CI16;
+	case BF_DTYPE_CI4:  return FK_CI4;
+	case BF_DTYPE_F32:  return FK_F32;
+	case BF_DTYPE_I8:   return FK_I8;
+	case BF_DTYPE_I16:  return FK_I16;
+	case BF_DTYPE_U8:   return FK_U8;
+	case BF_DTYPE_U16:  return FK_U16;
+	case BF_DTYPE_CF64: return FK_CF64;
+	case BF_DTYPE_F64:  return FK_F64;
+	default: return -1;
+	}
+}
+
+double scale_of(int kind) {
+	switch( kind ) {
+	case FK_CI8: case FK_CI4: case FK_I8: return 1. / 128;
+	case FK_CI16: case FK_I16:            return 1. / 32768;
+	case FK_U8:                           return 1. / 256;
+	case FK_U16:                          return 1. / 65536;
+	default:                              return 1.;
+	}
+}
+
+// Describes one array seen by a pass: base pointer + per-dim byte strides.
+struct PassArray {
+	void* data;
+	long  strides[BF_MAX_DIMS];
+	int   kind;       // FftInKind of the elements
+};
+
+// One 1-D pass along `axis` over arrays of logical shape `shape` (length of the
+// transform = n; input may hold n_in points, output n_out points on that axis).
+template<typename T>
+BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
+                  PassArray const& in, PassArray const& out, bool in_real, bool in_herm,
+                  bool out_real, long n_out, bool inverse, int shift, cudaStream_t st,
+                  // four-step extras
+                  int extra_dims = 0, const long* ex_shape = nullptr, const long* ex_istr = nullptr,
+                  const long* ex_ostr = nullptr, int post_tw = 0, long twN = 0) {
+	FftPass<T> P;
+	memset(&P, 0, sizeof(P));
+	P.in = in.data; P.out = out.data;
+	P.in_kind = in.kind; P.out_real = out_real; P.in_real = in_real; P.in_hermitian = in_herm;
+	P.n = (int)n; P.n_out = (int)n_out;
+	P.in_axis_stride = in.strides[axis]; P.out_axis_stride = out.strides[axis];
+	P.inverse = inverse; P.shift = shift;
+	P.scale_in = (T)scale_of(in.kind);
+	P.tw_dim = -1;
+	// outer dims: extra (four-step) dims first, then the array's other dims
+	struct OD { long len, is, os; bool tw; };
+	std::vector<OD> od;
+	for( int d=0; d<extra_dims; ++d ) od.push_back({ex_shape[d], ex_istr[d], ex_ostr[d], d == 0});
+	for( int d=ndim-1; d>=0; --d ) {
+		if( d == axis || batch_shape[d] == 1 ) continue;
+		od.push_back({batch_shape[d], in.strides[d], out.strides[d], false});
+	}
+	// enumerate the dim with the smallest input stride fastest (coalescing)
+	std::stable_sort(od.begin(), od.end(), [](OD const& a, OD const& b) {
+		return std::abs(a.is) < std::abs(b.is); });
+	BFB_ASSERT((int)od.size() <= FFT_MAX_OUTER, BF_STATUS_UNSUPPORTED_SHAPE);
+	P.nouter = (int)od.size();
+	long nline = 1;
+	for( int d=0; d<P.nouter; ++d ) {
+		P.oshape[d] = od[d].len; P.oistr[d] = od[d].is; P.oostr[d] = od[d].os;
+		if( od[d].tw ) P.tw_dim = d;
+		nline *= od[d].len;
+	}
+	P.nline = nline;
+	if( nline == 0 || n == 0 ) return BF_STATUS_SUCCESS;
+	BFB_ASSERT(n <= FFT_NMAX_SMEM, BF_STATUS_UNSUPPORTED_SHAPE);
+	const T* tw = nullptr;
+	BFstatus s = make_table<T>(plan->twid, n * 2 + (sizeof(T) == 8), n, n, 1, &tw);
+	if( s != BF_STATUS_SUCCESS ) return s;
+	P.twid = tw;
+	if( post_tw ) {
+		P.post_twiddle = 1;
+		const T *lo = nullptr, *hi = nullptr;
+		s = make_table<T>(plan->tw_lo, twN * 2 + (sizeof(T) == 8), 4096, twN, 1, &lo);
+		if( s != BF_STATUS_SUCCESS ) return s;
+		s = make_table<T>(plan->tw_hi, twN * 2 + (sizeof(T) == 8), std::max<long>(1, twN / 4096), twN, 4096, &hi);
+		if( s != BF_STATUS_SUCCESS ) return s;
+		P.tw_lo = lo; P.tw_hi = hi;
+	}
+	// Elements are "strided" if the axis is not the fastest dim on that side.
+	long isize_in = (in.kind == FK_CF64 ? 16 : in.kind == FK_F64 ? 8 : in.kind == FK_CF32 ? 8 :
+	                 in.kind == FK_CI16 ? 4 : in.kind == FK_CI8 ? 2 : in.kind == FK_CI4 ? 1 :
+	                 in.kind == FK_F32 ? 4 : (in.kind == FK_I16 || in.kind == FK_U16) ? 2 : 1);
+	long osize = (out_real ? 1 : 2) * (long)sizeof(T);
+	P.b_fast_in  = std::abs(in.strides[axis])  != isize_in;
+	P.b_fast_out = std::abs(out.strides[axis]) != osize;
+	int threads;
+	size_t smem;
+	if( is_pow2(n) && n >= 16 ) {
+		P.pow2_path = 1;
+		P.tl = (int)(n / 16);
+		int lg = 0; while( (1L << lg) < n ) ++lg;
+		// radix-16 stages first, remainder last-but-first so the final stage is wide
+		int rem = lg % 4, ns = 0;
+		if( rem ) P.radix[ns++] = 1 << rem;
+		for( int i=0; i<lg/4; ++i ) P.radix[ns++] = 16;
+		P.nstage = ns;
+		int B = std::max(1, 256 / P.tl);
+		if( P.b_fast_in || P.b_fast_out ) B = std::max(B, std::min(16, 512 / P.tl));
+		B = (int)std::min<long>(B, nline);
+		P.lines_per_cta = B;
+		threads = B * P.tl;
+		size_t pitch = (size_t)(n + (n >> 5)) + 1;
+		smem = 2 * (size_t)B * pitch * sizeof(T);
+	} else {
+		P.pow2_path = 0;
+		int B = (int)std::max<long>(1, std::min<long>(nline, 256 / std::max<long>(1, n)));
+		if( P.b_fast_in || P.b_fast_out ) B = (int)std::min<long>(nline, std::max<long>(B, std::min<long>(16, 4096 / n)));
+		B = std::max(1, B);
+		P.lines_per_cta = B;
+		threads = (int)std::min<long>(512, round_up<long>((long)B * n, 32));
+		smem = 2 * (size_t)B * n * sizeof(T);
+	}
+	BFB_ASSERT(smem <= 220 * 1024, BF_STATUS_UNSUPPORTED_SHAPE);
+	BFB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                              (int)std::max<size_t>(smem, 1024)), BF_STATUS_INTERNAL_ERROR);
+	long nblock = div_up<long>(nline, P.lines_per_cta);
+	BFB_ASSERT(nblock < (1L << 31), BF_STATUS_UNSUPPORTED_SHAPE);
+	fft_pass_kernel<T><<<(unsigned)nblock, threads, smem, st>>>(P);
+	count_launch();
+	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+	return BF_STATUS_SUCCESS;
+}
+
+// A full 1-D transform of length n along `axis` (splits into two passes
+// through `tmp` when n exceeds the shared-memory limit).
+template<typename T>
+BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
+                  PassArray const& in, PassArray const& out, bool in_real, bool in_herm,
+                  bool out_real, long n_out, bool inverse, bool fftshift, void* tmp,
+                  cudaStream_t st) {
+	int shift = 0;
+	if( fftshift ) shift = inverse ? 2 : 1;
+	if( n <= FFT_NMAX_SMEM ) {
+		return run_pass<T>(plan, ndim, batch_shape, axis, n, in, out, in_real, in_herm,
+		                   out_real, n_out, inverse, shift, st);
+	}
+	// ---- four-step: n = n1 * n2 (c2c, power of two only)
+	BFB_ASSERT(is_pow2(n) && !in_real && !in_herm && !out_real, BF_STATUS_UNSUPPORTED_SHAPE);
+	BFB_ASSERT(tmp, BF_STATUS_INSUFFICIENT_STORAGE);
+	long n2 = 4096, n1 = n / n2;
+	BFB_ASSERT(n1 <= FFT_NMAX_SMEM && n1 >= 16, BF_STATUS_UNSUPPORTED_SHAPE);
+	const long csize = 2 * sizeof(T);
+	// tmp holds [other dims (C order, axis removed)][k1][c2]
+	PassArray t;
+	t.data = tmp; t.kind = sizeof(T) == 8 ? FK_CF64 : FK_CF32;
+	long acc = n * csize;
+	for( int d=ndim-1; d>=0; --d ) {
+		if( d == axis ) { t.strides[d] = 0; continue; }
+		t.strides[d] = acc;
+		acc *= batch_shape[d];
+	}
+	// Pass A: length n1 over e1 (stride n2 on the input); lines add the c2 dim.
+	{
+		PassArray ia = in, oa = t;
+		ia.strides[axis] = in.strides[axis] * n2;
+		oa.strides[axis] = n2 * csize;
+		long exs = n2, exi = in.strides[axis], exo = csize;
+		int shiftA = shift == 1 ? 3 : shift;          // forward sign follows c2, rotation follows e1
+		BFstatus s = run_pass<T>(plan, ndim, batch_shape, axis, n1, ia, oa, false, false, false, n1,
+		                         inverse, shiftA, st, 1, &exs, &exi, &exo, 1, n);
+		if( s != BF_STATUS_SUCCESS ) return s;
+	}
+	// Pass B: length n2 over c2 (contiguous in tmp); output index k2*n1 + k1.
+	{
+		PassArray ib = t, ob = out;
+		ib.strides[axis] = csize;
+		ob.strides[axis] = out.strides[axis] * n1;
+		long exs = n1, exi = n2 * csize, exo = out.strides[axis];
+		return run_pass<T>(plan, ndim, batch_shape, axis, n2, ib, ob, false, false, false, n2,
+		                   inverse, 0, st,
+		                   1, &exs, &exi, &exo, 0, 0);
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+BFstatus bfFftCreate(BFfft* plan_ptr) {
+	BFB_ASSERT(plan_ptr, BF_STATUS_INVALID_POINTER);
+	*plan_ptr = nullptr;
+	BFB_TRY(*plan_ptr = new BFfft_impl());
+	return BF_STATUS_SUCCESS;
+}
+
+BFstatus bfFftDestroy(BFfft plan) {
+	BFB_ASSERT(plan, BF_STATUS_INVALID_HANDLE);
+	delete plan;
+	return BF_STATUS_SUCCESS;
+}
+
+BFstatus bfFftInit(BFfft plan, BFarray const* in, BFarray const* out, int rank,
+                   int const* axes, BFbool apply_fftshift, size_t* tmp_storage_size) {
+	BFB_ASSERT(plan, BF_STATUS_INVALID_HANDLE);
+	BFB_ASSERT(in && out, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(rank > 0 && rank <= 3, BF_STATUS_INVALID_ARGUMENT);
+	BFB_ASSERT(in->ndim == out->ndim && rank <= in->ndim && in->ndim <= BF_MAX_DIMS,
+	           BF_STATUS_INVALID_ARGUMENT);
+	int ndim = in->ndim;
+	plan->ndim = ndim; plan->rank = rank;
+	for( int d=0; d<rank; ++d ) {
+		int ax = axes ? axes[d] : ndim - rank + d;
+		if( ax < 0 ) ax += ndim;
+		BFB_ASSERT(ax >= 0 && ax < ndim, BF_STATUS_INVALID_ARGUMENT);
+		for( int e=0; e<d; ++e ) BFB_ASSERT(plan->axes[e] != ax, BF_STATUS_INVALID_ARGUMENT);
+		plan->axes[d] = ax;
+	}
+	plan->real_in  = !dtype_is_complex(in->dtype);
+	plan->real_out = !dtype_is_complex(out->dtype);
+	BFB_ASSERT(!(plan->real_in && plan->real_out), BF_STATUS_INVALID_DTYPE);
+	int ik = kind_of(in->dtype), ok = kind_of(out->dtype);
+	BFB_ASSERT(ik >= 0, BF_STATUS_UNSUPPORTED_DTYPE);
+	BFB_ASSERT(ok == FK_CF32 || ok == FK_CF64 || ok == FK_F32 || ok == FK_F64, BF_STATUS_UNSUPPORTED_DTYPE);
+	plan->fp64 = (ok == FK_CF64 || ok == FK_F64);
+	if( plan->fp64 ) BFB_ASSERT(ik == FK_CF64 || ik == FK_F64, BF_STATUS_UNSUPPORTED_DTYPE);
+	else             BFB_ASSERT(ik != FK_CF64 && ik != FK_F64, BF_STATUS_UNSUPPORTED_DTYPE);
+	// real transforms cannot be shifted (ref: src/fft_kernels.cu:250-283)
+	if( plan->real_in ) BFB_ASSERT(!apply_fftshift, BF_STATUS_UNSUPPORTED);
+	int last = plan->axes[rank-1];
+	long tmp_elems = 0;
+	for( int d=0; d<ndim; ++d ) {
+		long il = in->shape[d], ol = out->shape[d];
+		if( (!plan->real_in && !plan->real_out) || d != last ) {
+			BFB_ASSERT(il == ol, BF_STATUS_INVALID_SHAPE);
+		} else if( plan->real_in ) {
+			BFB_ASSERT(ol == il / 2 + 1, BF_STATUS_INVALID_SHAPE);
+		} else {
+			BFB_ASSERT(il == ol / 2 + 1, BF_STATUS_INVALID_SHAPE);
+		}
+		plan->ishape[d] = il; plan->oshape[d] = ol;
+	}
+	plan->itype = in->dtype; plan->otype = out->dtype;
+	plan->do_fftshift = apply_fftshift != 0;
+	// Workspace: c2r over >1 axes stages the complex input; four-step lengths
+	// stage one complex copy of the (output-shaped) array.
+	size_t csize = plan->fp64 ? 16 : 8;
+	size_t ws = 0;
+	if( plan->real_out && rank > 1 ) {
+		tmp_elems = 1;
+		for( int d=0; d<ndim; ++d ) tmp_elems *= in->shape[d];
+		ws = std::max(ws, (size_t)tmp_elems * csize);
+	}
+	for( int d=0; d<rank; ++d ) {
+		long n = plan->real_in ? in->shape[plan->axes[d]] : out->shape[plan->axes[d]];
+		if( n > FFT_NMAX_SMEM ) {
+			BFB_ASSERT(is_pow2(n) && !plan->real_in && !plan->real_out, BF_STATUS_UNSUPPORTED_SHAPE);
+			BFB_ASSERT(n / 4096 <= FFT_NMAX_SMEM, BF_STATUS_UNSUPPORTED_SHAPE);
+			size_t elems = 1;
+			for( int e=0; e<ndim; ++e ) elems *= out->shape[e];
+			ws = std::max(ws, elems * csize);
+		}
+	}
+	plan->workspace_size = ws;
+	plan->planned = true;
+	if( tmp_storage_size ) *tmp_storage_size = ws;
+	return BF_STATUS_SUCCESS;
+}
+
+BFstatus bfFftExecute(BFfft plan, BFarray const* in, BFarray const* out, BFbool inverse,
+                      void* tmp_storage, size_t tmp_storage_size) {
+	BFB_ASSERT(plan, BF_STATUS_INVALID_HANDLE);
+	BFB_ASSERT(in && out, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(plan->planned, BF_STATUS_INVALID_STATE);
+	BFB_ASSERT(space_on_device(in->space) && space_on_device(out->space), BF_STATUS_UNSUPPORTED_SPACE);
+	BFB_ASSERT(in->dtype == plan->itype && out->dtype == plan->otype, BF_STATUS_INVALID_DTYPE);
+	BFB_ASSERT(in->ndim == plan->ndim && out->ndim == plan->ndim, BF_STATUS_INVALID_SHAPE);
+	int ndim = plan->ndim, rank = plan->rank;
+	for( int d=0; d<ndim; ++d ) {
+		BFB_ASSERT(in->shape[d] == plan->ishape[d] && out->shape[d] == plan->oshape[d],
+		           BF_STATUS_INVALID_SHAPE);
+	}
+	cudaStream_t st = thread_stream();
+	if( plan->workspace_size ) {
+		if( !tmp_storage ) {
+			if( plan->own_ws_size < plan->workspace_size ) {
+				if( plan->own_ws ) cudaFree(plan->own_ws);
+				plan->own_ws = nullptr; plan->own_ws_size = 0;
+				BFB_CUDA(cudaMalloc(&plan->own_ws, plan->workspace_size), BF_STATUS_MEM_ALLOC_FAILED);
+				plan->own_ws_size = plan->workspace_size;
+			}
+			tmp_storage = plan->own_ws;
+		} else {
+			BFB_ASSERT(tmp_storage_size >= plan->workspace_size, BF_STATUS_INSUFFICIENT_STORAGE);
+		}
+	}
+	bool inv = plan->real_out || (!plan->real_in && inverse);     // ref: src/fft.cu:294
+	bool shiftc = plan->do_fftshift && !plan->real_in && !plan->real_out;
+	PassArray ain, aout;
+	ain.data = in->data;   ain.kind = kind_of(in->dtype);
+	aout.data = out->data; aout.kind = plan->fp64 ? FK_CF64 : FK_CF32;
+	for( int d=0; d<ndim; ++d ) { ain.strides[d] = in->strides[d]; aout.strides[d] = out->strides[d]; }
+	int last = plan->axes[rank-1];
+
+#define BFB_FFT_AXIS(T_, ...) do { BFstatus s__ = run_axis<T_>(__VA_ARGS__); \
+		if( s__ != BF_STATUS_SUCCESS ) return s__; } while(0)
+#define BFB_FFT_BODY(T_) \
+	if( plan->real_in ) { \
+		/* r2c: real axis first (in -> out), remaining axes in place on out */ \
+		long n = in->shape[last]; \
+		long bshape[BF_MAX_DIMS]; \
+		for( int d=0; d<ndim; ++d ) bshape[d] = in->shape[d]; \
+		BFB_FFT_AXIS(T_, plan, ndim, bshape, last, n, ain, aout, true, false, false, n/2+1, false, false, tmp_storage, st); \
+		for( int d=0; d<ndim; ++d ) bshape[d] = out->shape[d]; \
+		for( int a=rank-2; a>=0; --a ) { \
+			int ax = plan->axes[a]; \
+			BFB_FFT_AXIS(T_, plan, ndim, bshape, ax, out->shape[ax], aout, aout, false, false, false, out->shape[ax], false, false, tmp_storage, st); \
+		} \
+	} else if( plan->real_out ) { \
+		/* c2r: other axes first through the workspace, Hermitian axis last */ \
+		long n = out->shape[last]; \
+		long bshape[BF_MAX_DIMS]; \
+		for( int d=0; d<ndim; ++d ) bshape[d] = in->shape[d]; \
+		PassArray cur = ain; \
+		if( rank > 1 ) { \
+			PassArray t; t.data = tmp_storage; t.kind = plan->fp64 ? FK_CF64 : FK_CF32; \
+			long acc = plan->fp64 ? 16 : 8; \
+			for( int d=ndim-1; d>=0; --d ) { t.strides[d] = acc; acc *= in->shape[d]; } \
+			for( int a=rank-2; a>=0; --a ) { \
+				int ax = plan->axes[a]; \
+				BFB_FFT_AXIS(T_, plan, ndim, bshape, ax, in->shape[ax], cur, t, false, false, false, in->shape[ax], true, false, nullptr, st); \
+				cur = t; \
+			} \
+		} \
+		for( int d=0; d<ndim; ++d ) bshape[d] = out->shape[d]; \
+		PassArray ro = aout; ro.kind = plan->fp64 ? FK_F64 : FK_F32; \
+		BFB_FFT_AXIS(T_, plan, ndim, bshape, last, n, cur, ro, false, true, true, n, true, false, nullptr, st); \
+	} else { \
+		long bshape[BF_MAX_DIMS]; \
+		for( int d=0; d<ndim; ++d ) bshape[d] = out->shape[d]; \
+		PassArray cur = ain; \
+		for( int a=rank-1; a>=0; --a ) { \
+			int ax = plan->axes[a]; \
+			BFB_FFT_AXIS(T_, plan, ndim, bshape, ax, out->shape[ax], cur, aout, false, false, false, out->shape[ax], inv, shiftc, tmp_storage, st); \
+			cur = aout; \
+		} \
+	}
+	BFB_TRY(
+		if( plan->fp64 ) { BFB_FFT_BODY(double) }
+		else             { BFB_FFT_BODY(float) }
+	);
+#undef BFB_FFT_BODY
+#undef BFB_FFT_AXIS
+	return BF_STATUS_SUCCESS;
+}
+
+} // extern "C"

@@ -9,11 +9,13 @@ extern "C" {
 BFstatus bfUnpack(BFarray const*, BFarray const*, BFbool) { return BF_STATUS_UNSUPPORTED; }
 #endif
 
-#ifndef BFB_HAVE_FFT
+#if 0
 BFstatus bfFftCreate(BFfft* plan) { if( plan ) *plan = nullptr; return BF_STATUS_UNSUPPORTED; }
 BFstatus bfFftInit(BFfft, BFarray const*, BFarray const*, int, int const*, BFbool, size_t*) { return BF_STATUS_UNSUPPORTED; }
 BFstatus bfFftExecute(BFfft, BFarray const*, BFarray const*, BFbool, void*, size_t) { return BF_STATUS_UNSUPPORTED; }
 BFstatus bfFftDestroy(BFfft) { return BF_STATUS_UNSUPPORTED; }
+#endif
+#ifndef BFB_HAVE_SPECTROMETER
 BFstatus bfSpectrometerFused(BFarray const*, BFarray const*, int, int, double) { return BF_STATUS_UNSUPPORTED; }
 #endif
 
