@@ -18,6 +18,7 @@ from bifrost_b200.reduce import reduce
 from bifrost_b200.transpose import transpose
 from bifrost_b200.unpack import unpack
 from bifrost_b200.map import map, detect, accumulate
+from bifrost_b200.spectrometer import spectrometer
 
 __version__ = '0.1.0'
 

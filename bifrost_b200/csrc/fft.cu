@@ -130,7 +130,9 @@ template<typename T> struct Dft<T,1> {
 	static __device__ __forceinline__ void apply(T*, T*) {}
 };
 
-__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 5); }
+// interleaved complex in shared memory, one pad slot per 16 points: every access
+// pattern of the Stockham stages is conflict-free within a half-warp
+__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 4); }
 
 // ------------------------------------------------------------------- loading
 template<typename T>
@@ -208,12 +210,51 @@ __device__ __forceinline__ void fft_line_offsets(FftPass<T> const& P, long L, lo
 	}
 }
 
+template<typename T> struct Cx { T x, y; };
+
+// v[t] *= w^t for t = 1..R-1 from the exactly tabulated powers w, w^2, w^4, w^8
+// (every factor is a product of at most three table values).
+template<typename T, int R>
+__device__ __forceinline__ void fft_twiddle(T* r, T* i, const T* __restrict__ twid, int base, int n) {
+	const int mask = n - 1;
+	// w^1, w^2, w^4, w^8 from the table; the rest by at most two products
+#define BFB_TW_LOAD(k_)  const T w##k_##r = twid[2 * (size_t)((base * k_) & mask)], \
+                                 w##k_##i = twid[2 * (size_t)((base * k_) & mask) + 1]
+#define BFB_TW_MUL(c_, a_, b_) const T w##c_##r = w##a_##r * w##b_##r - w##a_##i * w##b_##i, \
+                                       w##c_##i = w##a_##r * w##b_##i + w##a_##i * w##b_##r
+	BFB_TW_LOAD(1);
+	fft_cmul(r[1], i[1], w1r, w1i);
+	if( R >= 4 ) {
+		BFB_TW_LOAD(2);
+		BFB_TW_MUL(3, 1, 2);
+		fft_cmul(r[2], i[2], w2r, w2i);
+		fft_cmul(r[3], i[3], w3r, w3i);
+		if( R >= 8 ) {
+			BFB_TW_LOAD(4);
+			BFB_TW_MUL(5, 1, 4); BFB_TW_MUL(6, 2, 4); BFB_TW_MUL(7, 3, 4);
+			fft_cmul(r[4 % R], i[4 % R], w4r, w4i); fft_cmul(r[5 % R], i[5 % R], w5r, w5i);
+			fft_cmul(r[6 % R], i[6 % R], w6r, w6i); fft_cmul(r[7 % R], i[7 % R], w7r, w7i);
+			if( R >= 16 ) {
+				BFB_TW_LOAD(8);
+				BFB_TW_MUL(9, 1, 8);  BFB_TW_MUL(10, 2, 8); BFB_TW_MUL(11, 3, 8); BFB_TW_MUL(12, 4, 8);
+				BFB_TW_MUL(13, 5, 8); BFB_TW_MUL(14, 6, 8); BFB_TW_MUL(15, 7, 8);
+				fft_cmul(r[8 % R],  i[8 % R],  w8r,  w8i);  fft_cmul(r[9 % R],  i[9 % R],  w9r,  w9i);
+				fft_cmul(r[10 % R], i[10 % R], w10r, w10i); fft_cmul(r[11 % R], i[11 % R], w11r, w11i);
+				fft_cmul(r[12 % R], i[12 % R], w12r, w12i); fft_cmul(r[13 % R], i[13 % R], w13r, w13i);
+				fft_cmul(r[14 % R], i[14 % R], w14r, w14i); fft_cmul(r[15 % R], i[15 % R], w15r, w15i);
+			}
+		}
+	}
+#undef BFB_TW_LOAD
+#undef BFB_TW_MUL
+}
+
 // One Stockham stage of radix R for the 16 points a thread owns.
 // FIRST: gather from global memory; LAST: scatter to global memory.
-template<typename T, int R>
-__device__ __forceinline__ void fft_stage(FftPass<T> const& P, int Ns, bool first, bool last,
-                                          bool live, int p, int TL, T* lre, T* lim,
-                                          const char* iline, char* oline, int sign_line, long twc) {
+template<typename T, int R, bool FIRST, bool LAST>
+__device__ __forceinline__ void fft_stage(FftPass<T> const& P, int Ns, bool live, int p, int TL,
+                                          Cx<T>* lbuf, const char* iline, char* oline,
+                                          int sign_line, long twc) {
 	constexpr int NB = 16 / R;                 // butterflies per thread
 	const int n = P.n;
 	T vr[16], vi[16];
@@ -224,18 +265,19 @@ __device__ __forceinline__ void fft_stage(FftPass<T> const& P, int Ns, bool firs
 			const int e = p + TL * m;
 			const int u = m % NB, t = m / NB;
 			T xr, xi;
-			if( first ) {
+			if( FIRST ) {
 				int es = e;
 				if( P.shift == 2 ) { es = e + n / 2; if( es >= n ) es -= n; }
 				int sg = (P.shift == 1) ? (e & 1) : sign_line;
 				fft_load(P, iline, es, sg, xr, xi);
 			} else {
-				xr = lre[fft_pad(e)]; xi = lim[fft_pad(e)];
+				Cx<T> v = lbuf[fft_pad(e)];
+				xr = v.x; xi = v.y;
 			}
 			vr[u * R + t] = xr; vi[u * R + t] = xi;
 		}
 	}
-	if( !first ) __syncthreads();              // everyone has read before anyone overwrites
+	if( !FIRST ) __syncthreads();              // everyone has read before anyone overwrites
 	if( live ) {
 #pragma unroll
 		for( int u=0; u<NB; ++u ) {
@@ -243,33 +285,37 @@ __device__ __forceinline__ void fft_stage(FftPass<T> const& P, int Ns, bool firs
 			const int k = j & (Ns - 1);
 			T* r = vr + u * R;
 			T* i = vi + u * R;
-			if( Ns > 1 ) {
-				const int tstep = n / (Ns * R);
-#pragma unroll
-				for( int t=1; t<R; ++t ) {
-					const T* w = P.twid + 2 * (size_t)(k * t * tstep);
-					fft_cmul(r[t], i[t], w[0], w[1]);
-				}
-			}
+			if( !FIRST ) fft_twiddle<T,R>(r, i, P.twid, k * (n / (Ns * R)), n);
 			Dft<T,R>::apply(r, i);
 			const int j0 = (j - k) * R + k;
-			if( last ) {
+			if( LAST ) {
 #pragma unroll
 				for( int t=0; t<R; ++t ) fft_store(P, oline, j0 + t * Ns, r[t], i[t], twc);
 			} else {
 #pragma unroll
 				for( int t=0; t<R; ++t ) {
-					int o = fft_pad(j0 + t * Ns);
-					lre[o] = r[t]; lim[o] = i[t];
+					Cx<T> v; v.x = r[t]; v.y = i[t];
+					lbuf[fft_pad(j0 + t * Ns)] = v;
 				}
 			}
 		}
 	}
-	if( !last ) __syncthreads();
+	if( !LAST ) __syncthreads();
+}
+
+template<typename T, int R>
+__device__ __forceinline__ void fft_stage_dispatch(FftPass<T> const& P, int Ns, bool first, bool last,
+                                                   bool live, int p, int TL, Cx<T>* lbuf,
+                                                   const char* iline, char* oline, int sign_line,
+                                                   long twc) {
+	if( first && last )  fft_stage<T,R,true, true >(P, Ns, live, p, TL, lbuf, iline, oline, sign_line, twc);
+	else if( first )     fft_stage<T,R,true, false>(P, Ns, live, p, TL, lbuf, iline, oline, sign_line, twc);
+	else if( last )      fft_stage<T,R,false,true >(P, Ns, live, p, TL, lbuf, iline, oline, sign_line, twc);
+	else                 fft_stage<T,R,false,false>(P, Ns, live, p, TL, lbuf, iline, oline, sign_line, twc);
 }
 
 template<typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 1)
 fft_pass_kernel(const __grid_constant__ FftPass<T> P) {
 	extern __shared__ __align__(16) unsigned char fft_smem[];
 	const int n = P.n;
@@ -280,8 +326,7 @@ fft_pass_kernel(const __grid_constant__ FftPass<T> P) {
 	if( P.pow2_path ) {
 		const int TL = P.tl;
 		const int pitch = fft_pad(n) + 1;
-		T* sre = (T*)fft_smem;
-		T* sim = sre + (size_t)B * pitch;
+		Cx<T>* sbuf = (Cx<T>*)fft_smem;
 		// thread -> (line b, point p); the line index runs fastest when the
 		// axis is strided in memory so that neighbouring lanes touch
 		// neighbouring addresses.
@@ -304,14 +349,13 @@ fft_pass_kernel(const __grid_constant__ FftPass<T> P) {
 				live = L < P.nline;
 				if( live ) fft_line_offsets(P, L, ioff, ooff, twc);
 			}
-			T* lre = sre + (size_t)b * pitch;
-			T* lim = sim + (size_t)b * pitch;
+			Cx<T>* lbuf = sbuf + (size_t)b * pitch;
 			char* oline = (char*)P.out + ooff;
 			switch( R ) {
-			case 16: fft_stage<T,16>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
-			case  8: fft_stage<T, 8>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
-			case  4: fft_stage<T, 4>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
-			default: fft_stage<T, 2>(P, Ns, first, last, live, p, TL, lre, lim, iline, oline, sign_line, twc); break;
+			case 16: fft_stage_dispatch<T,16>(P, Ns, first, last, live, p, TL, lbuf, iline, oline, sign_line, twc); break;
+			case  8: fft_stage_dispatch<T, 8>(P, Ns, first, last, live, p, TL, lbuf, iline, oline, sign_line, twc); break;
+			case  4: fft_stage_dispatch<T, 4>(P, Ns, first, last, live, p, TL, lbuf, iline, oline, sign_line, twc); break;
+			default: fft_stage_dispatch<T, 2>(P, Ns, first, last, live, p, TL, lbuf, iline, oline, sign_line, twc); break;
 			}
 			Ns *= R;
 		}
@@ -540,7 +584,7 @@ BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 		B = (int)std::min<long>(B, nline);
 		P.lines_per_cta = B;
 		threads = B * P.tl;
-		size_t pitch = (size_t)(n + (n >> 5)) + 1;
+		size_t pitch = (size_t)(n + (n >> 4)) + 1;
 		smem = 2 * (size_t)B * pitch * sizeof(T);
 	} else {
 		P.pow2_path = 0;

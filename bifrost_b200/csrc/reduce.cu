@@ -82,10 +82,99 @@ __device__ __forceinline__ float mag2(float x, float y) { float a = x * x; a += 
 // V: adjacent outputs per thread (MODE 0 only).  RF: compile-time factor with a
 // single vector load per output (0 = runtime loop).
 template<typename I, int MODE, int V, int RF>
+__device__ __forceinline__ void reduce_one(const char* __restrict__ src, char* __restrict__ dst,
+                                           ReduceParams const& p) {
+		const int op = p.op;
+	const int f = RF ? RF : p.factor;
+	if( MODE == 0 ) {
+		struct __align__(sizeof(I)*V) VecI { I v[V]; };
+		struct __align__(4*V)         VecO { float v[V]; };
+		float acc[V];
+		if( RF ) {
+			struct __align__(sizeof(I)*(RF?RF:1)) VecR { I v[RF?RF:1]; };
+			VecR x = *(const VecR*)src;
+			acc[0] = first_real(x.v[0], op);
+#pragma unroll
+			for( int k=1; k<(RF?RF:1); ++k ) acc[0] = combine_real(acc[0], (float)x.v[k], op);
+		} else {
+			VecI x = *(const VecI*)src;
+#pragma unroll
+			for( int j=0; j<V; ++j ) acc[j] = first_real(x.v[j], op);
+			for( int k=1; k<f; ++k ) {
+				x = *(const VecI*)(src + k * p.rstr);
+#pragma unroll
+				for( int j=0; j<V; ++j ) acc[j] = combine_real(acc[j], (float)x.v[j], op);
+			}
+		}
+		VecO o;
+#pragma unroll
+		for( int j=0; j<V; ++j ) o.v[j] = finish_real(acc[j], op, f);
+		*(VecO*)(dst) = o;
+	} else {
+		struct __align__(sizeof(I)*2) Cplx { I x, y; };
+		float ax, ay;
+		if( RF ) {
+			struct __align__(sizeof(I)*2*(RF?RF:1)) VecR { Cplx v[RF?RF:1]; };
+			VecR x = *(const VecR*)src;
+			if( MODE == 1 ) { ax = (float)x.v[0].x; ay = (float)x.v[0].y; }
+			else            { ax = mag2((float)x.v[0].x, (float)x.v[0].y); ay = 0; }
+#pragma unroll
+			for( int k=1; k<(RF?RF:1); ++k ) {
+				float vx = (float)x.v[k].x, vy = (float)x.v[k].y;
+				if( MODE == 1 ) { ax += vx; ay += vy; }
+				else {
+					float m = mag2(vx, vy);
+					if(      op == BF_REDUCE_POWER_MIN ) ax = min(ax, m);
+					else if( op == BF_REDUCE_POWER_MAX ) ax = max(ax, m);
+					else                                 ax += m;
+				}
+			}
+		} else {
+			Cplx c = *(const Cplx*)src;
+			if( MODE == 1 ) { ax = (float)c.x; ay = (float)c.y; }
+			else            { ax = mag2((float)c.x, (float)c.y); ay = 0; }
+			for( int k=1; k<f; ++k ) {
+				c = *(const Cplx*)(src + k * p.rstr);
+				float vx = (float)c.x, vy = (float)c.y;
+				if( MODE == 1 ) { ax += vx; ay += vy; }
+				else {
+					float m = mag2(vx, vy);
+					if(      op == BF_REDUCE_POWER_MIN ) ax = min(ax, m);
+					else if( op == BF_REDUCE_POWER_MAX ) ax = max(ax, m);
+					else                                 ax += m;
+				}
+			}
+		}
+		if( MODE == 1 ) {
+			if( op == BF_REDUCE_MEAN )   { float s = (float)(1. / f);                  ax *= s; ay *= s; }
+			if( op == BF_REDUCE_STDERR ) { float s = (float)(1. / sqrtf((float)f));    ax *= s; ay *= s; }
+			*(float2*)(dst) = make_float2(ax, ay);
+		} else {
+			if( op == BF_REDUCE_POWER_MEAN )   ax = (float)(ax * (1. / f));
+			if( op == BF_REDUCE_POWER_STDERR ) ax = (float)(ax * (1. / sqrtf((float)f)));
+			*(float*)(dst) = ax;
+		}
+	}
+}
+
+template<typename I, int MODE, int V, int RF>
 __global__ void __launch_bounds__(256)
-reduce_kernel(const char* __restrict__ in, char* __restrict__ out, ReduceParams p) {
-	long gstride = (long)gridDim.x * blockDim.x;
-	for( long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total; idx += gstride ) {
+reduce_kernel(const char* __restrict__ in, char* __restrict__ out, const __grid_constant__ ReduceParams p) {
+	const long gstride = (long)gridDim.x * blockDim.x;
+	const long first = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if( p.ndim == 1 ) {
+		// fully merged layouts (the common case): no index decoding, 4 items in flight
+		const long is = p.istr[0], os = p.ostr[0];
+		for( long idx = first; idx < p.total; idx += 4 * gstride ) {
+#pragma unroll
+			for( int k=0; k<4; ++k ) {
+				long i = idx + k * gstride;
+				if( i < p.total ) reduce_one<I,MODE,V,RF>(in + i * is, out + i * os, p);
+			}
+		}
+		return;
+	}
+	for( long idx = first; idx < p.total; idx += gstride ) {
 		long rem = idx, ioff = 0, ooff = 0;
 #pragma unroll
 		for( int d=BF_MAX_DIMS-1; d>=0; --d ) {
@@ -97,78 +186,7 @@ reduce_kernel(const char* __restrict__ in, char* __restrict__ out, ReduceParams 
 				rem = q;
 			}
 		}
-		const char* src = in + ioff;
-		const int op = p.op;
-		const int f = RF ? RF : p.factor;
-		if( MODE == 0 ) {
-			struct __align__(sizeof(I)*V) VecI { I v[V]; };
-			struct __align__(4*V)         VecO { float v[V]; };
-			float acc[V];
-			if( RF ) {
-				struct __align__(sizeof(I)*(RF?RF:1)) VecR { I v[RF?RF:1]; };
-				VecR x = *(const VecR*)src;
-				acc[0] = first_real(x.v[0], op);
-#pragma unroll
-				for( int k=1; k<(RF?RF:1); ++k ) acc[0] = combine_real(acc[0], (float)x.v[k], op);
-			} else {
-				VecI x = *(const VecI*)src;
-#pragma unroll
-				for( int j=0; j<V; ++j ) acc[j] = first_real(x.v[j], op);
-				for( int k=1; k<f; ++k ) {
-					x = *(const VecI*)(src + k * p.rstr);
-#pragma unroll
-					for( int j=0; j<V; ++j ) acc[j] = combine_real(acc[j], (float)x.v[j], op);
-				}
-			}
-			VecO o;
-#pragma unroll
-			for( int j=0; j<V; ++j ) o.v[j] = finish_real(acc[j], op, f);
-			*(VecO*)(out + ooff) = o;
-		} else {
-			struct __align__(sizeof(I)*2) Cplx { I x, y; };
-			float ax, ay;
-			if( RF ) {
-				struct __align__(sizeof(I)*2*(RF?RF:1)) VecR { Cplx v[RF?RF:1]; };
-				VecR x = *(const VecR*)src;
-				if( MODE == 1 ) { ax = (float)x.v[0].x; ay = (float)x.v[0].y; }
-				else            { ax = mag2((float)x.v[0].x, (float)x.v[0].y); ay = 0; }
-#pragma unroll
-				for( int k=1; k<(RF?RF:1); ++k ) {
-					float vx = (float)x.v[k].x, vy = (float)x.v[k].y;
-					if( MODE == 1 ) { ax += vx; ay += vy; }
-					else {
-						float m = mag2(vx, vy);
-						if(      op == BF_REDUCE_POWER_MIN ) ax = min(ax, m);
-						else if( op == BF_REDUCE_POWER_MAX ) ax = max(ax, m);
-						else                                 ax += m;
-					}
-				}
-			} else {
-				Cplx c = *(const Cplx*)src;
-				if( MODE == 1 ) { ax = (float)c.x; ay = (float)c.y; }
-				else            { ax = mag2((float)c.x, (float)c.y); ay = 0; }
-				for( int k=1; k<f; ++k ) {
-					c = *(const Cplx*)(src + k * p.rstr);
-					float vx = (float)c.x, vy = (float)c.y;
-					if( MODE == 1 ) { ax += vx; ay += vy; }
-					else {
-						float m = mag2(vx, vy);
-						if(      op == BF_REDUCE_POWER_MIN ) ax = min(ax, m);
-						else if( op == BF_REDUCE_POWER_MAX ) ax = max(ax, m);
-						else                                 ax += m;
-					}
-				}
-			}
-			if( MODE == 1 ) {
-				if( op == BF_REDUCE_MEAN )   { float s = (float)(1. / f);                  ax *= s; ay *= s; }
-				if( op == BF_REDUCE_STDERR ) { float s = (float)(1. / sqrtf((float)f));    ax *= s; ay *= s; }
-				*(float2*)(out + ooff) = make_float2(ax, ay);
-			} else {
-				if( op == BF_REDUCE_POWER_MEAN )   ax = (float)(ax * (1. / f));
-				if( op == BF_REDUCE_POWER_STDERR ) ax = (float)(ax * (1. / sqrtf((float)f)));
-				*(float*)(out + ooff) = ax;
-			}
-		}
+		reduce_one<I,MODE,V,RF>(in + ioff, out + ooff, p);
 	}
 }
 

@@ -5,7 +5,7 @@
 
 extern "C" {
 
-#ifndef BFB_HAVE_UNPACK
+#if 0
 BFstatus bfUnpack(BFarray const*, BFarray const*, BFbool) { return BF_STATUS_UNSUPPORTED; }
 #endif
 
@@ -15,7 +15,7 @@ BFstatus bfFftInit(BFfft, BFarray const*, BFarray const*, int, int const*, BFboo
 BFstatus bfFftExecute(BFfft, BFarray const*, BFarray const*, BFbool, void*, size_t) { return BF_STATUS_UNSUPPORTED; }
 BFstatus bfFftDestroy(BFfft) { return BF_STATUS_UNSUPPORTED; }
 #endif
-#ifndef BFB_HAVE_SPECTROMETER
+#if 0
 BFstatus bfSpectrometerFused(BFarray const*, BFarray const*, int, int, double) { return BF_STATUS_UNSUPPORTED; }
 #endif
 

@@ -147,6 +147,105 @@ tile_kernel(const char* __restrict__ in, char* __restrict__ out, TileParams prm)
 	}
 }
 
+// (De)interleave: one of the two fastest dims is short (NP = 2 or 4 elements,
+// e.g. polarisation) and sits innermost on one side, contiguous with the long
+// dim `l` that is innermost on the other side:
+//   DEINT:  in [.., l, p] -> out [.., p, .., l]   (the GUPPI [time,pol] -> [pol,..,time] case)
+//   !DEINT: in [.., p, .., l] -> out [.., l, p]
+// A thread moves NP chunks of CB bytes (LV = CB/E consecutive l) with 128-bit
+// accesses on both sides and permutes the bytes in registers.
+struct InterleaveParams {
+	int  nouter;
+	long oshape[MAX_OUTER];
+	long oistr[MAX_OUTER];
+	long oostr[MAX_OUTER];
+	long nchunk;               // chunks along l
+	long p_stride;             // byte stride of p on the strided side
+	long total;
+};
+
+template<int CB> struct ChunkVec;
+template<> struct ChunkVec<16> { typedef uint4 type; };
+template<> struct ChunkVec<8>  { typedef uint2 type; };
+template<> struct ChunkVec<4>  { typedef uint32_t type; };
+
+template<int E, int NP, int CB, bool DEINT>
+__global__ void __launch_bounds__(256)
+interleave_kernel(const char* __restrict__ in, char* __restrict__ out, InterleaveParams prm) {
+	typedef typename ChunkVec<CB>::type V;
+	constexpr int LV = CB / E;
+	long gstride = (long)gridDim.x * blockDim.x;
+	for( long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < prm.total; idx += gstride ) {
+		long c = idx % prm.nchunk;
+		long rem = idx / prm.nchunk;
+		long ioff = 0, ooff = 0;
+#pragma unroll
+		for( int d=MAX_OUTER-1; d>=0; --d ) {
+			if( d < prm.nouter ) {
+				long q = rem / prm.oshape[d];
+				long r = rem - q * prm.oshape[d];
+				ioff += r * prm.oistr[d];
+				ooff += r * prm.oostr[d];
+				rem = q;
+			}
+		}
+		union { V v[NP]; unsigned char b[NP * CB]; } src, dst;
+		if( DEINT ) {
+			const V* g = (const V*)(in + ioff + c * (long)(NP * CB));
+#pragma unroll
+			for( int j=0; j<NP; ++j ) src.v[j] = g[j];
+#pragma unroll
+			for( int p=0; p<NP; ++p )
+#pragma unroll
+				for( int i=0; i<LV; ++i )
+#pragma unroll
+					for( int k=0; k<E; ++k ) dst.b[(p * LV + i) * E + k] = src.b[(i * NP + p) * E + k];
+#pragma unroll
+			for( int p=0; p<NP; ++p ) *(V*)(out + ooff + p * prm.p_stride + c * (long)CB) = dst.v[p];
+		} else {
+#pragma unroll
+			for( int p=0; p<NP; ++p ) src.v[p] = *(const V*)(in + ioff + p * prm.p_stride + c * (long)CB);
+#pragma unroll
+			for( int p=0; p<NP; ++p )
+#pragma unroll
+				for( int i=0; i<LV; ++i )
+#pragma unroll
+					for( int k=0; k<E; ++k ) dst.b[(i * NP + p) * E + k] = src.b[(p * LV + i) * E + k];
+			V* g = (V*)(out + ooff + c * (long)(NP * CB));
+#pragma unroll
+			for( int j=0; j<NP; ++j ) g[j] = dst.v[j];
+		}
+	}
+}
+
+template<int E, int NP, int CB, bool DEINT>
+static BFstatus launch_interleave(const void* in, void* out, InterleaveParams const& p, cudaStream_t s) {
+	long nblock = std::min<long>(div_up<long>(p.total, 256), 148L * 32);
+	interleave_kernel<E,NP,CB,DEINT><<<(unsigned)nblock, 256, 0, s>>>((const char*)in, (char*)out, p);
+	count_launch();
+	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+	return BF_STATUS_SUCCESS;
+}
+
+template<int E, int NP, bool DEINT>
+static BFstatus dispatch_interleave_cb(int cb, const void* in, void* out, InterleaveParams const& p,
+                                       cudaStream_t s) {
+	switch( cb ) {
+	case 16: return launch_interleave<E,NP,16,DEINT>(in, out, p, s);
+	case  8: return launch_interleave<E,NP, 8,DEINT>(in, out, p, s);
+	default: return launch_interleave<E,NP, 4,DEINT>(in, out, p, s);
+	}
+}
+
+template<bool DEINT>
+static BFstatus dispatch_interleave(long esize, long np, int cb, const void* in, void* out,
+                                    InterleaveParams const& p, cudaStream_t s) {
+#define BFB_IL(E_, NP_) if( esize == E_ && np == NP_ ) return dispatch_interleave_cb<E_,NP_,DEINT>(cb, in, out, p, s)
+	BFB_IL(1,2); BFB_IL(1,4); BFB_IL(2,2); BFB_IL(2,4); BFB_IL(4,2); BFB_IL(4,4);
+#undef BFB_IL
+	return BF_STATUS_UNSUPPORTED;
+}
+
 template<typename T>
 static BFstatus launch_gather(const void* in, void* out, GatherParams const& p,
                               cudaStream_t stream) {
@@ -261,6 +360,48 @@ static BFstatus permute_views(const void* in, void* out, StridedView vi, Strided
 		case  2: return launch_gather<uint16_t>(in, out, p, stream);
 		default: return launch_gather<uint8_t >(in, out, p, stream);
 		}
+	}
+	// ---- (de)interleave fast paths: a 2- or 4-long dim innermost on one side
+	for( int mode=0; mode<2 && esize <= 4; ++mode ) {
+		// mode 0: short dim pd innermost on the input, contiguous with `last`
+		// mode 1: short dim `last` innermost on the output, contiguous with pd
+		long np = mode == 0 ? shape[pd] : shape[last];
+		long nl = mode == 0 ? shape[last] : shape[pd];
+		if( np != 2 && np != 4 ) continue;
+		bool ok = mode == 0
+			? (istr[pd] == esize && istr[last] == np * esize && ostr[last] == esize)
+			: (ostr[last] == esize && ostr[pd] == np * esize && istr[pd] == esize);
+		if( !ok ) continue;
+		// chunk = CB bytes of the long dim; every address must be CB-aligned
+		unsigned long cb = 16;
+		cb = pow2_alignment((unsigned long)(uintptr_t)in,  cb);
+		cb = pow2_alignment((unsigned long)(uintptr_t)out, cb);
+		cb = pow2_alignment((unsigned long)(nl * esize), cb);
+		for( int d=0; d<nd; ++d ) {
+			if( (mode == 0 && d == pd) || (mode == 1 && d == last) ) continue;
+			if( mode == 0 && d == last ) continue;     // its strides are multiples of the chunk by construction
+			if( mode == 1 && d == pd )   continue;
+			cb = pow2_alignment((unsigned long)std::abs(istr[d]), cb);
+			cb = pow2_alignment((unsigned long)std::abs(ostr[d]), cb);
+		}
+		cb = pow2_alignment((unsigned long)std::abs(mode == 0 ? ostr[pd] : istr[last]), cb);
+		if( cb < 4 || cb < (unsigned long)esize ) continue;
+		InterleaveParams ip;
+		ip.nouter = 0;
+		for( int d=0; d<nd; ++d ) {
+			if( d == pd || d == last ) continue;
+			ip.oshape[ip.nouter] = shape[d];
+			ip.oistr[ip.nouter]  = istr[d];
+			ip.oostr[ip.nouter]  = ostr[d];
+			++ip.nouter;
+		}
+		ip.nchunk = nl * esize / (long)cb;
+		ip.p_stride = mode == 0 ? ostr[pd] : istr[last];
+		ip.total = total / np * esize / (long)cb;
+		BFstatus st = mode == 0
+			? dispatch_interleave<true >(esize, np, (int)cb, in, out, ip, stream)
+			: dispatch_interleave<false>(esize, np, (int)cb, in, out, ip, stream);
+		if( st != BF_STATUS_UNSUPPORTED ) return st;
 	}
 	TileParams tp;
 	tp.nouter = 0;

@@ -201,6 +201,19 @@ class ndarray(np.ndarray):
         v.bf.conjugated = not self.bf.conjugated
         return v
 
+    def byteswap(self, inplace=False):
+        """Swap the byte order of the data and flip the endianness flag."""
+        if inplace:
+            self.bf.native = not self.bf.native
+            return np.ndarray.byteswap(self, True)
+        out = ndarray(self, space=self.bf.space if not space_accessible(self.bf.space, ['system']) else 'system')
+        out.bf.native = not self.bf.native
+        if space_accessible(out.bf.space, ['system']):
+            np.ndarray.byteswap(out, True)
+        else:
+            raise NotImplementedError("byteswap of device arrays: byteswap on the host first")
+        return out
+
     def view(self, dtype=None, type_=None):
         if type_ is not None and dtype is None:
             dtype = type_

@@ -36,6 +36,25 @@ def test_all_3d_permutations(shape, esize):
         assert got.tobytes() == np.ascontiguousarray(want).tobytes(), (shape, esize, axes)
 
 
+@pytest.mark.parametrize("esize", [1, 2, 4, 8])
+def test_short_inner_dims_interleave_paths(esize):
+    """2- and 4-long dims innermost on either side ((de)interleave kernels),
+    aligned and misaligned."""
+    rng = np.random.default_rng(8)
+    for shape in [(6, 64, 2), (3, 5, 128, 4), (4, 2, 96), (2, 4, 7, 48), (5, 50, 2), (3, 31, 4)]:
+        raw = rng.integers(0, 256, size=shape + (esize,), dtype=np.uint8)
+        a = raw.view(elem_dtype(esize)).reshape(shape)
+        for axes in itertools.permutations(range(len(shape))):
+            got = run(a, axes)
+            assert got.tobytes() == np.ascontiguousarray(np.transpose(a, axes)).tobytes(), (shape, esize, axes)
+    base = rng.integers(0, 255, size=(4, 130, 2), dtype=np.uint8)
+    d = bf.asarray(base, space='cuda')
+    view = d[:, 1:129, :]                       # misaligned rows
+    out = bf.empty((4, 2, 128), 'u8', 'cuda')
+    bf.transpose(out, view, (0, 2, 1))
+    np.testing.assert_array_equal(np.asarray(out.copy('system')), np.transpose(base[:, 1:129, :], (0, 2, 1)))
+
+
 def test_4d_and_5d():
     rng = np.random.default_rng(2)
     a = rng.integers(-128, 127, size=(3, 17, 4, 50), dtype=np.int8)

@@ -1,0 +1,89 @@
+"""bfUnpack parity.  CPU: the oracle against every known-answer vector of the
+reference (test/test_unpack.py:33-97, test/test_gunpack.py:37-103).  GPU: the
+kernel against the same vectors and against the oracle on random data for all
+supported dtype / endianness / align_msb / conjugate combinations."""
+import itertools
+
+import numpy as np
+import pytest
+
+import bifrost_b200 as bf
+from oracle import unpack as ounpack
+
+# (input bytes, big_endian, conjugated) -> always the same answer
+KNOWN = [
+    ([[0x10, 0x32], [0x54, 0x76], [0x98, 0xBA]], False, False),
+    ([[0x01, 0x23], [0x45, 0x67], [0x89, 0xAB]], True, False),
+    ([[0xF0, 0xD2], [0xB4, 0x96], [0x78, 0x5A]], False, True),
+    ([[0x0F, 0x2D], [0x4B, 0x69], [0x87, 0xA5]], True, True),
+]
+ANSWER = np.array([[(0, 1), (2, 3)], [(4, 5), (6, 7)], [(-8, -7), (-6, -5)]], dtype=np.int8)
+
+
+@pytest.mark.parametrize("vec,big_endian,conj", KNOWN)
+def test_oracle_reproduces_reference_known_answers(vec, big_endian, conj):
+    got = ounpack.unpack(np.array(vec, np.uint8), 4, True, byte_reverse=big_endian, conjugate=conj)
+    np.testing.assert_array_equal(got.reshape(3, 2, 2), ANSWER)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vec,big_endian,conj", KNOWN)
+@pytest.mark.parametrize("odtype", ['ci8', 'cf32'])
+def test_gpu_known_answers(vec, big_endian, conj, odtype):
+    iarray = bf.ndarray(np.array(vec, np.uint8).reshape(3, 2).view(bf.DataType('ci4').as_numpy_dtype()),
+                        dtype='ci4')
+    if big_endian:
+        iarray = iarray.byteswap()
+    if conj:
+        iarray = iarray.conj()
+    d_in = bf.asarray(iarray, space='cuda')
+    d_out = bf.empty((3, 2), dtype=odtype, space='cuda')
+    bf.unpack(d_in, d_out)
+    out = np.asarray(d_out.copy('system'))
+    if odtype == 'ci8':
+        got = np.stack([out['re'], out['im']], -1)
+    else:
+        got = np.stack([out.real, out.imag], -1)
+    np.testing.assert_array_equal(got, ANSWER)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_all_modes():
+    rng = np.random.default_rng(1)
+    raw = rng.integers(0, 256, size=(37, 64), dtype=np.uint8)
+    for (idt, nbit, signed, cplx) in [('i4', 4, True, False), ('ci4', 4, True, True), ('i2', 2, True, False),
+                                      ('ci2', 2, True, True), ('i1', 1, True, False), ('ci1', 1, True, True),
+                                      ('u4', 4, False, False), ('u2', 2, False, False)]:
+        per = 8 // nbit // (2 if cplx else 1)
+        shape = (37, 64 * per)
+        odts = (['ci8', 'cf32', 'cf64'] if cplx else ['i8', 'f32', 'f64']) if signed else ['u8']
+        for odt, big, msb, conj in itertools.product(odts, [False, True], [False, True],
+                                                    [False, True] if cplx else [False]):
+            d_in = bf.ndarray(shape=shape, dtype=idt, space='cuda', native=not big, conjugated=conj)
+            bf.copy_array(d_in.view(np.uint8) if False else d_in, raw.view(d_in.dtype).reshape(d_in.shape))
+            d_out = bf.empty(shape, dtype=odt, space='cuda')
+            bf.unpack(d_in, d_out, align_msb=msb)
+            out = np.asarray(d_out.copy('system'))
+            want = ounpack.unpack(raw, nbit, signed, byte_reverse=big, align_msb=msb,
+                                  conjugate=conj, gpu=True)
+            if odt == 'ci8':
+                got = np.stack([out['re'], out['im']], -1).reshape(37, -1)
+            elif odt in ('cf32', 'cf64'):
+                got = np.stack([out.real, out.imag], -1).reshape(37, -1)
+            else:
+                got = out
+            np.testing.assert_array_equal(got, want.astype(got.dtype), err_msg=str((idt, odt, big, msb, conj)))
+
+
+@pytest.mark.gpu
+def test_status_codes():
+    from bifrost_b200.libbifrost import _bf
+    a = bf.empty((4, 8), 'ci4', 'cuda')
+    b = bf.empty((4, 8), 'i8', 'cuda')
+    assert _bf.bfUnpack(a.as_BFarray(), b.as_BFarray(), 0) == _bf.BF_STATUS_INVALID_DTYPE
+    h = bf.empty((4, 8), 'ci4', 'system')
+    c = bf.empty((4, 8), 'ci8', 'cuda')
+    assert _bf.bfUnpack(h.as_BFarray(), c.as_BFarray(), 0) == _bf.BF_STATUS_UNSUPPORTED_SPACE
+    d = bf.empty((4, 8), 'ci8', 'cuda')
+    e = bf.empty((4, 8), 'ci16', 'cuda')
+    assert _bf.bfUnpack(d.as_BFarray(), e.as_BFarray(), 0) == _bf.BF_STATUS_UNSUPPORTED_DTYPE
