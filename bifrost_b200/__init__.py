@@ -19,6 +19,9 @@ from bifrost_b200.transpose import transpose
 from bifrost_b200.unpack import unpack
 from bifrost_b200.map import map, detect, accumulate
 from bifrost_b200.spectrometer import spectrometer
+from bifrost_b200 import views
+from bifrost_b200 import blocks
+from bifrost_b200.pipeline import Pipeline, get_default_pipeline, block_scope, block_view
 
 __version__ = '0.1.0'
 

@@ -1,0 +1,154 @@
+"""Host-side logic of the block executor on CPU (system space): gulping with
+mismatched sizes, input overlap, rare commits, header views -- the behaviours
+the hot-path blocks rely on (reference: test/test_pipeline_cpu.py patterns)."""
+from copy import deepcopy
+
+import numpy as np
+
+import bifrost_b200 as bf
+from bifrost_b200.pipeline import TransformBlock, Pipeline
+from bifrost_b200.blocks import array_source, callback_sink, copy
+
+
+def header(shape, dtype='f32', labels=None):
+    nd = len(shape)
+    return {'_tensor': {'dtype': dtype, 'shape': list(shape),
+                        'labels': labels or ['time'] + ['d%i' % i for i in range(1, nd)],
+                        'scales': [[0, 1.0] for _ in range(nd)],
+                        'units': ['s'] + [None] * (nd - 1)},
+            'name': 'test', 'gulp_nframe': 1}
+
+
+class Collect(object):
+    def __init__(self):
+        self.chunks, self.headers = [], []
+
+    def seq(self, iseq):
+        self.headers.append(deepcopy(iseq.header))
+
+    def data(self, ispan):
+        self.chunks.append(np.array(ispan.data.copy('system')))
+
+
+def test_copy_chain_with_mixed_gulp_sizes():
+    data = np.arange(50 * 3, dtype=np.float32).reshape(50, 3)
+    out = Collect()
+    with Pipeline() as p:
+        src = array_source(data, header([-1, 3]), gulp_nframe=7)
+        b = copy(src, gulp_nframe=4)
+        b = copy(b, gulp_nframe=9)
+        callback_sink(b, out.seq, out.data, gulp_nframe=5)
+        p.run()
+    got = np.concatenate(out.chunks, axis=0)
+    np.testing.assert_array_equal(got, data)
+    assert out.headers[0]['_tensor']['shape'] == [-1, 3]
+
+
+class MovingSum(TransformBlock):
+    """Needs `overlap` frames of history, like FdmtBlock (blocks/fdmt.py:112-124)."""
+    overlap = 3
+
+    def on_sequence(self, iseq):
+        return deepcopy(iseq.header)
+
+    def define_input_overlap_nframe(self, iseq):
+        return self.overlap
+
+    def on_data(self, ispan, ospan):
+        if ispan.nframe <= self.overlap:
+            return 0
+        x = np.asarray(ispan.data)
+        y = np.asarray(ospan.data)
+        n = ispan.nframe - self.overlap
+        for k in range(n):
+            y[k] = x[k:k + self.overlap + 1].sum(axis=0)
+
+
+def test_input_overlap_is_re_presented():
+    data = np.arange(40, dtype=np.float32).reshape(40, 1)
+    out = Collect()
+    with Pipeline() as p:
+        src = array_source(data, header([-1, 1]), gulp_nframe=8)
+        b = MovingSum(src, gulp_nframe=8)
+        callback_sink(b, out.seq, out.data)
+        p.run()
+    got = np.concatenate(out.chunks, axis=0)[:, 0]
+    want = np.array([data[k:k + 4, 0].sum() for k in range(40 - 3)])
+    np.testing.assert_array_equal(got[:len(want)], want)
+
+
+class EveryN(TransformBlock):
+    """Commits one frame every n inputs, like AccumulateBlock."""
+
+    def __init__(self, iring, n):
+        super(EveryN, self).__init__(iring, gulp_nframe=1)
+        self.n = n
+
+    def on_sequence(self, iseq):
+        self.count = 0
+        return deepcopy(iseq.header)
+
+    def on_data(self, ispan, ospan):
+        x, y = np.asarray(ispan.data), np.asarray(ospan.data)
+        if self.count == 0:
+            y[...] = x
+        else:
+            y[...] = y + x
+        self.count += 1
+        if self.count == self.n:
+            self.count = 0
+            return 1
+        return 0
+
+
+def test_rare_commits_accumulate_into_the_same_span():
+    data = np.ones((24, 2), np.float32) * np.arange(24)[:, None]
+    out = Collect()
+    with Pipeline() as p:
+        src = array_source(data, header([-1, 2]), gulp_nframe=5)
+        b = EveryN(src, 8)
+        callback_sink(b, out.seq, out.data)
+        p.run()
+    got = np.concatenate(out.chunks, axis=0)
+    want = data.reshape(3, 8, 2).sum(axis=1)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_views_rewrite_headers_without_moving_data():
+    data = np.arange(6 * 4 * 8, dtype=np.float32).reshape(6, 4, 8)
+    hdr = header([-1, 4, 8], labels=['time', 'freq', 'fine'])
+    hdr['_tensor']['scales'] = [[0, 1.0], [100.0, 8.0], [0.0, 1.0]]
+    hdr['_tensor']['units'] = ['s', 'MHz', 'MHz']
+    out = Collect()
+    with Pipeline() as p:
+        src = array_source(data, hdr, gulp_nframe=2)
+        v = bf.views.merge_axes(src, 'freq', 'fine', label='freq')
+        v = bf.views.rename_axis(v, 'freq', 'chan')
+        callback_sink(v, out.seq, out.data)
+        p.run()
+    t = out.headers[0]['_tensor']
+    assert t['shape'] == [-1, 32] and t['labels'] == ['time', 'chan'] and t['scales'][1] == [100.0, 1.0]
+    np.testing.assert_array_equal(np.concatenate(out.chunks, 0), data.reshape(6, 32))
+    out2 = Collect()
+    with Pipeline() as p:
+        src = array_source(data, hdr, gulp_nframe=3)
+        v = bf.views.split_axis(src, 'fine', 2, label='half')
+        callback_sink(v, out2.seq, out2.data)
+        p.run()
+    assert out2.headers[0]['_tensor']['shape'] == [-1, 4, 4, 2]
+    np.testing.assert_array_equal(np.concatenate(out2.chunks, 0), data.reshape(6, 4, 4, 2))
+
+
+def test_block_scope_and_space_validation():
+    data = np.zeros((4, 2), np.float32)
+    with Pipeline() as p:
+        with bf.block_scope(gulp_nframe=2, fuse=True):
+            src = array_source(data, header([-1, 2]), gulp_nframe=2)
+            b = bf.blocks.reduce(src, 'd1', 2)            # needs cuda space
+            assert b.gulp_nframe == 2 and b.fuse
+        try:
+            p.run()
+        except ValueError as e:
+            assert 'space' in str(e)
+        else:
+            raise AssertionError("system-space input to a cuda-only block must be rejected")
