@@ -1,0 +1,493 @@
+// linalg.cu -- bfLinAlg* for sm_100a: the cross-correlation ("X-engine") call
+// behind bf.blocks.correlate.
+//
+// Replaces: src/linalg.cu:877-904 (bfLinAlgMatMul), :242-357 (bfMatMul_aa),
+// :190-226 (dispatch to the xGPU-style kernel) and
+// src/linalg_kernels.cu:154-643 (bf_cherk_N diagonal/off-diagonal kernels).
+//
+// Semantics kept: with u = b (b^H.b form) or u(t,i) = conj(a[i][t]) (a.a^H form)
+//   c[..., i, j] = alpha * sum_t conj(u[t][i]) * u[t][j] + beta * c[..., i, j]   for i >= j
+// and every element above the diagonal is left untouched
+// (python/bifrost/blocks/correlate.py:69, test/test_pipeline.py:258-298,
+// test/test_linalg.py:168-185).  Integer inputs accumulate exactly in int32.
+//
+// Two kernels:
+//  * corr_tc_kernel -- tcgen05 int8 tensor cores.  The interleaved complex
+//    samples of one frequency channel form a real row-major matrix
+//    M[t][2i+p] (p = re/im).  Its Gram matrix G = M^T M holds all four real
+//    products of every pair: Re C_ij = G[2i][2j] + G[2i+1][2j+1],
+//    Im C_ij = G[2i][2j+1] - G[2i+1][2j].  Time (the reduction dim) is the slow
+//    axis in memory, i.e. both MMA operands are MN-major: TMA drops
+//    [64 t][128 B] boxes with the 128-byte swizzle straight into the canonical
+//    MN-major UMMA layout, one elected thread issues
+//    tcgen05.mma.kind::i8 (M=128, N=128, K=32) into a TMEM accumulator, and four
+//    epilogue warps pull the int32 tile out of TMEM, pair rows with a lane
+//    shuffle, and write the lower-triangular cf32 tile through shared memory
+//    so that global stores are row-contiguous.  Only tiles on or below the
+//    diagonal are launched; diagonal tiles load one operand.
+//  * corr_simt_kernel -- shared-memory tiled SIMT fallback for layouts TMA
+//    cannot describe (strides not multiples of 16 B, a.a^H form, ci16/cf32).
+#include "core.hpp"
+#include "shape.hpp"
+
+#include <cuda.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace bfb {
+
+// =============================================================== SIMT fallback
+struct SimtParams {
+	const char* u;           // element (t, i) at u + t*stride_t + i*stride_i (bytes)
+	long  stride_t, stride_i, stride_b;
+	float2* c; long c_row, c_batch;      // float2 units
+	int   n, ntime, nbatch;
+	float alpha, beta;
+	int   conj_u;            // u = conj(memory)
+};
+
+template<typename I> struct CIn { I x, y; };
+
+template<typename I, typename Acc>
+__global__ void __launch_bounds__(256)
+corr_simt_kernel(SimtParams P) {
+	// 32x32 output tile per CTA, 16x16 threads, 2x2 outputs per thread
+	__shared__ float2 su_i[32][33];
+	__shared__ float2 su_j[32][33];
+	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+	const int ntile = (P.n + 31) / 32;
+	int tile = blockIdx.x;
+	// lower-triangular tile index -> (ti, tj), ti >= tj
+	int ti = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+	while( ti * (ti + 1) / 2 > tile ) --ti;
+	while( (ti + 1) * (ti + 2) / 2 <= tile ) ++ti;
+	int tj = tile - ti * (ti + 1) / 2;
+	(void)ntile;
+	const int b = blockIdx.y;
+	const char* ub = P.u + (long)b * P.stride_b;
+	Acc re[2][2] = {{0, 0}, {0, 0}}, im[2][2] = {{0, 0}, {0, 0}};
+	for( int t0 = 0; t0 < P.ntime; t0 += 32 ) {
+		// stage 32 time samples of the i-block and the j-block
+		for( int k = threadIdx.x; k < 32 * 32; k += 256 ) {
+			int tt = k >> 5, ii = k & 31;
+			int t = t0 + tt;
+			float2 vi = make_float2(0.f, 0.f), vj = make_float2(0.f, 0.f);
+			if( t < P.ntime ) {
+				int gi = ti * 32 + ii, gj = tj * 32 + ii;
+				if( gi < P.n ) {
+					CIn<I> v = *(const CIn<I>*)(ub + (long)t * P.stride_t + (long)gi * P.stride_i);
+					vi = make_float2((float)v.x, (float)v.y);
+				}
+				if( gj < P.n ) {
+					CIn<I> v = *(const CIn<I>*)(ub + (long)t * P.stride_t + (long)gj * P.stride_i);
+					vj = make_float2((float)v.x, (float)v.y);
+				}
+			}
+			su_i[tt][ii] = vi; su_j[tt][ii] = vj;
+		}
+		__syncthreads();
+#pragma unroll 4
+		for( int tt = 0; tt < 32; ++tt ) {
+			float2 a[2] = {su_i[tt][ty], su_i[tt][ty + 16]};
+			float2 c[2] = {su_j[tt][tx], su_j[tt][tx + 16]};
+#pragma unroll
+			for( int p=0; p<2; ++p )
+#pragma unroll
+				for( int q=0; q<2; ++q ) {
+					// conj(u_i) * u_j
+					re[p][q] += (Acc)a[p].x * (Acc)c[q].x + (Acc)a[p].y * (Acc)c[q].y;
+					im[p][q] += (Acc)a[p].x * (Acc)c[q].y - (Acc)a[p].y * (Acc)c[q].x;
+				}
+		}
+		__syncthreads();
+	}
+	float2* cb = P.c + (long)b * P.c_batch;
+#pragma unroll
+	for( int p=0; p<2; ++p )
+#pragma unroll
+		for( int q=0; q<2; ++q ) {
+			int i = ti * 32 + ty + 16 * p, j = tj * 32 + tx + 16 * q;
+			if( i < P.n && j < P.n && i >= j ) {
+				float vr = (float)re[p][q], vi = (float)im[p][q];
+				if( P.conj_u ) vi = -vi;
+				float2* dst = cb + (long)i * P.c_row + j;
+				float2 o = make_float2(P.alpha * vr, P.alpha * vi);
+				if( P.beta != 0.f ) { float2 old = *dst; o.x += P.beta * old.x; o.y += P.beta * old.y; }
+				*dst = o;
+			}
+		}
+}
+
+// ============================================================ tcgen05 kernel
+enum { TC_KT = 64, TC_STAGES = 4, TC_TILE_BYTES = TC_KT * 128, TC_THREADS = 192 };
+
+struct TcParams {
+	float2* c; long c_row, c_batch;      // float2 units
+	int   n;                 // complex elements per time sample
+	int   ntime;
+	int   ntile;             // lower-triangular 128x128 tiles per batch
+	float alpha, beta;
+	int   conj_u;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAIT_LOOP:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra DONE;\n\t"
+		"bra WAIT_LOOP;\n\t"
+		"DONE:\n\t}"
+		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int x, int y, int z) {
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+		" [%0], [%1, {%3, %4, %5}], [%2];"
+		:: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+// 64-bit shared-memory matrix descriptor: MN-major, 128-byte swizzle, one
+// 128-byte atom wide; 8-row groups are 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+	uint64_t d = 0;
+	d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+	d |= (uint64_t)(1024 >> 4) << 16;                 // leading byte offset (unused: single atom in MN)
+	d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups
+	d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+	d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+	return d;
+}
+// Instruction descriptor: S32 accumulate, signed int8 A and B, both MN-major,
+// M = 128, N = 128.
+__device__ __forceinline__ uint32_t umma_idesc_i8_128x128() {
+	uint32_t d = 0;
+	d |= 2u << 4;            // c_format = S32
+	d |= 1u << 7;            // a_format = INT8 (signed)
+	d |= 1u << 10;           // b_format = INT8 (signed)
+	d |= 1u << 15;           // a_major = MN
+	d |= 1u << 16;           // b_major = MN
+	d |= (128u >> 3) << 17;  // n_dim
+	d |= (128u >> 4) << 24;  // m_dim
+	return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS)
+corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
+	extern __shared__ __align__(1024) unsigned char tc_smem[];
+	// layout: [stages][A 8 KB | B 8 KB] | staging float2[64][65] | barriers
+	// the swizzled operand tiles need 1024-byte alignment in the shared window
+	unsigned char* tiles = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
+	float2* staging = (float2*)(tiles + TC_STAGES * 2 * TC_TILE_BYTES);
+	uint64_t* full_bar  = (uint64_t*)(staging + 64 * 65);
+	uint64_t* empty_bar = full_bar + TC_STAGES;
+	uint64_t* tmem_bar  = empty_bar + TC_STAGES;
+	uint32_t* tmem_slot = (uint32_t*)(tmem_bar + 1);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int batch = blockIdx.y;
+	// lower-triangular tile index -> (I, J), I >= J
+	int tile = blockIdx.x;
+	int I = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+	while( I * (I + 1) / 2 > tile ) --I;
+	while( (I + 1) * (I + 2) / 2 <= tile ) ++I;
+	const int J = tile - I * (I + 1) / 2;
+	const bool diag = (I == J);
+	const int nk = (P.ntime + TC_KT - 1) / TC_KT;
+
+	if( threadIdx.x == 0 ) {
+		for( int s=0; s<TC_STAGES; ++s ) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+		mbar_init(tmem_bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if( warp == 1 ) {
+		// allocate 128 TMEM columns (power of two >= 32); the address lands in smem
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+		             :: "r"(smem_u32(tmem_slot)), "n"(128));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const uint32_t tmem_base = *tmem_slot;
+
+	if( warp == 0 ) {
+		// ===================== TMA producer =====================
+		if( lane == 0 ) {
+			for( int it=0; it<nk; ++it ) {
+				const int s = it % TC_STAGES;
+				const uint32_t ph = (it / TC_STAGES) & 1;
+				mbar_wait(&empty_bar[s], ph ^ 1);
+				unsigned char* a = tiles + (size_t)s * 2 * TC_TILE_BYTES;
+				mbar_expect_tx(&full_bar[s], diag ? TC_TILE_BYTES : 2 * TC_TILE_BYTES);
+				tma_load_3d(a, &tmap, &full_bar[s], 128 * I, it * TC_KT, batch);
+				if( !diag ) tma_load_3d(a + TC_TILE_BYTES, &tmap, &full_bar[s], 128 * J, it * TC_KT, batch);
+			}
+		}
+	} else if( warp == 1 ) {
+		// ===================== MMA issuer =====================
+		const uint32_t idesc = umma_idesc_i8_128x128();
+		for( int it=0; it<nk; ++it ) {
+			const int s = it % TC_STAGES;
+			const uint32_t ph = (it / TC_STAGES) & 1;
+			mbar_wait(&full_bar[s], ph);
+			asm volatile("tcgen05.fence::after_thread_sync;");
+			if( lane == 0 ) {
+				const uint32_t a_addr = smem_u32(tiles + (size_t)s * 2 * TC_TILE_BYTES);
+				const uint32_t b_addr = diag ? a_addr : a_addr + TC_TILE_BYTES;
+#pragma unroll
+				for( int kk=0; kk<TC_KT/32; ++kk ) {
+					const uint64_t da = umma_desc_mn_sw128(a_addr + kk * 32 * 128);
+					const uint64_t db = umma_desc_mn_sw128(b_addr + kk * 32 * 128);
+					const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+					asm volatile(
+						"{\n\t.reg .pred p;\n\t"
+						"setp.ne.b32 p, %4, 0;\n\t"
+						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+						:: "r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+				}
+				// release the smem stage once these MMAs have consumed it
+				asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+				             :: "r"(smem_u32(&empty_bar[s])) : "memory");
+				if( it == nk - 1 ) {
+					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+					             :: "r"(smem_u32(tmem_bar)) : "memory");
+				}
+			}
+			__syncwarp();
+		}
+	} else {
+		// ===================== epilogue (warps 2..5) =====================
+		mbar_wait(tmem_bar, 0);
+		asm volatile("tcgen05.fence::after_thread_sync;");
+		const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+		const int m = quarter * 32 + lane;                  // row of the 128x128 int32 tile
+		const int il = m >> 1, par = m & 1;                 // complex row, re/im row of the pair
+		float* stf = (float*)staging;
+#pragma unroll 1
+		for( int c0=0; c0<128; c0+=32 ) {
+			uint32_t r[32];
+			const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+			asm volatile(
+				"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+				"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+				"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+				: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+				  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+				  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+				  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+				: "r"(taddr));
+			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+			for( int q=0; q<16; ++q ) {
+				// even row 2i holds (G[2i][2j], G[2i][2j+1]); odd row holds
+				// (G[2i+1][2j], G[2i+1][2j+1]); swap the second entries.
+				int mine0 = (int)r[2*q], mine1 = (int)r[2*q+1];
+				int other1 = __shfl_xor_sync(0xffffffffu, mine1, 1);
+				// even lane: Re = G[2i][2j] + G[2i+1][2j+1]; odd lane: Im = G[2i][2j+1] - G[2i+1][2j]
+				int v = par ? (other1 - mine0) : (mine0 + other1);
+				int jl = (c0 >> 1) + q;
+				stf[(il * 65 + jl) * 2 + par] = (float)v;
+			}
+		}
+		// all four epilogue warps have staged their rows
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+		const int te = threadIdx.x - 64;                    // 0..127
+		float2* cb = P.c + (long)batch * P.c_batch;
+		for( int idx = te; idx < 64 * 64; idx += 128 ) {
+			int il2 = idx >> 6, jl2 = idx & 63;
+			int i = I * 64 + il2, j = J * 64 + jl2;
+			if( i < P.n && j < P.n && i >= j ) {
+				float2 v = staging[il2 * 65 + jl2];
+				if( P.conj_u ) v.y = -v.y;
+				float2 o = make_float2(P.alpha * v.x, P.alpha * v.y);
+				float2* dst = cb + (long)i * P.c_row + j;
+				if( P.beta != 0.f ) { float2 old = *dst; o.x += P.beta * old.x; o.y += P.beta * old.y; }
+				*dst = o;
+			}
+		}
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	if( warp == 1 ) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
+	}
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+	static PFN_encodeTiled fn = nullptr;
+	static bool tried = false;
+	if( !tried ) {
+		tried = true;
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if( cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+		    qres == cudaDriverEntryPointSuccess ) {
+			fn = (PFN_encodeTiled)p;
+		}
+	}
+	return fn;
+}
+
+} // namespace bfb
+
+using namespace bfb;
+
+struct BFlinalg_impl {
+	int dummy = 0;
+};
+
+namespace {
+
+// c[..,i,j] = alpha sum_t conj(u(t,i)) u(t,j) + beta c, lower triangle.
+// u(t,i) lives at data + t*stride_t + i*stride_i (+ batch offsets).
+BFstatus correlate(BFdtype utype, const void* udata, long stride_t, long stride_i,
+                   int conj_u, long n, long ntime,
+                   int nbdim, const long* bshape, const long* ustr, const long* cstr,
+                   void* cdata, long c_row_bytes, double alpha, double beta, cudaStream_t st) {
+	if( n == 0 ) return BF_STATUS_SUCCESS;
+	BFB_ASSERT(c_row_bytes % 8 == 0, BF_STATUS_UNSUPPORTED_STRIDE);
+	// Kernel batch = innermost batch dim; outer batch dims are looped on the host.
+	long kb = 1, kb_ustr = 0, kb_cstr = 0;
+	int kdim = -1;
+	for( int d=0; d<nbdim; ++d ) if( bshape[d] >= kb ) { kb = bshape[d]; kdim = d; }
+	if( kdim >= 0 ) { kb_ustr = ustr[kdim]; kb_cstr = cstr[kdim]; BFB_ASSERT(kb_cstr % 8 == 0, BF_STATUS_UNSUPPORTED_STRIDE); }
+	BFB_ASSERT(kb <= 65535, BF_STATUS_UNSUPPORTED_SHAPE);
+	long nouter = 1;
+	for( int d=0; d<nbdim; ++d ) if( d != kdim ) nouter *= bshape[d];
+	bool tc_ok = utype == BF_DTYPE_CI8 && stride_i == 2 && stride_t % 16 == 0 &&
+	             (kb == 1 || (kb_ustr % 16 == 0 && kb_ustr >= 16)) && n >= 16 && ntime >= 1 &&
+	             ntime * 2L * 127 * 127 < (1L << 31) && get_encode_fn() != nullptr &&
+	             getenv("BFB_LINALG_SIMT") == nullptr;
+	for( long o=0; o<nouter; ++o ) {
+		long rem = o, uoff = 0, coff = 0;
+		for( int d=nbdim-1; d>=0; --d ) {
+			if( d == kdim ) continue;
+			long r = rem % bshape[d]; rem /= bshape[d];
+			uoff += r * ustr[d]; coff += r * cstr[d];
+		}
+		const char* ub = (const char*)udata + uoff;
+		float2* cb = (float2*)((char*)cdata + coff);
+		bool use_tc = tc_ok && ((uintptr_t)ub % 16 == 0);
+		if( use_tc ) {
+			CUtensorMap tmap;
+			cuuint64_t gdim[3] = {(cuuint64_t)(2 * n), (cuuint64_t)ntime, (cuuint64_t)kb};
+			cuuint64_t gstr[2] = {(cuuint64_t)stride_t, (cuuint64_t)(kb > 1 ? kb_ustr : stride_t * ntime)};
+			if( gstr[1] % 16 ) gstr[1] = round_up<cuuint64_t>(gstr[1], 16);
+			cuuint32_t box[3] = {128, TC_KT, 1};
+			cuuint32_t estr[3] = {1, 1, 1};
+			CUresult res = get_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)ub, gdim, gstr,
+			                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+			                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			if( res != CUDA_SUCCESS ) use_tc = false;
+			if( use_tc ) {
+				TcParams P;
+				P.c = cb; P.c_row = c_row_bytes / 8; P.c_batch = kb_cstr / 8;
+				P.n = (int)n; P.ntime = (int)ntime;
+				int T = (int)div_up<long>(2 * n, 128);
+				P.ntile = T * (T + 1) / 2;
+				P.alpha = (float)alpha; P.beta = (float)beta; P.conj_u = conj_u;
+				size_t smem = (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 64 * 65 * sizeof(float2) +
+				              (2 * TC_STAGES + 1) * sizeof(uint64_t) + 16;
+				smem += 1024;   // room for the 1024-byte alignment of the dynamic window
+				BFB_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				                              (int)smem), BF_STATUS_INTERNAL_ERROR);
+				dim3 grid(P.ntile, (unsigned)kb);
+				corr_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, P);
+				count_launch();
+				BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+				continue;
+			}
+		}
+		SimtParams S;
+		S.u = ub; S.stride_t = stride_t; S.stride_i = stride_i; S.stride_b = kb_ustr;
+		S.c = cb; S.c_row = c_row_bytes / 8; S.c_batch = kb_cstr / 8;
+		S.n = (int)n; S.ntime = (int)ntime; S.nbatch = (int)kb;
+		S.alpha = (float)alpha; S.beta = (float)beta; S.conj_u = conj_u;
+		int T = (int)div_up<long>(n, 32);
+		dim3 grid(T * (T + 1) / 2, (unsigned)kb);
+		switch( utype ) {
+		case BF_DTYPE_CI8:  corr_simt_kernel<int8_t, int><<<grid, 256, 0, st>>>(S); break;
+		case BF_DTYPE_CI16: corr_simt_kernel<int16_t, float><<<grid, 256, 0, st>>>(S); break;
+		case BF_DTYPE_CF32: corr_simt_kernel<float, float><<<grid, 256, 0, st>>>(S); break;
+		default: BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
+		}
+		count_launch();
+		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+	}
+	return BF_STATUS_SUCCESS;
+}
+
+} // namespace
+
+extern "C" {
+
+BFstatus bfLinAlgCreate(BFlinalg* handle_ptr) {
+	BFB_ASSERT(handle_ptr, BF_STATUS_INVALID_POINTER);
+	*handle_ptr = nullptr;
+	BFB_TRY(*handle_ptr = new BFlinalg_impl());
+	return BF_STATUS_SUCCESS;
+}
+
+BFstatus bfLinAlgDestroy(BFlinalg handle) {
+	BFB_ASSERT(handle, BF_STATUS_INVALID_HANDLE);
+	delete handle;
+	return BF_STATUS_SUCCESS;
+}
+
+BFstatus bfLinAlgMatMul(BFlinalg handle, double alpha, BFarray const* a, BFarray const* b,
+                        double beta, BFarray const* c) {
+	BFB_ASSERT(handle, BF_STATUS_INVALID_HANDLE);
+	BFB_ASSERT(a || b, BF_STATUS_INVALID_ARGUMENT);
+	BFB_ASSERT(c, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(space_on_device(c->space), BF_STATUS_UNSUPPORTED_SPACE);
+	// General a.b products are cuBLAS calls in the reference
+	// (src/linalg.cu:479-637) and are not part of this build's hot path.
+	BFB_ASSERT(!(a && b), BF_STATUS_UNSUPPORTED);
+	BFarray const* x = a ? a : b;
+	BFB_ASSERT(space_on_device(x->space), BF_STATUS_UNSUPPORTED_SPACE);
+	BFB_ASSERT(x->ndim == c->ndim && x->ndim >= 2 && x->ndim <= BF_MAX_DIMS, BF_STATUS_INVALID_SHAPE);
+	BFB_ASSERT(c->dtype == BF_DTYPE_CF32, BF_STATUS_UNSUPPORTED_DTYPE);
+	BFB_ASSERT(x->dtype == BF_DTYPE_CI8 || x->dtype == BF_DTYPE_CI16 || x->dtype == BF_DTYPE_CF32,
+	           BF_STATUS_UNSUPPORTED_DTYPE);
+	int nd = x->ndim;
+	// b^H.b: x is [.., t, i];  a.a^H: x is [.., i, t] and u(t,i) = conj(a[i][t])
+	long n      = a ? x->shape[nd-2] : x->shape[nd-1];
+	long ntime  = a ? x->shape[nd-1] : x->shape[nd-2];
+	long str_i  = a ? x->strides[nd-2] : x->strides[nd-1];
+	long str_t  = a ? x->strides[nd-1] : x->strides[nd-2];
+	int  conj_u = (a ? 1 : 0) ^ (x->conjugated ? 1 : 0);
+	BFB_ASSERT(c->shape[nd-1] == n && c->shape[nd-2] == n, BF_STATUS_INVALID_SHAPE);
+	BFB_ASSERT(c->strides[nd-1] == 8, BF_STATUS_UNSUPPORTED_STRIDE);
+	long bshape[BF_MAX_DIMS], ustr[BF_MAX_DIMS], cstr[BF_MAX_DIMS];
+	int nb = 0;
+	for( int d=0; d<nd-2; ++d ) {
+		BFB_ASSERT(x->shape[d] == c->shape[d] || x->shape[d] == 1, BF_STATUS_INVALID_SHAPE);
+		if( c->shape[d] == 1 ) continue;
+		bshape[nb] = c->shape[d];
+		ustr[nb] = x->shape[d] == 1 ? 0 : x->strides[d];     // broadcast
+		cstr[nb] = c->strides[d];
+		++nb;
+	}
+	BFB_TRY(return correlate(x->dtype, x->data, str_t, str_i, conj_u, n, ntime, nb, bshape, ustr, cstr,
+	                         c->data, c->strides[nd-2], alpha, beta, thread_stream()));
+}
+
+} // extern "C"

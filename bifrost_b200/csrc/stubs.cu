@@ -19,7 +19,7 @@ BFstatus bfFftDestroy(BFfft) { return BF_STATUS_UNSUPPORTED; }
 BFstatus bfSpectrometerFused(BFarray const*, BFarray const*, int, int, double) { return BF_STATUS_UNSUPPORTED; }
 #endif
 
-#ifndef BFB_HAVE_LINALG
+#if 0
 BFstatus bfLinAlgCreate(BFlinalg* h) { if( h ) *h = nullptr; return BF_STATUS_UNSUPPORTED; }
 BFstatus bfLinAlgDestroy(BFlinalg) { return BF_STATUS_UNSUPPORTED; }
 BFstatus bfLinAlgMatMul(BFlinalg, double, BFarray const*, BFarray const*, double, BFarray const*) { return BF_STATUS_UNSUPPORTED; }

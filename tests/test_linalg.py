@@ -1,0 +1,180 @@
+"""bfLinAlgMatMul (correlator forms) parity.  CPU: the oracle against the
+closed-form case of the reference's pipeline test (test/test_pipeline.py:66-72,
+258-298).  GPU: tensor-core path and SIMT fallback against the oracle --
+integer-exact -- over the sweep of test/test_linalg.py:221-240 (odd sizes,
+misaligned views) and BASELINE config 4 shapes; upper triangle untouched;
+beta accumulation; a.a^H form."""
+import os
+
+import numpy as np
+import pytest
+
+import bifrost_b200 as bf
+from bifrost_b200.linalg import LinAlg
+from oracle import linalg as olinalg
+
+CI8 = bf.DataType('ci8').as_numpy_dtype()
+
+
+def closed_form_input(ntime, nchan, nstand, npol):
+    """CorrelateTestInputBlock of the reference (test/test_pipeline.py:66-72)."""
+    i = np.arange(nstand * npol * 2) % 255 - 127
+    x = np.empty((ntime, nchan, nstand * npol), dtype=CI8)
+    x['re'] = i[0::2]
+    x['im'] = i[1::2]
+    return x
+
+
+def test_oracle_reproduces_reference_closed_form():
+    ntime, nchan, nstand, npol = 12, 3, 10, 2
+    x = closed_form_input(ntime, nchan, nstand, npol)
+    got = olinalg.correlate(np.transpose(x, (1, 0, 2)))
+    i = np.arange(nstand * npol * 2) % 255 - 127
+    v = (i[0::2] + 1j * i[1::2]).astype(np.complex64)
+    expected = ntime * v[:, None].conj() * v[None, :]
+    triu = np.triu_indices(nstand * npol, 1)
+    expected[triu] = 0
+    np.testing.assert_allclose(got, np.broadcast_to(expected, got.shape), rtol=1e-6)
+
+
+def rand_ci8(rng, shape):
+    x = np.empty(shape, dtype=CI8)
+    x['re'] = rng.integers(-127, 128, size=shape)
+    x['im'] = rng.integers(-127, 128, size=shape)
+    return x
+
+
+def run_bhb(x_tcn, beta=0.0, alpha=1.0, c0=None, perm=(1, 0, 2)):
+    """x_tcn: [ntime, nchan, n] host array; correlate over time per channel."""
+    d_x = bf.asarray(x_tcn, space='cuda')
+    xv = d_x.transpose(perm)
+    nchan, n = x_tcn.shape[1], x_tcn.shape[2]
+    c_init = np.zeros((nchan, n, n), np.complex64) if c0 is None else c0
+    d_c = bf.asarray(c_init, space='cuda')
+    LinAlg().matmul(alpha, None, xv, beta, d_c)
+    return np.asarray(d_c.copy('system'))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ntime,nchan,n", [(512, 4, 512), (100, 3, 128), (64, 2, 64), (1000, 1, 72),
+                                           (8, 5, 200), (33, 2, 16), (129, 1, 136)])
+def test_tensor_core_path_is_integer_exact(ntime, nchan, n):
+    rng = np.random.default_rng(ntime + n)
+    x = rand_ci8(rng, (ntime, nchan, n))
+    sentinel = (np.arange(nchan * n * n).reshape(nchan, n, n) % 7 + 1j).astype(np.complex64)
+    got = run_bhb(x, c0=sentinel)
+    want = olinalg.correlate(np.transpose(x, (1, 0, 2)), c=sentinel)
+    np.testing.assert_array_equal(got, want)          # incl. untouched upper triangle
+
+
+@pytest.mark.gpu
+def test_tensor_core_equals_simt_fallback():
+    rng = np.random.default_rng(5)
+    x = rand_ci8(rng, (300, 3, 256))
+    a = run_bhb(x)
+    os.environ['BFB_LINALG_SIMT'] = '1'
+    try:
+        b = run_bhb(x)
+    finally:
+        del os.environ['BFB_LINALG_SIMT']
+    np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_reference_sweep_small_and_misaligned():
+    """test/test_linalg.py:221-240 (subset): nstand 1..65 x ntime x nchan x misalign."""
+    rng = np.random.default_rng(1234)
+    for nstand in [1, 2, 3, 4, 5, 8, 9, 16, 17, 31, 32, 33, 64, 65]:
+        for ntime in [1, 2, 3, 4, 8, 12]:
+            for nchan in [1, 2, 5]:
+                for mis in [0, 2]:
+                    n_full = nstand * 2
+                    x = rand_ci8(rng, (ntime, nchan, n_full))
+                    d_x = bf.asarray(x, space='cuda')
+                    xv = d_x.transpose(1, 0, 2)[..., mis:]
+                    n = n_full - mis
+                    if n <= 0:
+                        continue
+                    d_c = bf.zeros((nchan, n, n), 'cf32', 'cuda')
+                    LinAlg().matmul(1, None, xv, 0, d_c)
+                    got = np.asarray(d_c.copy('system'))
+                    want = olinalg.correlate(np.transpose(x, (1, 0, 2))[..., mis:])
+                    np.testing.assert_array_equal(got, want, err_msg=str((nstand, ntime, nchan, mis)))
+
+
+@pytest.mark.gpu
+def test_beta_alpha_and_batch_dims():
+    rng = np.random.default_rng(6)
+    x1, x2 = rand_ci8(rng, (128, 2, 64)), rand_ci8(rng, (128, 2, 64))
+    c = run_bhb(x1)
+    c = run_bhb(x2, beta=1.0, c0=c)
+    want = olinalg.correlate(np.transpose(x2, (1, 0, 2)), c=olinalg.correlate(np.transpose(x1, (1, 0, 2))), beta=1.0)
+    np.testing.assert_array_equal(c, want)
+    c2 = run_bhb(x1, alpha=0.5)
+    np.testing.assert_array_equal(c2, olinalg.correlate(np.transpose(x1, (1, 0, 2)), alpha=0.5))
+    # extra leading batch dim: [beam, chan, time, n]
+    xb = rand_ci8(rng, (3, 64, 4, 48))                # [beam, time, chan, n]
+    d_x = bf.asarray(xb, space='cuda')
+    xv = d_x.transpose(0, 2, 1, 3)
+    d_c = bf.zeros((3, 4, 48, 48), 'cf32', 'cuda')
+    LinAlg().matmul(1, None, xv, 0, d_c)
+    np.testing.assert_array_equal(np.asarray(d_c.copy('system')),
+                                  olinalg.correlate(np.transpose(xb, (0, 2, 1, 3))))
+
+
+@pytest.mark.gpu
+def test_aah_form_and_float_inputs():
+    rng = np.random.default_rng(7)
+    a = rand_ci8(rng, (2, 24, 100))                   # [batch, n, ntime]
+    d_a = bf.asarray(a, space='cuda')
+    d_c = bf.zeros((2, 24, 24), 'cf32', 'cuda')
+    LinAlg().matmul(1, d_a, None, 0, d_c)
+    av = a['re'].astype(np.float64) + 1j * a['im']
+    full = av @ np.swapaxes(av.conj(), -1, -2)
+    il = np.tril_indices(24)
+    want = np.zeros((2, 24, 24), np.complex64)
+    want[..., il[0], il[1]] = full[..., il[0], il[1]]
+    np.testing.assert_array_equal(np.asarray(d_c.copy('system')), want)
+    xf = (rng.normal(size=(3, 200, 40)) + 1j * rng.normal(size=(3, 200, 40))).astype(np.complex64)
+    d_cf = bf.zeros((3, 40, 40), 'cf32', 'cuda')
+    LinAlg().matmul(1, None, bf.asarray(xf, space='cuda'), 0, d_cf)
+    np.testing.assert_allclose(np.asarray(d_cf.copy('system')), olinalg.correlate(xf), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_correlate_block_closed_form():
+    """The reference's pipeline test for CorrelateBlock (test/test_pipeline.py:230-298)."""
+    from bifrost_b200 import blocks
+    from bifrost_b200.pipeline import Pipeline
+    ntime, nchan, nstand, npol = 96, 4, 16, 2
+    x = closed_form_input(ntime, nchan, nstand, npol).reshape(ntime, nchan, nstand, npol)
+    hdr = {'_tensor': {'dtype': 'ci8', 'shape': [-1, nchan, nstand, npol],
+                       'labels': ['time', 'freq', 'station', 'pol'],
+                       'scales': [[0, 1e-3], [100.0, 0.1], None, None], 'units': ['s', 'MHz', None, None]},
+           'name': 'corr', 'gulp_nframe': 32}
+    chunks = []
+    with Pipeline() as p:
+        src = blocks.array_source(x, hdr, gulp_nframe=32)
+        b = blocks.copy(src, space='cuda')
+        b = blocks.correlate(b, nframe_per_integration=96)
+        b = blocks.copy(b, space='system')
+        blocks.callback_sink(b, None, lambda s: chunks.append(np.array(s.data)))
+        p.run()
+    got = chunks[0].reshape(nchan, nstand * npol, nstand * npol)
+    i = np.arange(nstand * npol * 2) % 255 - 127
+    v = (i[0::2] + 1j * i[1::2]).astype(np.complex64)
+    expected = ntime * v[:, None].conj() * v[None, :]
+    il = np.tril_indices(nstand * npol)
+    np.testing.assert_allclose(got[:, il[0], il[1]], np.broadcast_to(expected[il], (nchan, len(il[0]))), rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_unsupported_forms_return_status():
+    from bifrost_b200.libbifrost import _bf
+    a = bf.empty((4, 8), 'cf32', 'cuda')
+    b = bf.empty((8, 4), 'cf32', 'cuda')
+    c = bf.empty((4, 4), 'cf32', 'cuda')
+    h = LinAlg()
+    assert _bf.bfLinAlgMatMul(h.obj, 1.0, a.as_BFarray(), b.as_BFarray(), 0.0, c.as_BFarray()) == \
+        _bf.BF_STATUS_UNSUPPORTED
+    assert _bf.bfLinAlgMatMul(h.obj, 1.0, None, None, 0.0, c.as_BFarray()) == _bf.BF_STATUS_INVALID_ARGUMENT
