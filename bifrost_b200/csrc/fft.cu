@@ -38,6 +38,7 @@
 // strided, so global accesses stay coalesced for transforms over slow axes.
 #include "core.hpp"
 #include "shape.hpp"
+#include "fft4096.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -415,6 +416,45 @@ fft_pass_kernel(const __grid_constant__ FftPass<T> P) {
 	}
 }
 
+// ---------------------------------------------------------------------------
+// Fast path: forward/inverse c2c of length 4096 along a contiguous axis, float.
+// One line per CTA, 256 threads, the register-resident radix-16 core of
+// fft4096.cuh; input conversion specialised at compile time.
+template<int KIND>
+__global__ void __launch_bounds__(256, 2)
+fft4096_fast_kernel(const __grid_constant__ FftPass<float> P) {
+	extern __shared__ __align__(16) unsigned char fast_smem[];
+	float2* buf = (float2*)fast_smem;
+	float2* tb  = buf + SPEC_PITCH;
+	const int p = threadIdx.x;
+	fft4096_init_twiddles(tb, (const float2*)P.twid, p);
+	for( long L = blockIdx.x; L < P.nline; L += gridDim.x ) {
+		long ioff, ooff, twc;
+		fft_line_offsets(P, L, ioff, ooff, twc);
+		const char* iline = (const char*)P.in + ioff;
+		float2* oline = (float2*)((char*)P.out + ooff);
+		float vr[16], vi[16];
+		const float sgn = (P.shift == 1 && (p & 1)) ? -1.f : 1.f;     // index parity = parity of p
+		const float sc = sgn * P.scale_in;
+#pragma unroll
+		for( int m=0; m<16; ++m ) {
+			int e = p + 256 * m;
+			if( P.shift == 2 ) e ^= 2048;                                // rotate by n/2
+			float r, i;
+			if( KIND == FK_CF32 )      { float2 v = ((const float2*)iline)[e]; r = v.x; i = v.y; }
+			else if( KIND == FK_CI8 )  { char2 v = ((const char2*)iline)[e];   r = v.x; i = v.y; }
+			else                       { short2 v = ((const short2*)iline)[e]; r = v.x; i = v.y; }
+			vr[m] = r * sc;
+			vi[m] = P.inverse ? -(i * sc) : i * sc;
+		}
+		fft4096(vr, vi, buf, tb, p);
+#pragma unroll
+		for( int t=0; t<16; ++t ) {
+			oline[p + 256 * t] = make_float2(vr[t], P.inverse ? -vi[t] : vi[t]);
+		}
+	}
+}
+
 } // namespace bfb
 
 using namespace bfb;
@@ -568,6 +608,29 @@ BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 	long osize = (out_real ? 1 : 2) * (long)sizeof(T);
 	P.b_fast_in  = std::abs(in.strides[axis])  != isize_in;
 	P.b_fast_out = std::abs(out.strides[axis]) != osize;
+	if( sizeof(T) == 4 && n == 4096 && !in_real && !in_herm && !out_real && n_out == n && !post_tw &&
+	    shift != 3 && !P.b_fast_in && !P.b_fast_out &&
+	    (in.kind == FK_CF32 || in.kind == FK_CI8 || in.kind == FK_CI16) &&
+	    (uintptr_t)in.data % isize_in == 0 ) {
+		bool aligned = true;
+		for( int d=0; d<P.nouter; ++d ) aligned = aligned && (P.oistr[d] % isize_in == 0) && (P.oostr[d] % 8 == 0);
+		if( aligned ) {
+			size_t fsmem = ((size_t)SPEC_PITCH + 8 * 256) * sizeof(float2);
+			unsigned fgrid = (unsigned)std::min<long>(nline, 148L * 16);
+			FftPass<float> const& PF = *(FftPass<float> const*)(const void*)&P;
+#define BFB_FFT_FAST(K_) do { \
+				BFB_CUDA(cudaFuncSetAttribute(fft4096_fast_kernel<K_>, \
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), BF_STATUS_INTERNAL_ERROR); \
+				fft4096_fast_kernel<K_><<<fgrid, 256, fsmem, st>>>(PF); } while(0)
+			if( in.kind == FK_CF32 )     BFB_FFT_FAST(FK_CF32);
+			else if( in.kind == FK_CI8 ) BFB_FFT_FAST(FK_CI8);
+			else                         BFB_FFT_FAST(FK_CI16);
+#undef BFB_FFT_FAST
+			count_launch();
+			BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+			return BF_STATUS_SUCCESS;
+		}
+	}
 	int threads;
 	size_t smem;
 	if( is_pow2(n) && n >= 16 ) {

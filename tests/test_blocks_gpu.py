@@ -12,7 +12,10 @@ import bifrost_b200 as bf
 from bifrost_b200 import blocks, views
 from bifrost_b200.pipeline import Pipeline
 from oracle import fdmt as ofdmt
-from tests.test_spectrometer import make as make_voltages, oracle_chain
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_spectrometer import make as make_voltages, oracle_chain  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -31,7 +34,8 @@ class Collect(object):
 def guppi_header(nchan, nfft):
     return {'_tensor': {'dtype': 'ci8', 'shape': [-1, nchan, nfft, 2],
                         'labels': ['time', 'freq', 'fine_time', 'pol'],
-                        'scales': [[0, nfft * 1e-6], [1200.0, 400.0 / nchan], [0, 1e-6], None],
+                        'scales': [[0, nfft * nchan / 400e6], [1200.0, 400.0 / nchan],
+                                   [0, nchan / 400e6], None],
                         'units': ['s', 'MHz', 's', None]},
             'name': 'guppi', 'gulp_nframe': 1}
 

@@ -59,8 +59,9 @@ def test_gpu_matches_oracle_all_modes():
         odts = (['ci8', 'cf32', 'cf64'] if cplx else ['i8', 'f32', 'f64']) if signed else ['u8']
         for odt, big, msb, conj in itertools.product(odts, [False, True], [False, True],
                                                     [False, True] if cplx else [False]):
-            d_in = bf.ndarray(shape=shape, dtype=idt, space='cuda', native=not big, conjugated=conj)
-            bf.copy_array(d_in.view(np.uint8) if False else d_in, raw.view(d_in.dtype).reshape(d_in.shape))
+            d_raw = bf.asarray(raw, space='cuda')            # packed bytes on the device
+            d_in = bf.ndarray(space='cuda', buffer=d_raw.ctypes.data, shape=shape, dtype=idt,
+                              native=not big, conjugated=conj)
             d_out = bf.empty(shape, dtype=odt, space='cuda')
             bf.unpack(d_in, d_out, align_msb=msb)
             out = np.asarray(d_out.copy('system'))
