@@ -6,7 +6,9 @@ int8 filterbank (config 2: max_dm=100 -> max_delay=794, 131072 output samples
 per gulp), plus % of the HBM roofline.  One "step" = one gulp through
 bfFdmtExecute.  `value` is timed with the input resident in HBM; `e2e` is the
 same call made from HOST buffers (pinned) with the H2D copy of the gulp and
-the D2H read of the dispersion bank inside the timed region.
+the D2H read of the dispersion bank inside the timed region.  The second half
+of the metric (FFT -> detect -> reduce -> accumulate on the ci8 GUPPI gulp,
+config 3) is reported in the `chain` object (one fused kernel).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -14,6 +16,8 @@ N > 1 (under torchrun): rank g processes its own 4096-channel sub-band (weak
 scaling, no data-path collective -- SURVEY 8e); time = max over ranks.
 `--impl reference` times the CPU restatement of the reference algorithm
 (oracle/) on the host cores of this box on a bounded sample of the workload.
+`--dry-run` exercises the multi-rank host logic (sharding, barrier, max over
+ranks) on the gloo backend with no GPU work (tests/test_bench_cpu.py).
 """
 import argparse
 import json
@@ -30,11 +34,14 @@ sys.path.insert(0, ROOT)
 
 NCHAN = 4096
 NTIME_OUT = 131072
+# bounded CPU sample: 1/4 of the gulp's time span, all 4096 channels (env override: tests only)
+CPU_SAMPLE_NTIME = int(os.environ.get('BENCH_CPU_SAMPLE_NTIME', 32768))
 F0_MHZ = 1000.0
 BW_MHZ = 400.0
 DT_S = 256e-6
 MAX_DM = 100.0
 KDM = 4.148741601e3
+METRIC = 'Msamples/s through FDMT+FFT->detect->reduce on 4096-chan ci8; % HBM roofline'
 
 
 def max_delay_for(f0, df, nchan, dt, max_dm):
@@ -88,7 +95,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -102,6 +109,7 @@ class ClockSampler(object):
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -141,12 +149,14 @@ def cpu_fdmt_sample(w, ntime_sample, threads=None):
     """Times the oracle (CPU restatement of the reference algorithm) on a
     bounded sample: the full 4096 channels, `ntime_sample` time samples.
     Returns (Msamples/s, kind, cores, seconds)."""
-    x = make_input(w, 4321, ntime=ntime_sample + w['max_delay'])
     try:
         from oracle import fdmt_c
         have_c = fdmt_c.available()
     except Exception:
         have_c = False
+    if not have_c:
+        ntime_sample = min(ntime_sample, 8192)        # the numpy port is ~10x slower
+    x = make_input(w, 4321, ntime=ntime_sample + w['max_delay'])
     nsamp = w['nchan'] * ntime_sample
     if have_c:
         from oracle import fdmt_c
@@ -170,7 +180,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     w = workload(0)
-    ntime_sample = 8192
+    ntime_sample = CPU_SAMPLE_NTIME
     vals, secs = [], []
     cores = 1
     for i in range(args.warmup + args.steps):
@@ -179,10 +189,9 @@ def run_reference_arm(args, rank, world):
             vals.append(v)
             secs.append(dt)
     value = float(np.mean(vals))
-    sample = (f"oracle CPU FDMT on {w['nchan']} chan x {ntime_sample} samples "
+    sample = (f"oracle CPU FDMT (oracle/fdmt_c.c, pthreads) on {w['nchan']} chan x {ntime_sample} samples "
               f"(1/{NTIME_OUT // ntime_sample} of the gulp) per step, {cores} threads")
-    line = dict(impl='reference', metric='FDMT throughput, 4096-chan int8 filterbank, max_delay=%d'
-                % w['max_delay'], value=value, unit='Msamples/s', n_gpus=args.gpus,
+    line = dict(impl='reference', metric=METRIC, value=value, unit='Msamples/s', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=float(np.mean(secs) * 1e3),
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                 data='synthetic',
@@ -192,6 +201,32 @@ def run_reference_arm(args, rank, world):
                                   sample=sample),
                 e2e=dict(value=value, unit='Msamples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- dry run
+def run_dry(args, rank, world):
+    """Multi-rank host logic without a GPU: sharding, barrier, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('gloo')
+    w = workload(rank)
+    ms = 1.0 + 0.5 * rank                      # pretend rank r needs 1 + r/2 ms per step
+    f0s = [w['f0']]
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, torch.tensor([w['f0']], dtype=torch.float64))
+        f0s = [float(p.item()) for p in parts]
+    if rank == 0:
+        print(json.dumps(dict(dry_run=True, n_gpus=world, ms_per_step=ms,
+                              value=w['nchan'] * NTIME_OUT * world / (ms * 1e-3) / 1e6,
+                              subband_f0_mhz=f0s, max_delay=w['max_delay'])))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -207,6 +242,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-chain', action='store_true')
+    ap.add_argument('--dry-run', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -216,6 +253,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference_arm(args, rank, world)
+        return
+    if args.dry_run:
+        run_dry(args, rank, world)
         return
 
     import torch
@@ -266,6 +306,7 @@ def main():
         barrier()
         if sampler:
             sampler.start()
+            time.sleep(0.1)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = bf.launch_count()
         ev0.record(stream)
@@ -312,6 +353,31 @@ def main():
         except Exception:
             pass
 
+    # ---- second half of the metric: the fused GUPPI chain (config 3), per rank
+    chain = None
+    if not args.no_chain:
+        del ws, d_out
+        nframe, cchan, nfft, f_avg = 32, 4096, 4096, 4
+        nbyte = nframe * cchan * nfft * 4
+        raw = torch.randint(-127, 128, (nbyte,), dtype=torch.int8, device='cuda')
+        xg = bf.empty((nframe, cchan, nfft, 2), 'ci8', 'cuda')
+        from bifrost_b200.libbifrost import _bf, _check
+        _check(_bf.bfMemcpy(xg.ctypes.data, xg.as_BFarray().space, raw.data_ptr(),
+                            xg.as_BFarray().space, nbyte))
+        torch.cuda.synchronize()
+        del raw
+        og = bf.zeros((4, cchan * nfft // f_avg), 'f32', 'cuda')
+        ms_c, _, _ = timed(lambda: bf.spectrometer(xg, og, nfft, f_avg, 0.0), 3, 10)
+        ms_c /= 10
+        gbs = nbyte / (ms_c * 1e-3) / 1e9
+        chain = dict(workload='BASELINE config 3: GUPPI ci8 [32 frames, 4096 chan, 4096 fine_time, 2 pol] -> '
+                              'fft(fine_time, fftshift) -> stokes -> reduce(f_avg=4) -> accumulate(32 frames); '
+                              'bfSpectrometerFused, one kernel per gulp per GPU',
+                     ms_per_gulp=ms_c, value=nframe * cchan * nfft * world / (ms_c * 1e-3) / 1e6,
+                     unit='Msamples/s', hbm_GBps=gbs, hbm_frac=gbs / peaks['hbm_gbs'],
+                     note='fp32-issue bound (2 x 4096-pt FFT per 16 KB read); see DESIGN.md')
+        log('chain ms/gulp', ms_c)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -319,13 +385,13 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, kind, cores, dt = cpu_fdmt_sample(w, 8192)
+        v, kind, cores, dt = cpu_fdmt_sample(w, CPU_SAMPLE_NTIME)
         cpu = dict(value=v, unit='Msamples/s', cores=cores, kind=kind,
-                   sample=f"{nchan} chan x 8192 samples (1/16 of the gulp), {dt:.2f} s, "
+                   sample=f"oracle CPU FDMT: {nchan} chan x {CPU_SAMPLE_NTIME} samples "
+                          f"(1/{NTIME_OUT // CPU_SAMPLE_NTIME} of the gulp), {dt:.2f} s, "
                           f"{cores} thread(s) of {os.cpu_count()} host cores")
 
-    line = dict(metric='FDMT throughput, 4096-chan int8 filterbank, max_delay=%d' % md,
-                value=value, unit='Msamples/s', n_gpus=world, steps=args.steps,
+    line = dict(metric=METRIC, value=value, unit='Msamples/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload='BASELINE config 2: bfFdmtExecute, max_dm=100 '
@@ -333,11 +399,11 @@ def main():
                                      'int8 filterbank per GPU; f0=1000 MHz, bw=400 MHz, dt=256 us',
                             sharding='one 4096-chan sub-band per GPU, no collective' if world > 1
                                      else 'single GPU',
-                            l2='input 537 MB + output 419 MB per step exceed the 126 MB L2'),
+                            l2='input 540 MB + output 419 MB per step exceed the 126 MB L2'),
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit='Msamples/s', ms_per_step=ms_e2e,
                          h2d_bytes_per_step=int(nchan * ntime), d2h_bytes_per_step=int(md * ntime * 4)),
-                gpu_launches=int(launches), clocks=clocks)
+                gpu_launches=int(launches), clocks=clocks, chain=chain)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
