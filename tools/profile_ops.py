@@ -1,0 +1,29 @@
+"""One launch each of the fused spectrometer and the tcgen05 correlator for ncu
+captures (not a benchmark: numbers under ncu are never reported)."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bifrost_b200 as bf
+
+rng = np.random.default_rng(5)
+which = sys.argv[1] if len(sys.argv) > 1 else 'spectrometer,correlate'
+if 'spectrometer' in which:
+    nframe, nchan, nfft = 8, 4096, 4096
+    raw = rng.integers(-127, 128, size=(nframe, nchan, nfft, 2, 2), dtype=np.int8)
+    x = bf.asarray(raw.view(bf.DataType('ci8').as_numpy_dtype()).reshape(nframe, nchan, nfft, 2), space='cuda')
+    o = bf.zeros((4, nchan * nfft // 4), 'f32', 'cuda')
+    for _ in range(2):
+        bf.spectrometer(x, o, nfft, 4, 0.0)
+    bf.device.stream_synchronize()
+    del x, o
+if 'correlate' in which:
+    ntime, nchan, n = 2048, 512, 512
+    raw = rng.integers(-127, 128, size=(ntime, nchan, n, 2), dtype=np.int8)
+    x = bf.asarray(raw.view(bf.DataType('ci8').as_numpy_dtype()).reshape(ntime, nchan, n), space='cuda')
+    c = bf.zeros((nchan, n, n), 'cf32', 'cuda')
+    la = bf.linalg.LinAlg()
+    for _ in range(2):
+        la.matmul(1, None, x.transpose(1, 0, 2), 0, c)
+    bf.device.stream_synchronize()
+print('done')
