@@ -314,7 +314,17 @@ def main():
             fn()
         ev1.record(stream)
         barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = None
+        if sampler:
+            # the timed region can be shorter than nvidia-smi's sampling period:
+            # keep the same load running (untimed) until a few samples exist
+            t_end = time.time() + 1.5
+            while len(sampler.lines) < 8 and time.time() < t_end:
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize()
+            clocks = sampler.stop()
+            clocks['window'] = 'timed steps + untimed post-roll of the same steps (nvidia-smi -lms 50)'
         ms = ev0.elapsed_time(ev1)
         launches = bf.launch_count() - launches0
         if world > 1:

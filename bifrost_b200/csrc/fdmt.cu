@@ -448,6 +448,8 @@ fdmt_tail_kernel(const float* __restrict__ prev, long pstride, long pbatchstride
 
 } // namespace bfb
 
+#include "fdmt_tiles.cuh"
+
 using namespace bfb;
 
 struct BFfdmt_impl {
@@ -480,6 +482,11 @@ struct BFfdmt_impl {
 	long   cfg_tail_tile = 1L << 30;
 	bool   cfg_force_v1 = false;
 	bool   head_ok = false;
+	// fused tail passes (fdmt_tiles.cuh); empty = row-blocked tail steps
+	std::vector<TilePass> passes;
+	TilePass head_pass;                  // steps 1..K straight from 1-byte input
+	bool   head_pass_ok = false;
+	int    cfg_tile_d = 32, cfg_tile_smem_kb = 110, cfg_tile_threads = 256;
 	// exec workspace
 	void*  own_exec_storage = nullptr;
 	size_t own_exec_size = 0;
@@ -496,6 +503,15 @@ struct BFfdmt_impl {
 		if( own_plan_storage ) cudaFree(own_plan_storage);
 		if( own_exec_storage ) cudaFree(own_exec_storage);
 		if( d_items ) cudaFree(d_items);
+		free_passes();
+	}
+	void free_passes() {
+		for( TilePass& tp : passes ) if( tp.d_items ) cudaFree(tp.d_items);
+		passes.clear();
+		if( head_pass.d_items ) cudaFree(head_pass.d_items);
+		if( head_pass.d_aux )   cudaFree(head_pass.d_aux);
+		head_pass = TilePass();
+		head_pass_ok = false;
 	}
 };
 
@@ -547,6 +563,95 @@ static void head_geometry(FdmtPlan const& P, int K, std::vector<HeadBand>* bands
 	}
 	*halo = (*halo + 3) / 4 * 4;     // keeps window and global time 4-aligned together
 	*nd0 = max_nd0;
+}
+
+static size_t tile_pass_smem(TilePass const& tp) {
+	return (size_t)tp.nphase * tp.nwarp * tp.slots * sizeof(int4) + tp.raw_bytes + (size_t)tp.smem_floats * sizeof(float);
+}
+static bool upload_tile_pass(TilePass* tp) {
+	size_t bytes = tp->items.size() * sizeof(int4);
+	if( cudaMalloc((void**)&tp->d_items, bytes) != cudaSuccess ||
+	    cudaMemcpy(tp->d_items, tp->items.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess ) {
+		if( tp->d_items ) cudaFree(tp->d_items);
+		tp->d_items = nullptr;
+		return false;
+	}
+	if( !tp->aux.empty() ) {
+		bytes = tp->aux.size() * sizeof(int4);
+		if( cudaMalloc((void**)&tp->d_aux, bytes) != cudaSuccess ||
+		    cudaMemcpy(tp->d_aux, tp->aux.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess ) {
+			cudaFree(tp->d_items); tp->d_items = nullptr;
+			if( tp->d_aux ) cudaFree(tp->d_aux);
+			tp->d_aux = nullptr;
+			return false;
+		}
+	}
+	return true;
+}
+// FINAL x RAW instantiations of the tile kernel
+static BFstatus launch_tile_pass(TilePass const& tp, TileParams const& q_, bool fin, int raw,
+                                 long ntime, long nbatch, cudaStream_t st) {
+	TileParams q = q_;
+	q.ntile = div_up<long>(ntime, tp.T);
+	q.tiles_per_cta = std::max(1, env_int("BFB_FDMT_TILES_PER_CTA", 8));
+	dim3 grid((unsigned)div_up<long>(q.ntile, q.tiles_per_cta), (unsigned)tp.nprog, (unsigned)nbatch);
+	int smem = (int)tile_pass_smem(tp);
+#define BFB_TILE_LAUNCH(F_, R_) do { \
+		BFB_CUDA(cudaFuncSetAttribute(fdmt_tile_kernel<F_, R_>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, smem), BF_STATUS_INTERNAL_ERROR); \
+		fdmt_tile_kernel<F_, R_><<<grid, tp.nwarp * 32, smem, st>>>(q); } while(0)
+	if( fin ) { if( raw == 0 ) BFB_TILE_LAUNCH(true, 0);  else if( raw == 1 ) BFB_TILE_LAUNCH(true, 1);  else BFB_TILE_LAUNCH(true, 2); }
+	else      { if( raw == 0 ) BFB_TILE_LAUNCH(false, 0); else if( raw == 1 ) BFB_TILE_LAUNCH(false, 1); else BFB_TILE_LAUNCH(false, 2); }
+#undef BFB_TILE_LAUNCH
+	count_launch();
+	return BF_STATUS_SUCCESS;
+}
+
+// Splits the steps above the head into fused passes of at most 4 steps
+// (BFB_FDMT_SPLIT="8,10" names the last step of every pass but the final one)
+// and builds their item tables.  Leaves `passes` empty when a pass does not fit.
+static void build_tail_passes(BFfdmt_impl* plan) {
+	FdmtPlan const& P = plan->plan;
+	plan->free_passes();
+	plan->cfg_tile_d       = std::max(4, env_int("BFB_FDMT_TILE_D", 32));
+	plan->cfg_tile_smem_kb = std::min(env_int("BFB_FDMT_TILE_SMEM_KB", 110), 227);
+	plan->cfg_tile_threads = std::max(32, std::min(256, env_int("BFB_FDMT_TILE_THREADS", 256) / 32 * 32));
+	if( env_int("BFB_FDMT_TILES", 1) == 0 ) return;
+	int first = plan->K + 1, last = P.nstep() - 1;
+	if( first > last ) return;
+	std::vector<int> ends;
+	if( const char* e = getenv("BFB_FDMT_SPLIT") ) {
+		for( const char* q=e; *q; ) {
+			int v = atoi(q);
+			if( v >= first && v < last && (ends.empty() || v > ends.back()) ) ends.push_back(v);
+			while( *q && *q != ',' ) ++q;
+			if( *q == ',' ) ++q;
+		}
+	} else {
+		int n = last - first + 1, npass = div_up<int>(n, 4);
+		for( int k=1; k<npass; ++k ) ends.push_back(first + (n * k) / npass - 1);
+	}
+	ends.push_back(last);
+	int nwarp = plan->cfg_tile_threads / 32;
+	size_t smem_cap = (size_t)plan->cfg_tile_smem_kb * 1024;
+	int s0 = first;
+	for( int s1 : ends ) {
+		TilePass tp;
+		bool ok = false;
+		for( int D=plan->cfg_tile_d; D>=4 && !ok; D/=2 )
+			ok = build_tile_pass(P, s0, s1, D, nwarp, &tp) && tile_pass_smem(tp) <= smem_cap;
+		if( !ok || !upload_tile_pass(&tp) ) { plan->free_passes(); return; }
+		plan->passes.push_back(tp);
+		s0 = s1 + 1;
+	}
+	// the head as a raw tile pass (1-byte inputs)
+	if( env_int("BFB_FDMT_RAWTILES", 1) != 0 ) {
+		TilePass hp;
+		bool ok = false;
+		for( int D=std::max(plan->cfg_tile_d, 32); D>=4 && !ok; D/=2 )
+			ok = build_tile_pass(P, 1, plan->K, D, nwarp, &hp, true) && tile_pass_smem(hp) <= smem_cap;
+		if( ok && upload_tile_pass(&hp) ) { plan->head_pass = hp; plan->head_pass_ok = true; }
+	}
 }
 
 extern "C" {
@@ -650,6 +755,7 @@ BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
 	BFB_CUDA(cudaMemcpyAsync(plan->d_head, head.data(), head.size()*sizeof(HeadBand),
 	                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
 	BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
+	BFB_TRY(build_tail_passes(plan));
 	return BF_STATUS_SUCCESS;
 }
 
@@ -916,6 +1022,20 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 		BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
 	}
 	hp.items = plan->d_items; hp.item_slots = plan->item_slots;
+	const bool raw_head = plan->head_pass_ok && (in->dtype == BF_DTYPE_I8 || in->dtype == BF_DTYPE_U8);
+	if( raw_head ) {
+		TilePass const& tp = plan->head_pass;
+		TileParams q;
+		q.src = nullptr; q.sstride = q.sbatch = 0;
+		q.dst = hp.dst; q.dstride = hp.dstride; q.dbatch = hp.dbatchstride;
+		q.items = tp.d_items; q.aux = tp.d_aux;
+		q.raw = in->data; q.rstride = istride; q.rbatch = ibatch;
+		q.raw_bytes = tp.raw_bytes; q.edge_margin = tp.edge_margin;
+		q.ntime = ntime; q.src_limit = 0; q.dst_limit = sstride;
+		q.T = tp.T; q.nphase = tp.nphase; q.slots = tp.slots;
+		BFstatus ls = launch_tile_pass(tp, q, head_is_final, in->dtype == BF_DTYPE_I8 ? 1 : 2, ntime, nbatch, st);
+		if( ls != BF_STATUS_SUCCESS ) return ls;
+	} else {
 #define BFB_FDMT_HEAD(T_) do { \
 		BFB_CUDA(cudaFuncSetAttribute(fdmt_head_kernel<T_>, \
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem), BF_STATUS_INTERNAL_ERROR); \
@@ -931,10 +1051,34 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	}
 #undef BFB_FDMT_HEAD
 	count_launch();
+	}
 	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
 	if( head_is_final ) return BF_STATUS_SUCCESS;
 
-	// ---------------- ... and the tail, swept tile by tile so it stays in L2.
+	if( !plan->passes.empty() ) {
+		// ---------------- ... and the remaining steps as fused shared-memory passes
+		float* c = cur;
+		float* n = nxt;
+		for( size_t k=0; k<plan->passes.size(); ++k ) {
+			TilePass const& tp = plan->passes[k];
+			bool fin = (tp.s1 == nstep - 1);
+			TileParams q;
+			q.src = c; q.sstride = sstride; q.sbatch = sbatchstride;
+			if( fin ) { q.dst = (float*)out->data; q.dstride = ostride; q.dbatch = obatch; }
+			else      { q.dst = n;                 q.dstride = sstride; q.dbatch = sbatchstride; }
+			q.items = tp.d_items; q.aux = nullptr; q.raw = nullptr; q.rstride = q.rbatch = 0;
+			q.raw_bytes = 0; q.edge_margin = tp.edge_margin;
+			q.ntime = ntime; q.src_limit = sstride; q.dst_limit = sstride;
+			q.T = tp.T; q.nphase = tp.nphase; q.slots = tp.slots;
+			BFstatus ls = launch_tile_pass(tp, q, fin, 0, ntime, nbatch, st);
+			if( ls != BF_STATUS_SUCCESS ) return ls;
+			std::swap(c, n);
+		}
+		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+		return BF_STATUS_SUCCESS;
+	}
+
+	// ---------------- ... or the tail, swept tile by tile so it stays in L2.
 	// Step s of tile [lo, hi) must cover [lo - halo_s, hi) where halo_s is the
 	// total delay still to be applied by later steps.
 	int first = plan->K + 1;
