@@ -486,7 +486,7 @@ struct BFfdmt_impl {
 	std::vector<TilePass> passes;
 	TilePass head_pass;                  // steps 1..K straight from 1-byte input
 	bool   head_pass_ok = false;
-	int    cfg_tile_d = 32, cfg_tile_smem_kb = 110, cfg_tile_threads = 256;
+	int    cfg_tile_d = 24, cfg_tile_smem_kb = 110, cfg_tile_threads = 256;
 	// exec workspace
 	void*  own_exec_storage = nullptr;
 	size_t own_exec_size = 0;
@@ -593,7 +593,7 @@ static BFstatus launch_tile_pass(TilePass const& tp, TileParams const& q_, bool 
                                  long ntime, long nbatch, cudaStream_t st) {
 	TileParams q = q_;
 	q.ntile = div_up<long>(ntime, tp.T);
-	q.tiles_per_cta = std::max(1, env_int("BFB_FDMT_TILES_PER_CTA", 8));
+	q.tiles_per_cta = std::max(1, env_int("BFB_FDMT_TILES_PER_CTA", 1));
 	dim3 grid((unsigned)div_up<long>(q.ntile, q.tiles_per_cta), (unsigned)tp.nprog, (unsigned)nbatch);
 	int smem = (int)tile_pass_smem(tp);
 #define BFB_TILE_LAUNCH(F_, R_) do { \
@@ -613,7 +613,7 @@ static BFstatus launch_tile_pass(TilePass const& tp, TileParams const& q_, bool 
 static void build_tail_passes(BFfdmt_impl* plan) {
 	FdmtPlan const& P = plan->plan;
 	plan->free_passes();
-	plan->cfg_tile_d       = std::max(4, env_int("BFB_FDMT_TILE_D", 32));
+	plan->cfg_tile_d       = std::max(4, env_int("BFB_FDMT_TILE_D", 24));
 	plan->cfg_tile_smem_kb = std::min(env_int("BFB_FDMT_TILE_SMEM_KB", 110), 227);
 	plan->cfg_tile_threads = std::max(32, std::min(256, env_int("BFB_FDMT_TILE_THREADS", 256) / 32 * 32));
 	if( env_int("BFB_FDMT_TILES", 1) == 0 ) return;
@@ -629,7 +629,7 @@ static void build_tail_passes(BFfdmt_impl* plan) {
 		}
 	} else {
 		int n = last - first + 1, npass = div_up<int>(n, 4);
-		for( int k=1; k<npass; ++k ) ends.push_back(first + (n * k) / npass - 1);
+		for( int k=1; k<npass; ++k ) ends.push_back(first + div_up<int>(n * k, npass) - 1);
 	}
 	ends.push_back(last);
 	int nwarp = plan->cfg_tile_threads / 32;

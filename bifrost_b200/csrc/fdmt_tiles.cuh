@@ -33,7 +33,6 @@ namespace bfb {
 enum { TILE_NO_A = 1, TILE_NO_B = 2, TILE_SLOW = 4 };
 enum { TILE_VPL = 3 };                       // float4 per lane per row
 enum { TILE_LMAX = 128 * TILE_VPL };         // longest row window (floats)
-enum { TILE_PF = 5 };                        // stage rows a warp prefetches in registers
 
 // Work item (int4).  Stage phase:  x global row, y time offset of sample 0
 // relative to t0 (<= 0, multiple of 4), z shared offset, w nvec.
@@ -431,7 +430,7 @@ __device__ __forceinline__ float tile_state0_exact(const unsigned char* x, int d
 // RAW: 0 = the source is the float state of step s0-1; 1 / 2 = the source is
 // the signed / unsigned 1-byte input array itself (s0 == 1).
 template<bool FINAL, int RAW>
-__global__ void __launch_bounds__(256, RAW ? 3 : 2)
+__global__ void __launch_bounds__(256, 3)
 fdmt_tile_kernel(const __grid_constant__ TileParams P) {
 	extern __shared__ __align__(16) float tsmem[];
 	const int  lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -452,12 +451,10 @@ fdmt_tile_kernel(const __grid_constant__ TileParams P) {
 	const int4* const stage_items = sitems + warp * P.slots;
 	__syncthreads();
 
-	// Stage rows of the NEXT tile are prefetched into registers while the
-	// current tile is merged, so their HBM latency is off the critical path.
-	// A warp keeps up to TILE_PF rows in flight; rows beyond that (wide
-	// programs) are loaded at the top of the tile.
-	uint32_t pf_w[RAW ? TILE_PF : 1][4];
-	float4   pf_v[RAW ? 1 : TILE_PF][TILE_VPL];
+	// Staging keeps the loads of TILE_NB rows per warp in flight before any of
+	// them is consumed (prefetching the next tile's rows across the merge
+	// phases was measured to add nothing on top of that).
+	constexpr int TILE_NB = RAW ? 5 : 3;
 	auto raw_row = [&](const int4& it, long t0n, const unsigned char*& g, long& lo, long& hi) {
 		const long wstart = t0n + it.y;
 		g = rin + (long)it.x * P.rstride + wstart;        // may point before the row
@@ -504,28 +501,21 @@ fdmt_tile_kernel(const __grid_constant__ TileParams P) {
 	};
 	int nstage = 0;                                   // this warp's stage rows
 	while( nstage < P.slots && stage_items[nstage].w != 0 ) ++nstage;
-	const int npf = min(nstage, (int)TILE_PF);
 
 	const long tile_begin = (long)blockIdx.x * P.tiles_per_cta;
 	const long tile_end   = min(P.ntile, tile_begin + P.tiles_per_cta);
-#pragma unroll
-	for( int m=0; m<TILE_PF; ++m ) if( m < npf ) load_stage(tile_begin * P.T, m, pf_w[RAW ? m : 0], pf_v[RAW ? 0 : m]);
-
 	for( long tile=tile_begin; tile<tile_end; ++tile ) {
 	const long t0 = tile * P.T;
 	const int4* items = stage_items;
+	for( int m0=0; m0<nstage; m0+=TILE_NB ) {
+		uint32_t rw[RAW ? TILE_NB : 1][4];
+		float4   rv[RAW ? 1 : TILE_NB][TILE_VPL];
 #pragma unroll
-	for( int m=0; m<TILE_PF; ++m ) if( m < npf ) store_stage(t0, m, pf_w[RAW ? m : 0], pf_v[RAW ? 0 : m]);
-	for( int m=TILE_PF; m<nstage; ++m ) {
-		uint32_t ow[4]; float4 ov[TILE_VPL];
-		load_stage(t0, m, ow, ov);
-		store_stage(t0, m, ow, ov);
+		for( int q=0; q<TILE_NB; ++q ) if( m0 + q < nstage ) load_stage(t0, m0 + q, rw[RAW ? q : 0], rv[RAW ? 0 : q]);
+#pragma unroll
+		for( int q=0; q<TILE_NB; ++q ) if( m0 + q < nstage ) store_stage(t0, m0 + q, rw[RAW ? q : 0], rv[RAW ? 0 : q]);
 	}
 	__syncthreads();
-	if( tile + 1 < tile_end ) {
-#pragma unroll
-		for( int m=0; m<TILE_PF; ++m ) if( m < npf ) load_stage(t0 + P.T, m, pf_w[RAW ? m : 0], pf_v[RAW ? 0 : m]);
-	}
 
 	for( int phase=1; phase<P.nphase; ++phase ) {
 		items += nwarp * P.slots;

@@ -121,21 +121,32 @@ def test_reference_smoke_semantics(ntime, nchan, md, batch):
 @pytest.mark.gpu
 @pytest.mark.parametrize("knob", [dict(BFB_FDMT_V1='1'), dict(BFB_FDMT_K='2'), dict(BFB_FDMT_K='4', BFB_FDMT_SMEM_KB='48'),
                                   dict(BFB_FDMT_K='8'), dict(BFB_FDMT_TAIL_TILE='1024', BFB_FDMT_TAIL_ROWS='3'),
-                                  dict(BFB_FDMT_THREADS='128')])
+                                  dict(BFB_FDMT_THREADS='128'),
+                                  dict(BFB_FDMT_TILES='0'), dict(BFB_FDMT_RAWTILES='0'),
+                                  dict(BFB_FDMT_TILE_D='8', BFB_FDMT_SPLIT='7,9'),
+                                  dict(BFB_FDMT_TILE_D='64', BFB_FDMT_TILES_PER_CTA='3'),
+                                  dict(BFB_FDMT_K='3', BFB_FDMT_TILE_THREADS='128'),
+                                  dict(BFB_FDMT_K='1', BFB_FDMT_SPLIT='2,3,5,8')])
 def test_every_schedule_gives_the_same_bits(knob):
-    """The step-by-step schedule (v1) and the fused head + tiled tail (v2) at
-    several split levels / tile sizes must agree bit for bit with the oracle."""
+    """The step-by-step schedule (v1), the fused head + row-blocked tail (v2)
+    and the shared-memory tile passes (default; fdmt_tiles.cuh) at several
+    split levels / block sizes must agree bit for bit with the oracle."""
     rng = np.random.default_rng(21)
     old = {k: os.environ.get(k) for k in knob}
     os.environ.update(knob)
     try:
-        for (ntime, nchan, md, dtype) in [(3000, 300, 150, np.int8), (5000, 64, 40, np.float32),
-                                         (700, 1024, 90, np.uint8), (2500, 37, 33, np.int16)]:
+        for (ntime, nchan, md, dtype, f0, bw) in [
+                (3000, 300, 150, np.int8, 1100., 300.), (5000, 64, 40, np.float32, 1100., 300.),
+                (700, 1024, 90, np.uint8, 1100., 300.), (2500, 37, 33, np.int16, 1100., 300.),
+                # wide fractional band: step-0 rows with more than 4 delays (exact path of the raw pass)
+                (2000, 48, 400, np.int8, 60., 30.), (1500, 21, 300, np.uint8, 40., 25.)]:
             if dtype == np.float32:
                 x = rng.normal(size=(nchan, ntime)).astype(np.float32)
+            elif dtype == np.int8:
+                x = rng.integers(-128, 128, size=(nchan, ntime)).astype(dtype)
             else:
-                x = rng.integers(0, 100, size=(nchan, ntime)).astype(dtype)
-            f0, df = 1100., 300. / nchan
+                x = rng.integers(0, 256 if dtype == np.uint8 else 100, size=(nchan, ntime)).astype(dtype)
+            df = bw / nchan
             got = run_gpu(x, md, f0, df)
             want = np.full((md, ntime), SENTINEL, np.float32)
             ofdmt.fdmt(x, md, f0, df, out=want)

@@ -13,10 +13,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   --log-file gpurun_out/r01_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
   > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-  -k regex:fdmt_ -s 8 -c 8 --csv --log-file gpurun_out/r01_fdmt_dram.csv python tools/profile_fdmt.py 2 \
+  -k regex:fdmt_ -s 3 -c 3 --csv --log-file gpurun_out/r01_fdmt_dram.csv python tools/profile_fdmt.py 2 \
   > gpurun_out/fdmt_dram.log 2>&1; echo "ncu dram rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:fdmt_tail -s 7 -c 7 \
-  -o gpurun_out/r01_fdmt_tail -f python tools/profile_fdmt.py 2 > gpurun_out/fdmt_tail_full.log 2>&1; echo "ncu tail rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:fdmt_tile -s 3 -c 3 \
+  -o gpurun_out/r01_fdmt_tiles -f python tools/profile_fdmt.py 2 > gpurun_out/fdmt_tiles_full.log 2>&1; echo "ncu tiles rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"spectrometer|corr_tc" -s 1 -c 2 \
   -o gpurun_out/r01_spec_corr -f python tools/profile_ops.py > gpurun_out/spec_corr_full.log 2>&1; echo "ncu spec/corr rc=$?"
 ls -la gpurun_out | tail -20
