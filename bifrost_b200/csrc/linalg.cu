@@ -121,7 +121,8 @@ corr_simt_kernel(SimtParams P) {
 }
 
 // ============================================================ tcgen05 kernel
-enum { TC_KT = 64, TC_STAGES = 4, TC_TILE_BYTES = TC_KT * 128, TC_THREADS = 192 };
+enum { TC_KT = 64, TC_STAGES = 3, TC_TILE_BYTES = TC_KT * 128, TC_THREADS = 192,
+       TC_STAGE_BYTES = 3 * TC_TILE_BYTES };    // A | B0 | B1
 
 struct TcParams {
 	float2* c; long c_row, c_batch;      // float2 units
@@ -163,22 +164,22 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
 	uint64_t d = 0;
 	d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
-	d |= (uint64_t)(1024 >> 4) << 16;                 // leading byte offset (unused: single atom in MN)
+	d |= (uint64_t)(TC_TILE_BYTES >> 4) << 16;        // leading byte offset: next 128-byte atom along MN (N = 256)
 	d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups
 	d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
 	d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
 	return d;
 }
 // Instruction descriptor: S32 accumulate, signed int8 A and B, both MN-major,
-// M = 128, N = 128.
-__device__ __forceinline__ uint32_t umma_idesc_i8_128x128() {
+// M = 128, N = 128 or 256.
+__device__ __forceinline__ uint32_t umma_idesc_i8(uint32_t n_dim) {
 	uint32_t d = 0;
 	d |= 2u << 4;            // c_format = S32
 	d |= 1u << 7;            // a_format = INT8 (signed)
 	d |= 1u << 10;           // b_format = INT8 (signed)
 	d |= 1u << 15;           // a_major = MN
 	d |= 1u << 16;           // b_major = MN
-	d |= (128u >> 3) << 17;  // n_dim
+	d |= (n_dim >> 3) << 17; // n_dim
 	d |= (128u >> 4) << 24;  // m_dim
 	return d;
 }
@@ -186,10 +187,10 @@ __device__ __forceinline__ uint32_t umma_idesc_i8_128x128() {
 __global__ void __launch_bounds__(TC_THREADS)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 	extern __shared__ __align__(1024) unsigned char tc_smem[];
-	// layout: [stages][A 8 KB | B 8 KB] | staging float2[64][65] | barriers
+	// layout: [stages][A 8 KB | B0 8 KB | B1 8 KB] | staging float2[64][65] | barriers
 	// the swizzled operand tiles need 1024-byte alignment in the shared window
 	unsigned char* tiles = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
-	float2* staging = (float2*)(tiles + TC_STAGES * 2 * TC_TILE_BYTES);
+	float2* staging = (float2*)(tiles + TC_STAGES * TC_STAGE_BYTES);
 	uint64_t* full_bar  = (uint64_t*)(staging + 64 * 65);
 	uint64_t* empty_bar = full_bar + TC_STAGES;
 	uint64_t* tmem_bar  = empty_bar + TC_STAGES;
@@ -197,13 +198,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int batch = blockIdx.y;
-	// lower-triangular tile index -> (I, J), I >= J
-	int tile = blockIdx.x;
-	int I = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
-	while( I * (I + 1) / 2 > tile ) --I;
-	while( (I + 1) * (I + 2) / 2 <= tile ) ++I;
-	const int J = tile - I * (I + 1) / 2;
-	const bool diag = (I == J);
+	// Work unit: row block I (128 rows of the real Gram matrix) x a pair of
+	// column blocks (2 JJ, 2 JJ + 1) with 2 JJ <= I.  The second block is
+	// dropped when it lies above the diagonal (nb = 1).  A 128 x 256 tile moves
+	// 24 KB per K slab for two blocks instead of 32 KB: the kernel is bound by
+	// L2 -> SM operand traffic, not by the tensor pipe.
+	int I = 0, rem = blockIdx.x;
+	while( rem >= I / 2 + 1 ) { rem -= I / 2 + 1; ++I; }
+	const int J0 = 2 * rem;
+	const int nb = (J0 + 1 <= I) ? 2 : 1;
+	// operand aliasing: a column block equal to the row block is loaded once
+	const bool a_is_b0 = (J0 == I), a_is_b1 = (nb == 2 && J0 + 1 == I);
 	const int nk = (P.ntime + TC_KT - 1) / TC_KT;
 
 	if( threadIdx.x == 0 ) {
@@ -212,9 +217,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if( warp == 1 ) {
-		// allocate 128 TMEM columns (power of two >= 32); the address lands in smem
+		// 256 TMEM columns: a 128 x 256 int32 accumulator; the address lands in smem
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-		             :: "r"(smem_u32(tmem_slot)), "n"(128));
+		             :: "r"(smem_u32(tmem_slot)), "n"(256));
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
@@ -225,27 +230,30 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 	if( warp == 0 ) {
 		// ===================== TMA producer =====================
 		if( lane == 0 ) {
+			const uint32_t bytes = (uint32_t)TC_TILE_BYTES * (nb + ((a_is_b0 || a_is_b1) ? 0 : 1));
 			for( int it=0; it<nk; ++it ) {
 				const int s = it % TC_STAGES;
 				const uint32_t ph = (it / TC_STAGES) & 1;
 				mbar_wait(&empty_bar[s], ph ^ 1);
-				unsigned char* a = tiles + (size_t)s * 2 * TC_TILE_BYTES;
-				mbar_expect_tx(&full_bar[s], diag ? TC_TILE_BYTES : 2 * TC_TILE_BYTES);
-				tma_load_3d(a, &tmap, &full_bar[s], 128 * I, it * TC_KT, batch);
-				if( !diag ) tma_load_3d(a + TC_TILE_BYTES, &tmap, &full_bar[s], 128 * J, it * TC_KT, batch);
+				unsigned char* a = tiles + (size_t)s * TC_STAGE_BYTES;
+				mbar_expect_tx(&full_bar[s], bytes);
+				if( !(a_is_b0 || a_is_b1) ) tma_load_3d(a, &tmap, &full_bar[s], 128 * I, it * TC_KT, batch);
+				tma_load_3d(a + TC_TILE_BYTES, &tmap, &full_bar[s], 128 * J0, it * TC_KT, batch);
+				if( nb == 2 ) tma_load_3d(a + 2 * TC_TILE_BYTES, &tmap, &full_bar[s], 128 * (J0 + 1), it * TC_KT, batch);
 			}
 		}
 	} else if( warp == 1 ) {
 		// ===================== MMA issuer =====================
-		const uint32_t idesc = umma_idesc_i8_128x128();
+		const uint32_t idesc = umma_idesc_i8(nb == 2 ? 256u : 128u);
 		for( int it=0; it<nk; ++it ) {
 			const int s = it % TC_STAGES;
 			const uint32_t ph = (it / TC_STAGES) & 1;
 			mbar_wait(&full_bar[s], ph);
 			asm volatile("tcgen05.fence::after_thread_sync;");
 			if( lane == 0 ) {
-				const uint32_t a_addr = smem_u32(tiles + (size_t)s * 2 * TC_TILE_BYTES);
-				const uint32_t b_addr = diag ? a_addr : a_addr + TC_TILE_BYTES;
+				const uint32_t st_addr = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES);
+				const uint32_t b_addr = st_addr + TC_TILE_BYTES;
+				const uint32_t a_addr = a_is_b0 ? b_addr : (a_is_b1 ? b_addr + TC_TILE_BYTES : st_addr);
 #pragma unroll
 				for( int kk=0; kk<TC_KT/32; ++kk ) {
 					const uint64_t da = umma_desc_mn_sw128(a_addr + kk * 32 * 128);
@@ -272,56 +280,61 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 		mbar_wait(tmem_bar, 0);
 		asm volatile("tcgen05.fence::after_thread_sync;");
 		const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
-		const int m = quarter * 32 + lane;                  // row of the 128x128 int32 tile
+		const int m = quarter * 32 + lane;                  // row of the 128 x 256 int32 tile
 		const int il = m >> 1, par = m & 1;                 // complex row, re/im row of the pair
 		float* stf = (float*)staging;
-#pragma unroll 1
-		for( int c0=0; c0<128; c0+=32 ) {
-			uint32_t r[32];
-			const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-			asm volatile(
-				"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-				"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-				"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-				: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-				  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-				  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-				  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-				: "r"(taddr));
-			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-			for( int q=0; q<16; ++q ) {
-				// even row 2i holds (G[2i][2j], G[2i][2j+1]); odd row holds
-				// (G[2i+1][2j], G[2i+1][2j+1]); swap the second entries.
-				int mine0 = (int)r[2*q], mine1 = (int)r[2*q+1];
-				int other1 = __shfl_xor_sync(0xffffffffu, mine1, 1);
-				// even lane: Re = G[2i][2j] + G[2i+1][2j+1]; odd lane: Im = G[2i][2j+1] - G[2i+1][2j]
-				int v = par ? (other1 - mine0) : (mine0 + other1);
-				int jl = (c0 >> 1) + q;
-				stf[(il * 65 + jl) * 2 + par] = (float)v;
-			}
-		}
-		// all four epilogue warps have staged their rows
-		asm volatile("bar.sync 1, 128;" ::: "memory");
 		const int te = threadIdx.x - 64;                    // 0..127
 		float2* cb = P.c + (long)batch * P.c_batch;
-		for( int idx = te; idx < 64 * 64; idx += 128 ) {
-			int il2 = idx >> 6, jl2 = idx & 63;
-			int i = I * 64 + il2, j = J * 64 + jl2;
-			if( i < P.n && j < P.n && i >= j ) {
-				float2 v = staging[il2 * 65 + jl2];
-				if( P.conj_u ) v.y = -v.y;
-				float2 o = make_float2(P.alpha * v.x, P.alpha * v.y);
-				float2* dst = cb + (long)i * P.c_row + j;
-				if( P.beta != 0.f ) { float2 old = *dst; o.x += P.beta * old.x; o.y += P.beta * old.y; }
-				*dst = o;
+		for( int h=0; h<nb; ++h ) {
+			const int J = J0 + h;
+#pragma unroll 1
+			for( int c0=0; c0<128; c0+=32 ) {
+				uint32_t r[32];
+				const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * h + c0);
+				asm volatile(
+					"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+					"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+					"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+					: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+					  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+					  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+					  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+					: "r"(taddr));
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+				for( int q=0; q<16; ++q ) {
+					// even row 2i holds (G[2i][2j], G[2i][2j+1]); odd row holds
+					// (G[2i+1][2j], G[2i+1][2j+1]); swap the second entries.
+					int mine0 = (int)r[2*q], mine1 = (int)r[2*q+1];
+					int other1 = __shfl_xor_sync(0xffffffffu, mine1, 1);
+					// even lane: Re = G[2i][2j] + G[2i+1][2j+1]; odd lane: Im = G[2i][2j+1] - G[2i+1][2j]
+					int v = par ? (other1 - mine0) : (mine0 + other1);
+					int jl = (c0 >> 1) + q;
+					stf[(il * 65 + jl) * 2 + par] = (float)v;
+				}
 			}
+			// all four epilogue warps have staged their rows
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			for( int idx = te; idx < 64 * 64; idx += 128 ) {
+				int il2 = idx >> 6, jl2 = idx & 63;
+				int i = I * 64 + il2, j = J * 64 + jl2;
+				if( i < P.n && j < P.n && i >= j ) {
+					float2 v = staging[il2 * 65 + jl2];
+					if( P.conj_u ) v.y = -v.y;
+					float2 o = make_float2(P.alpha * v.x, P.alpha * v.y);
+					float2* dst = cb + (long)i * P.c_row + j;
+					if( P.beta != 0.f ) { float2 old = *dst; o.x += P.beta * old.x; o.y += P.beta * old.y; }
+					*dst = o;
+				}
+			}
+			// the staging buffer is reused by the second column block
+			asm volatile("bar.sync 1, 128;" ::: "memory");
 		}
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
 	__syncthreads();
 	if( warp == 1 ) {
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(256));
 	}
 }
 
@@ -402,9 +415,10 @@ BFstatus correlate(BFdtype utype, const void* udata, long stride_t, long stride_
 				P.c = cb; P.c_row = c_row_bytes / 8; P.c_batch = kb_cstr / 8;
 				P.n = (int)n; P.ntime = (int)ntime;
 				int T = (int)div_up<long>(2 * n, 128);
-				P.ntile = T * (T + 1) / 2;
+				P.ntile = 0;
+				for( int i=0; i<T; ++i ) P.ntile += i / 2 + 1;     // (row block, column-block pair) units
 				P.alpha = (float)alpha; P.beta = (float)beta; P.conj_u = conj_u;
-				size_t smem = (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 64 * 65 * sizeof(float2) +
+				size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 64 * 65 * sizeof(float2) +
 				              (2 * TC_STAGES + 1) * sizeof(uint64_t) + 16;
 				smem += 1024;   // room for the 1024-byte alignment of the dynamic window
 				BFB_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
