@@ -121,7 +121,7 @@ corr_simt_kernel(SimtParams P) {
 }
 
 // ============================================================ tcgen05 kernel
-enum { TC_KT = 64, TC_STAGES = 3, TC_TILE_BYTES = TC_KT * 128, TC_THREADS = 192,
+enum { TC_KT = 64, TC2_STAGES = 3, TC_TILE_BYTES = TC_KT * 128, TC_THREADS = 192,
        TC_STAGE_BYTES = 3 * TC_TILE_BYTES };    // A | B0 | B1
 
 struct TcParams {
@@ -184,6 +184,69 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(uint32_t n_dim) {
 	return d;
 }
 
+// Epilogue of one (row block I, column blocks J0 .. J0+nb-1) unit, run by warps
+// 2..5: TMEM -> registers (32x32b.x32), combine the interleaved re/im rows of
+// the real Gram matrix into complex visibilities with a lane-pair shuffle,
+// stage through shared memory and store coalesced lower-triangle cf32.
+__device__ __forceinline__ void tc_epilogue(uint64_t* tmem_bar, uint32_t tmem_base, float2* staging,
+                                            TcParams const& P, int batch, int I, int J0, int nb,
+                                            int warp, int lane) {
+	mbar_wait(tmem_bar, 0);
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+	const int m = quarter * 32 + lane;                  // row of the 128 x 256 int32 tile
+	const int il = m >> 1, par = m & 1;                 // complex row, re/im row of the pair
+	float* stf = (float*)staging;
+	const int te = threadIdx.x - 64;                    // 0..127
+	float2* cb = P.c + (long)batch * P.c_batch;
+	for( int h=0; h<nb; ++h ) {
+		const int J = J0 + h;
+#pragma unroll 1
+		for( int c0=0; c0<128; c0+=32 ) {
+			uint32_t r[32];
+			const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * h + c0);
+			asm volatile(
+				"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+				"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+				"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+				: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+				  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+				  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+				  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+				: "r"(taddr));
+			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+			for( int q=0; q<16; ++q ) {
+				// even row 2i holds (G[2i][2j], G[2i][2j+1]); odd row holds
+				// (G[2i+1][2j], G[2i+1][2j+1]); swap the second entries.
+				int mine0 = (int)r[2*q], mine1 = (int)r[2*q+1];
+				int other1 = __shfl_xor_sync(0xffffffffu, mine1, 1);
+				// even lane: Re = G[2i][2j] + G[2i+1][2j+1]; odd lane: Im = G[2i][2j+1] - G[2i+1][2j]
+				int v = par ? (other1 - mine0) : (mine0 + other1);
+				int jl = (c0 >> 1) + q;
+				stf[(il * 65 + jl) * 2 + par] = (float)v;
+			}
+		}
+		// all four epilogue warps have staged their rows
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+		for( int idx = te; idx < 64 * 64; idx += 128 ) {
+			int il2 = idx >> 6, jl2 = idx & 63;
+			int i = I * 64 + il2, j = J * 64 + jl2;
+			if( i < P.n && j < P.n && i >= j ) {
+				float2 v = staging[il2 * 65 + jl2];
+				if( P.conj_u ) v.y = -v.y;
+				float2 o = make_float2(P.alpha * v.x, P.alpha * v.y);
+				float2* dst = cb + (long)i * P.c_row + j;
+				if( P.beta != 0.f ) { float2 old = *dst; o.x += P.beta * old.x; o.y += P.beta * old.y; }
+				*dst = o;
+			}
+		}
+		// the staging buffer is reused by the second column block
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+	}
+	}
+
+template<int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 	extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -276,66 +339,144 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 			__syncwarp();
 		}
 	} else {
-		// ===================== epilogue (warps 2..5) =====================
-		mbar_wait(tmem_bar, 0);
-		asm volatile("tcgen05.fence::after_thread_sync;");
-		const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
-		const int m = quarter * 32 + lane;                  // row of the 128 x 256 int32 tile
-		const int il = m >> 1, par = m & 1;                 // complex row, re/im row of the pair
-		float* stf = (float*)staging;
-		const int te = threadIdx.x - 64;                    // 0..127
-		float2* cb = P.c + (long)batch * P.c_batch;
-		for( int h=0; h<nb; ++h ) {
-			const int J = J0 + h;
-#pragma unroll 1
-			for( int c0=0; c0<128; c0+=32 ) {
-				uint32_t r[32];
-				const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * h + c0);
-				asm volatile(
-					"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-					"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-					"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-					: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-					  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-					  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-					  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-					: "r"(taddr));
-				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-				for( int q=0; q<16; ++q ) {
-					// even row 2i holds (G[2i][2j], G[2i][2j+1]); odd row holds
-					// (G[2i+1][2j], G[2i+1][2j+1]); swap the second entries.
-					int mine0 = (int)r[2*q], mine1 = (int)r[2*q+1];
-					int other1 = __shfl_xor_sync(0xffffffffu, mine1, 1);
-					// even lane: Re = G[2i][2j] + G[2i+1][2j+1]; odd lane: Im = G[2i][2j+1] - G[2i+1][2j]
-					int v = par ? (other1 - mine0) : (mine0 + other1);
-					int jl = (c0 >> 1) + q;
-					stf[(il * 65 + jl) * 2 + par] = (float)v;
-				}
-			}
-			// all four epilogue warps have staged their rows
-			asm volatile("bar.sync 1, 128;" ::: "memory");
-			for( int idx = te; idx < 64 * 64; idx += 128 ) {
-				int il2 = idx >> 6, jl2 = idx & 63;
-				int i = I * 64 + il2, j = J * 64 + jl2;
-				if( i < P.n && j < P.n && i >= j ) {
-					float2 v = staging[il2 * 65 + jl2];
-					if( P.conj_u ) v.y = -v.y;
-					float2 o = make_float2(P.alpha * v.x, P.alpha * v.y);
-					float2* dst = cb + (long)i * P.c_row + j;
-					if( P.beta != 0.f ) { float2 old = *dst; o.x += P.beta * old.x; o.y += P.beta * old.y; }
-					*dst = o;
-				}
-			}
-			// the staging buffer is reused by the second column block
-			asm volatile("bar.sync 1, 128;" ::: "memory");
-		}
+		tc_epilogue(tmem_bar, tmem_base, staging, P, batch, I, J0, nb, warp, lane);
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
 	__syncthreads();
 	if( warp == 1 ) {
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(256));
 	}
+}
+
+// ---------------------------------------------------------------------------
+// Cluster variant: a CTA pair owns the 256 x 256 super tile (row blocks 2 II
+// and 2 II + 1) x (column blocks 2 JJ and 2 JJ + 1), JJ <= II.  Each CTA loads
+// ONE of the two column blocks per K slab and TMA-multicasts it to both CTAs, so
+// the pair moves A0 + A1 + B0 + B1 = 32 KB per slab for four output blocks
+// (8 KB per block instead of 12).  On diagonal super tiles the row blocks ARE
+// the column blocks and nothing else is loaded.  A stage may be refilled only
+// after BOTH CTAs' MMAs have released it: every tcgen05.commit is multicast to
+// the empty barrier of both CTAs (count 2).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                               int x, int y, int z, uint16_t mask) {
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+		" [%0], [%1, {%3, %4, %5}], [%2], %6;"
+		:: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "h"(mask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS)
+corr_tc2_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
+	extern __shared__ __align__(1024) unsigned char tc_smem[];
+	unsigned char* tiles = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
+	float2* staging = (float2*)(tiles + TC2_STAGES * TC_STAGE_BYTES);
+	uint64_t* full_bar  = (uint64_t*)(staging + 64 * 65);
+	uint64_t* empty_bar = full_bar + TC2_STAGES;
+	uint64_t* tmem_bar  = empty_bar + TC2_STAGES;
+	uint32_t* tmem_slot = (uint32_t*)(tmem_bar + 1);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int batch = blockIdx.y;
+	const int rank = (int)cluster_ctarank();            // 0 / 1: upper / lower row block of the pair
+	// super tile index -> (II, JJ), II >= JJ
+	const int st = blockIdx.x >> 1;
+	int II = (int)((sqrtf(8.f * st + 1.f) - 1.f) * 0.5f);
+	while( II * (II + 1) / 2 > st ) --II;
+	while( (II + 1) * (II + 2) / 2 <= st ) ++II;
+	const int JJ = st - II * (II + 1) / 2;
+	const bool sdiag = (II == JJ);
+	const int I = 2 * II + rank, J0 = 2 * JJ;
+	// column blocks this CTA needs: on the diagonal super tile the upper row
+	// block only has its own diagonal block
+	const int nb = (sdiag && rank == 0) ? 1 : 2;
+	const int nk = (P.ntime + TC_KT - 1) / TC_KT;
+
+	if( threadIdx.x == 0 ) {
+		for( int s=0; s<TC2_STAGES; ++s ) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
+		mbar_init(tmem_bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if( warp == 1 ) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+		             :: "r"(smem_u32(tmem_slot)), "n"(256));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const uint32_t tmem_base = *tmem_slot;
+	// the peer's barriers must be initialised before anything is multicast to it
+	cluster_sync_all();
+
+	if( warp == 0 ) {
+		// ===================== TMA producer =====================
+		if( lane == 0 ) {
+			// both column blocks always arrive (one from each CTA); the row block
+			// is loaded only off the diagonal
+			const uint32_t bytes = (uint32_t)TC_TILE_BYTES * (sdiag ? 2 : 3);
+			for( int it=0; it<nk; ++it ) {
+				const int s = it % TC2_STAGES;
+				const uint32_t ph = (it / TC2_STAGES) & 1;
+				mbar_wait(&empty_bar[s], ph ^ 1);            // both CTAs have released the stage
+				unsigned char* a = tiles + (size_t)s * TC_STAGE_BYTES;
+				mbar_expect_tx(&full_bar[s], bytes);
+				if( !sdiag ) tma_load_3d(a, &tmap, &full_bar[s], 128 * I, it * TC_KT, batch);
+				tma_load_3d_mc(a + (1 + rank) * TC_TILE_BYTES, &tmap, &full_bar[s],
+				               128 * (J0 + rank), it * TC_KT, batch, (uint16_t)0x3);
+			}
+		}
+	} else if( warp == 1 ) {
+		// ===================== MMA issuer =====================
+		const uint32_t idesc = umma_idesc_i8(nb == 2 ? 256u : 128u);
+		for( int it=0; it<nk; ++it ) {
+			const int s = it % TC2_STAGES;
+			const uint32_t ph = (it / TC2_STAGES) & 1;
+			mbar_wait(&full_bar[s], ph);
+			asm volatile("tcgen05.fence::after_thread_sync;");
+			if( lane == 0 ) {
+				const uint32_t st_addr = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES);
+				const uint32_t b_addr = st_addr + TC_TILE_BYTES;
+				const uint32_t a_addr = sdiag ? b_addr + rank * TC_TILE_BYTES : st_addr;
+#pragma unroll
+				for( int kk=0; kk<TC_KT/32; ++kk ) {
+					const uint64_t da = umma_desc_mn_sw128(a_addr + kk * 32 * 128);
+					const uint64_t db = umma_desc_mn_sw128(b_addr + kk * 32 * 128);
+					const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+					asm volatile(
+						"{\n\t.reg .pred p;\n\t"
+						"setp.ne.b32 p, %4, 0;\n\t"
+						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+						:: "r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+				}
+				// release the stage in BOTH CTAs once these MMAs have consumed it
+				asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+				             :: "r"(smem_u32(&empty_bar[s])), "h"((uint16_t)0x3) : "memory");
+				if( it == nk - 1 ) {
+					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+					             :: "r"(smem_u32(tmem_bar)) : "memory");
+				}
+			}
+			__syncwarp();
+		}
+	} else {
+		tc_epilogue(tmem_bar, tmem_base, staging, P, batch, I, J0, nb, warp, lane);
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	if( warp == 1 ) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(256));
+	}
+	// neither CTA may exit while the other can still multicast into it
+	cluster_sync_all();
 }
 
 // ------------------------------------------------------------------ host side
@@ -418,13 +559,34 @@ BFstatus correlate(BFdtype utype, const void* udata, long stride_t, long stride_
 				P.ntile = 0;
 				for( int i=0; i<T; ++i ) P.ntile += i / 2 + 1;     // (row block, column-block pair) units
 				P.alpha = (float)alpha; P.beta = (float)beta; P.conj_u = conj_u;
-				size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 64 * 65 * sizeof(float2) +
-				              (2 * TC_STAGES + 1) * sizeof(uint64_t) + 16;
-				smem += 1024;   // room for the 1024-byte alignment of the dynamic window
-				BFB_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				                              (int)smem), BF_STATUS_INTERNAL_ERROR);
-				dim3 grid(P.ntile, (unsigned)kb);
-				corr_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, P);
+				static const bool use_cluster = getenv("BFB_LINALG_CLUSTER") != nullptr;
+				static const int  nstage = getenv("BFB_LINALG_STAGES") ? atoi(getenv("BFB_LINALG_STAGES")) : 3;
+				auto smem_for = [](int stages) {
+					return (size_t)stages * TC_STAGE_BYTES + 64 * 65 * sizeof(float2) +
+					       (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;   // + 1024: alignment of the window
+				};
+				if( use_cluster && T >= 2 ) {
+					int TT = (T + 1) / 2;                           // 256-row super blocks
+					size_t smem = smem_for(TC2_STAGES);
+					BFB_CUDA(cudaFuncSetAttribute(corr_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					                              (int)smem), BF_STATUS_INTERNAL_ERROR);
+					dim3 grid2(2 * (TT * (TT + 1) / 2), (unsigned)kb);
+					corr_tc2_kernel<<<grid2, TC_THREADS, smem, st>>>(tmap, P);
+				} else {
+					dim3 grid(P.ntile, (unsigned)kb);
+#define BFB_TC_LAUNCH(S_) do { size_t smem = smem_for(S_); \
+						BFB_CUDA(cudaFuncSetAttribute(corr_tc_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+						                              (int)smem), BF_STATUS_INTERNAL_ERROR); \
+						corr_tc_kernel<S_><<<grid, TC_THREADS, smem, st>>>(tmap, P); } while(0)
+					switch( nstage ) {
+					case 2:  BFB_TC_LAUNCH(2); break;
+					case 4:  BFB_TC_LAUNCH(4); break;
+					case 5:  BFB_TC_LAUNCH(5); break;
+					case 8:  BFB_TC_LAUNCH(8); break;
+					default: BFB_TC_LAUNCH(3); break;
+					}
+#undef BFB_TC_LAUNCH
+				}
 				count_launch();
 				BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
 				continue;
