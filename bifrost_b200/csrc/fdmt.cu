@@ -18,6 +18,15 @@
 //
 // All index arithmetic is 64-bit (the reference's 32-bit `t + ostride*row`
 // overflows at 4096 chan x 128k samples).
+//
+// Schedules (all produce the same bits; tests/test_fdmt.py runs each):
+//   v3 (default, 1-byte inputs)  three shared-memory tile passes,
+//        fdmt_tiles.cuh: steps 1..K from the raw input, then the remaining
+//        steps in passes of up to 4 steps over (band, delay block, time tile)
+//   v2   fused head kernel (steps 0..K in shared memory, any input dtype) +
+//        one row-blocked launch per remaining step      BFB_FDMT_TILES=0
+//   v1   one launch per step, the reference's schedule  BFB_FDMT_V1=1
+//        (also used for negative_delays)
 #include "core.hpp"
 #include "shape.hpp"
 #include "fdmt_plan.hpp"

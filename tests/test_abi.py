@@ -83,3 +83,21 @@ def test_invalid_arguments_return_status_not_crash():
     with pytest.raises(RuntimeError):
         from bifrost_b200.libbifrost import _check
         _check(_bf.BF_STATUS_INVALID_SHAPE)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under bifrost_b200/ (Python or
+    C++/CUDA) may import, include or load it, and the binding must fail loudly
+    when the CUDA library is missing (no CPU fallback)."""
+    import re
+    pkg = os.path.join(ROOT, 'bifrost_b200')
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.hpp', '.h')):
+                text = open(os.path.join(dirpath, f), errors='replace').read()
+                if re.search(r'^\s*(from|import)\s+oracle\b|#include\s+"[^"]*oracle|libfdmt_oracle|oracle/_ref', text, re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert offenders == []
+    src = open(os.path.join(pkg, 'libbifrost.py')).read()
+    assert 'raise' in src and 'libbifrost_b200' in src
