@@ -251,6 +251,25 @@ def test_large_gulp_properties():
     np.testing.assert_array_equal(out2[:, 2000:ntime - md], out[:, 1000:ntime - md - 1000])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("md,f0,bw", [(204, 1000., 400.), (794, 1000., 400.), (1621, 1200., 300.)])
+def test_schedules_agree_bit_for_bit_at_baseline_sizes(md, f0, bw):
+    """BASELINE config 2 geometry (4096 channels; max_delay 204 / 794 / 1621 as in
+    SURVEY 8d) on a shortened gulp: the default tile-pass schedule must give the
+    same bits as the step-by-step schedule, which the small cases pin against the
+    oracle and the reference's own kernels."""
+    nchan, ntime = 4096, 6000 + md
+    rng = np.random.default_rng(md)
+    x = np.clip(np.rint(rng.normal(0, 20, size=(nchan, ntime))), -127, 127).astype(np.int8)
+    got = run_gpu(x, md, f0, bw / nchan)
+    os.environ['BFB_FDMT_V1'] = '1'
+    try:
+        want = run_gpu(x, md, f0, bw / nchan)
+    finally:
+        os.environ.pop('BFB_FDMT_V1', None)
+    assert_same_bits(got, want)
+
+
 def test_plan_that_leaves_its_parent_band_is_rejected():
     """nchan=256, max_delay=300 at 1000-1400 MHz makes a source row index fall
     outside its parent band (step 7); the reference hits assert() and aborts

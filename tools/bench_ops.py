@@ -109,6 +109,21 @@ def main():
                Msamples_per_s=round(w['nchan'] * bench.NTIME_OUT / ms / 1e3, 1))
         del d_in, d_out, plan
 
+    if 'fdmt_scaling' in ops:
+        # the same 4096-channel gulp at max_delay 204 / 1621
+        import bench
+        for md, f0, bw in ((204, 1000., 400.), (1621, 1200., 300.)):
+            ntime = bench.NTIME_OUT + md
+            x = rng.integers(-64, 64, size=(4096, ntime), dtype=np.int8)
+            d_in = bf.asarray(x, space='cuda')
+            d_out = bf.zeros((md, ntime), 'f32', 'cuda')
+            plan = bf.fdmt.Fdmt()
+            plan.init(4096, md, f0, bw / 4096)
+            ms = timeit(lambda: plan.execute(d_in, d_out), stream=stream)
+            report('fdmt 4096x%d i8 md=%d' % (ntime, md), ms, ntime * (4096 + 4 * md),
+                   Msamples_per_s=round(4096 * bench.NTIME_OUT / ms / 1e3, 1))
+            del d_in, d_out, plan
+
     # ---- GUPPI chain (config 3): ci8 [nframe, 4096 chan, 4096 fine_time, 2 pol]
     nframe, nchan, nfft, npol = args.nframe, 4096, 4096, 2
     I = nframe * nchan * nfft * npol * 2         # bytes of ci8 in the gulp

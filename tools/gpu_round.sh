@@ -3,7 +3,8 @@
 # command, and --set full captures of the dominant kernels.  Outputs in gpurun_out/.
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+timeout 600 python tools/bench_ops.py --ops fdmt,fdmt_scaling,correlate,transpose,fft,detect,reduce,accumulate --nframe 16 > gpurun_out/bench_ops.jsonl 2>&1; tail -12 gpurun_out/bench_ops.jsonl | cut -c1-200
 tail -3 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; echo "bench rc=$?"
 cat gpurun_out/bench_r01.json
