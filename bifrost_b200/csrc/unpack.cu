@@ -72,9 +72,51 @@ unpack_kernel(const unsigned char* __restrict__ in, Out* __restrict__ out, long 
 	}
 }
 
+// 8-bit outputs, 16-byte aligned: one thread turns 16 packed bytes (one uint4
+// load) into 16 * 8/NBIT output bytes (8/NBIT uint4 stores).  The field
+// arithmetic is unpack_byte's, so results are identical to the scalar kernel.
+template<int NBIT, bool SIGNED>
+__global__ void __launch_bounds__(256)
+unpack_vec_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long nvec,
+                  bool rev, bool msb, bool conj) {
+	constexpr int K = 8 / NBIT;
+	long gstride = (long)gridDim.x * blockDim.x;
+	for( long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gstride ) {
+		const uint4 v = __ldg(in + i);
+		const unsigned w[4] = {v.x, v.y, v.z, v.w};
+		unsigned ow[4 * K];
+#pragma unroll
+		for( int q=0; q<4*K; ++q ) ow[q] = 0;
+#pragma unroll
+		for( int b=0; b<16; ++b ) {
+			signed char o[K];
+			unpack_byte<NBIT,SIGNED>((w[b >> 2] >> (8 * (b & 3))) & 0xFFu, rev, msb, conj, o);
+#pragma unroll
+			for( int j=0; j<K; ++j ) {
+				const int e = b * K + j;
+				ow[e >> 2] |= (unsigned)(unsigned char)o[j] << (8 * (e & 3));
+			}
+		}
+#pragma unroll
+		for( int q=0; q<K; ++q )
+			out[i * K + q] = make_uint4(ow[4*q], ow[4*q+1], ow[4*q+2], ow[4*q+3]);
+	}
+}
+
 template<int NBIT, bool SIGNED, typename Out>
 static BFstatus launch_unpack(const void* in, void* out, long nbyte, bool rev, bool msb,
                               bool conj, cudaStream_t s) {
+	if( sizeof(Out) == 1 && nbyte >= 16 && (uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0 ) {
+		long nvec = nbyte / 16;
+		unsigned vgrid = (unsigned)std::min<long>(div_up<long>(nvec, 256), 148L * 16);
+		unpack_vec_kernel<NBIT,SIGNED><<<vgrid, 256, 0, s>>>((const uint4*)in, (uint4*)out, nvec, rev, msb, conj);
+		count_launch();
+		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+		in  = (const unsigned char*)in + nvec * 16;
+		out = (Out*)out + nvec * 16 * (8 / NBIT);
+		nbyte -= nvec * 16;
+		if( nbyte == 0 ) return BF_STATUS_SUCCESS;
+	}
 	bool vec_ok = ((uintptr_t)out % (8 / NBIT)) == 0;
 	unsigned grid = (unsigned)std::min<long>(div_up<long>(nbyte, 256), 148L * 32);
 	unpack_kernel<NBIT,SIGNED,Out><<<grid, 256, 0, s>>>((const unsigned char*)in, (Out*)out,
