@@ -455,6 +455,117 @@ fft4096_fast_kernel(const __grid_constant__ FftPass<float> P) {
 	}
 }
 
+// v[m] *= w^m, m = 1..R-1, from the tabulated powers w^(2^i) (R = 2, 4, 8, 16).
+template<int R>
+__device__ __forceinline__ void fast_twiddle(float (&ar)[R], float (&ai)[R], const float2* __restrict__ tbq) {
+	float2 w[R];
+#pragma unroll
+	for( int i=0; (1 << i) < R; ++i ) w[1 << i] = tbq[i * 256];
+#pragma unroll
+	for( int m=3; m<R; ++m ) {
+		if( (m & (m - 1)) == 0 ) continue;                  // powers of two come from the table
+		const int hi = (m >= 8) ? 8 : (m >= 4) ? 4 : 2;     // m = hi + rest, rest < hi
+		w[m] = cmulf(w[m - hi], w[hi]);
+	}
+#pragma unroll
+	for( int m=1; m<R; ++m ) {
+		float tr = ar[m] * w[m].x - ai[m] * w[m].y;
+		ai[m] = ar[m] * w[m].y + ai[m] * w[m].x;
+		ar[m] = tr;
+	}
+}
+
+// Contiguous c2c transforms of length N = 256 * R3 (256 .. 4096): 16 points per
+// thread, N/16 threads per line, 256/(N/16) lines per CTA, radix 16 x 16 x R3
+// Stockham stages through padded interleaved shared memory (same scheme as
+// fft4096.cuh); the last stage stores straight to global memory.
+template<int KIND, int R3>
+__global__ void __launch_bounds__(256, 2)
+fft_fast_kernel(const __grid_constant__ FftPass<float> P) {
+	constexpr int N = 256 * R3, T = 16 * R3, G = 256 / T, Q = 16 / R3;
+	constexpr int LOG = (R3 == 16) ? 4 : (R3 == 8) ? 3 : (R3 == 4) ? 2 : (R3 == 2) ? 1 : 0;
+	constexpr int PITCH = N + (N >> 4) + 1;
+	extern __shared__ __align__(16) unsigned char fast_smem[];
+	float2* buf = (float2*)fast_smem;
+	float2* tb  = buf + G * PITCH;                       // [4 + Q*LOG][256] twiddle bases
+	const int tid = threadIdx.x, g = tid / T, p = tid % T;
+	buf += g * PITCH;
+	const float2* tw = (const float2*)P.twid;            // W_N^k
+#pragma unroll
+	for( int i=0; i<4; ++i ) tb[i * 256 + tid] = tw[(R3 * ((p & 15) << i)) & (N - 1)];
+#pragma unroll
+	for( int q=0; q<Q; ++q )
+#pragma unroll
+		for( int i=0; i<LOG; ++i ) tb[(4 + q * LOG + i) * 256 + tid] = tw[(((p + T * q) & 255) << i) & (N - 1)];
+	// (the first barrier below publishes the table)
+	for( long L0 = (long)blockIdx.x * G; L0 < P.nline; L0 += (long)gridDim.x * G ) {
+		const long L = L0 + g;
+		const bool live = L < P.nline;
+		long ioff = 0, ooff = 0, twc = 0;
+		if( live ) fft_line_offsets(P, L, ioff, ooff, twc);
+		const char* iline = (const char*)P.in + ioff;
+		char* oline = (char*)P.out + ooff;
+		const long os = P.out_axis_stride;            // bytes between output points (8 unless four-step pass B)
+		float vr[16], vi[16];
+		const float sgn = (P.shift == 1 && (p & 1)) ? -1.f : 1.f;     // index parity = parity of p (T is even)
+		const float sc = sgn * P.scale_in;
+#pragma unroll
+		for( int m=0; m<16; ++m ) {
+			int e = p + T * m;
+			if( P.shift == 2 ) e ^= N / 2;                            // rotate by n/2
+			float r = 0.f, i = 0.f;
+			if( live ) {
+				if( KIND == FK_CF32 )      { float2 v = ((const float2*)iline)[e]; r = v.x; i = v.y; }
+				else if( KIND == FK_CI8 )  { char2 v = ((const char2*)iline)[e];   r = v.x; i = v.y; }
+				else                       { short2 v = ((const short2*)iline)[e]; r = v.x; i = v.y; }
+			}
+			vr[m] = r * sc;
+			vi[m] = P.inverse ? -(i * sc) : i * sc;
+		}
+		// stage 1 (Ns = 1)
+		SDft<16>::apply(vr, vi);
+		__syncthreads();                              // previous readers of the buffer are done
+#pragma unroll
+		for( int t=0; t<16; ++t ) buf[spad(16 * p + t)] = make_float2(vr[t], vi[t]);
+		__syncthreads();
+		// stage 2 (Ns = 16)
+#pragma unroll
+		for( int m=0; m<16; ++m ) { float2 v = buf[spad(p + T * m)]; vr[m] = v.x; vi[m] = v.y; }
+		apply_twiddles(vr, vi, tb[tid], tb[256 + tid], tb[512 + tid], tb[768 + tid]);
+		SDft<16>::apply(vr, vi);
+		const int k2 = p & 15;
+		const int j0 = (p - k2) * 16 + k2;
+		if( R3 == 1 ) {
+			if( live ) {
+#pragma unroll
+				for( int t=0; t<16; ++t ) *(float2*)(oline + (long)(j0 + 16 * t) * os) = make_float2(vr[t], P.inverse ? -vi[t] : vi[t]);
+			}
+			continue;
+		}
+		__syncthreads();
+#pragma unroll
+		for( int t=0; t<16; ++t ) buf[spad(j0 + 16 * t)] = make_float2(vr[t], vi[t]);
+		__syncthreads();
+		// stage 3 (Ns = 256, radix R3): Q butterflies per thread
+#pragma unroll
+		for( int u=0; u<16; ++u ) { float2 v = buf[spad(p + T * u)]; vr[u] = v.x; vi[u] = v.y; }
+#pragma unroll
+		for( int q=0; q<Q; ++q ) {
+			float ar[R3], ai[R3];
+#pragma unroll
+			for( int m=0; m<R3; ++m ) { ar[m] = vr[q + Q * m]; ai[m] = vi[q + Q * m]; }
+			fast_twiddle<R3>(ar, ai, tb + (4 + q * LOG) * 256 + tid);
+			SDft<R3>::apply(ar, ai);
+			const int j = p + T * q, k = j & 255;
+			if( live ) {
+#pragma unroll
+				for( int t=0; t<R3; ++t )
+					*(float2*)(oline + (long)((j - k) * R3 + k + 256 * t) * os) = make_float2(ar[t], P.inverse ? -ai[t] : ai[t]);
+			}
+		}
+	}
+}
+
 } // namespace bfb
 
 using namespace bfb;
@@ -608,23 +719,34 @@ BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 	long osize = (out_real ? 1 : 2) * (long)sizeof(T);
 	P.b_fast_in  = std::abs(in.strides[axis])  != isize_in;
 	P.b_fast_out = std::abs(out.strides[axis]) != osize;
-	if( sizeof(T) == 4 && n == 4096 && !in_real && !in_herm && !out_real && n_out == n && !post_tw &&
-	    shift != 3 && !P.b_fast_in && !P.b_fast_out &&
+	if( sizeof(T) == 4 && n >= 256 && n <= 4096 && is_pow2(n) && !in_real && !in_herm && !out_real && n_out == n && !post_tw &&
+	    shift != 3 && !P.b_fast_in && (!P.b_fast_out || out.strides[axis] % 8 == 0) && out.strides[axis] > 0 &&
 	    (in.kind == FK_CF32 || in.kind == FK_CI8 || in.kind == FK_CI16) &&
 	    (uintptr_t)in.data % isize_in == 0 ) {
 		bool aligned = true;
 		for( int d=0; d<P.nouter; ++d ) aligned = aligned && (P.oistr[d] % isize_in == 0) && (P.oostr[d] % 8 == 0);
 		if( aligned ) {
-			size_t fsmem = ((size_t)SPEC_PITCH + 8 * 256) * sizeof(float2);
-			unsigned fgrid = (unsigned)std::min<long>(nline, 148L * 16);
+			const int r3 = (int)(n / 256);
+			const int lines = (int)(4096 / n);                   // lines per CTA
+			size_t fsmem = ((size_t)lines * (n + n / 16 + 1) + 12 * 256) * sizeof(float2);
+			unsigned fgrid = (unsigned)std::min<long>(div_up<long>(nline, lines), 148L * 16);
 			FftPass<float> const& PF = *(FftPass<float> const*)(const void*)&P;
-#define BFB_FFT_FAST(K_) do { \
-				BFB_CUDA(cudaFuncSetAttribute(fft4096_fast_kernel<K_>, \
+#define BFB_FFT_FAST2(K_, R_) do { \
+				BFB_CUDA(cudaFuncSetAttribute(fft_fast_kernel<K_, R_>, \
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), BF_STATUS_INTERNAL_ERROR); \
-				fft4096_fast_kernel<K_><<<fgrid, 256, fsmem, st>>>(PF); } while(0)
+				fft_fast_kernel<K_, R_><<<fgrid, 256, fsmem, st>>>(PF); } while(0)
+#define BFB_FFT_FAST(K_) do { \
+				switch( r3 ) { \
+				case 1:  BFB_FFT_FAST2(K_, 1);  break; \
+				case 2:  BFB_FFT_FAST2(K_, 2);  break; \
+				case 4:  BFB_FFT_FAST2(K_, 4);  break; \
+				case 8:  BFB_FFT_FAST2(K_, 8);  break; \
+				default: BFB_FFT_FAST2(K_, 16); break; \
+				} } while(0)
 			if( in.kind == FK_CF32 )     BFB_FFT_FAST(FK_CF32);
 			else if( in.kind == FK_CI8 ) BFB_FFT_FAST(FK_CI8);
 			else                         BFB_FFT_FAST(FK_CI16);
+#undef BFB_FFT_FAST2
 #undef BFB_FFT_FAST
 			count_launch();
 			BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
@@ -685,8 +807,9 @@ BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 	// ---- four-step: n = n1 * n2 (c2c, power of two only)
 	BFB_ASSERT(is_pow2(n) && !in_real && !in_herm && !out_real, BF_STATUS_UNSUPPORTED_SHAPE);
 	BFB_ASSERT(tmp, BF_STATUS_INSUFFICIENT_STORAGE);
-	long n2 = 4096, n1 = n / n2;
-	BFB_ASSERT(n1 <= FFT_NMAX_SMEM && n1 >= 16, BF_STATUS_UNSUPPORTED_SHAPE);
+	// n2 = 4096 when that leaves n1 >= 16 (n >= 65536); 16384 and 32768 split as 16 x n/16
+	long n2 = std::min<long>(4096, n / 16), n1 = n / n2;
+	BFB_ASSERT(n1 <= FFT_NMAX_SMEM && n1 >= 16 && n2 >= 16, BF_STATUS_UNSUPPORTED_SHAPE);
 	const long csize = 2 * sizeof(T);
 	// tmp holds [other dims (C order, axis removed)][k1][c2]
 	PassArray t;

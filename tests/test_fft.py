@@ -59,9 +59,11 @@ def test_c2c_nd_reference_shapes():
     c2c_case((33, 31, 65, 16), [0, 2], rng)
 
 
-def test_c2c_large_four_step():
+@pytest.mark.parametrize("n", [1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 20])
+def test_c2c_large_four_step(n):
+    """Lengths above the single-pass limit (8192): n = n1 * n2 with n2 = min(4096, n/16);
+    131072 is the README-exact GUPPI fine_time length (SURVEY 8d config 3 stretch)."""
     rng = np.random.default_rng(5)
-    n = 1 << 20
     x = (rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))).astype(np.complex64)
     for inverse, shift in [(False, False), (True, False), (False, True), (True, True)]:
         got = run(x, (2, n), 'cf32', [1], inverse, shift)

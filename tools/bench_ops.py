@@ -158,6 +158,21 @@ def main():
         report('chain.accumulate one frame', ms, 3 * 4 * 4 * nchan * nfft // 4)
         del d_r, d_acc
 
+    if 'fftsizes' in ops:
+        # c2c forward FFTs of other lengths (ci8 -> cf32), 2^28 complex samples each
+        for nfft_ in (256, 1024, 2048, 8192, 16384, 131072):
+            nbatch = (1 << 27) // nfft_
+            raw = rng.integers(-127, 128, size=(nbatch, nfft_, 2), dtype=np.int8)
+            xi = raw.view(bf.DataType('ci8').as_numpy_dtype()).reshape(nbatch, nfft_)
+            d_i = bf.asarray(xi, space='cuda')
+            d_o = bf.empty((nbatch, nfft_), 'cf32', 'cuda')
+            plan = bf.fft.Fft()
+            plan.init(d_i, d_o, axes=[1], apply_fftshift=False)
+            ms = timeit(lambda: plan.execute(d_i, d_o), nrep=5, stream=stream)
+            report('fft ci8->cf32 n=%d batch=%d' % (nfft_, nbatch), ms, 10 * nbatch * nfft_,
+                   Msamples_per_s=round(nbatch * nfft_ / ms / 1e3, 1))
+            del d_i, d_o, plan
+
     if 'correlate' in ops:
         nchan_c, nstand, npol_c = 512, 256, 2
         n = nstand * npol_c
