@@ -35,6 +35,7 @@
 #include <algorithm>
 #include <vector>
 #include <cstdlib>
+#include <cstring>
 
 namespace bfb {
 
@@ -765,6 +766,26 @@ BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
 	                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
 	BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
 	BFB_TRY(build_tail_passes(plan));
+	return BF_STATUS_SUCCESS;
+}
+
+BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+                         double exponent, int s0, int s1, int block_rows, int nwarp,
+                         int raw, int* header, int* items, int* aux) {
+	BFB_ASSERT(header, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(nchan > 1 && max_delay >= 1 && nwarp >= 1 && block_rows >= 1, BF_STATUS_INVALID_ARGUMENT);
+	FdmtPlan P;
+	bool ok = false;
+	BFB_TRY(ok = P.build((int)nchan, (int)max_delay, f0, df, exponent));
+	BFB_ASSERT(ok, BF_STATUS_INTERNAL_ERROR);
+	TilePass tp;
+	BFB_TRY(ok = build_tile_pass(P, s0, s1, block_rows, nwarp, &tp, raw != 0));
+	BFB_ASSERT(ok, BF_STATUS_UNSUPPORTED_SHAPE);
+	header[0] = tp.T; header[1] = tp.nprog; header[2] = tp.nphase; header[3] = tp.slots;
+	header[4] = tp.smem_floats; header[5] = tp.raw_bytes; header[6] = tp.edge_margin;
+	header[7] = (int)tp.items.size();
+	if( items ) memcpy(items, tp.items.data(), tp.items.size() * sizeof(int4));
+	if( aux && !tp.aux.empty() ) memcpy(aux, tp.aux.data(), tp.aux.size() * sizeof(int4));
 	return BF_STATUS_SUCCESS;
 }
 

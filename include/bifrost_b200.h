@@ -306,6 +306,18 @@ BFstatus bfSpectrometerFused(BFarray const* in, BFarray const* out,
 BFstatus bfFdmtPlanQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                          double exponent, int step, int* nrow, int* rows);
 
+/* B200 extension (test hook, host only): the work-item tables of one FDMT tile
+ * pass (steps s0..s1, delay blocks of about `block_rows` rows, `nwarp` warps per
+ * CTA; raw != 0: steps 1..s1 straight from a 1-byte input) as bfFdmtExecute
+ * would run it -- see csrc/fdmt_tiles.cuh for the item layout.
+ * header[8] = {T, nprog, nphase, slots, smem_floats, raw_bytes, edge_margin,
+ * nitem} with nitem = nprog*nphase*nwarp*slots; items (if not NULL) receives
+ * 4*nitem ints, aux (raw passes, if not NULL) 4*nprog*nwarp*slots ints.
+ * BF_STATUS_UNSUPPORTED_SHAPE when the pass cannot be tiled. */
+BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+                         double exponent, int s0, int s1, int block_rows, int nwarp,
+                         int raw, int* header, int* items, int* aux);
+
 /* Number of kernels this library has launched since load (all threads). */
 BFstatus bfGetLaunchCount(unsigned long long* count);
 
