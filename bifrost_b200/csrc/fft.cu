@@ -455,6 +455,79 @@ fft4096_fast_kernel(const __grid_constant__ FftPass<float> P) {
 	}
 }
 
+// 32-point forward DFT in registers: two 16-point DFTs of the even / odd
+// samples and the W_32^k butterflies.
+__device__ __forceinline__ void sdft32(float (&re)[32], float (&im)[32]) {
+	float er[16], ei[16], qr[16], qi[16];
+#pragma unroll
+	for( int k=0; k<16; ++k ) { er[k] = re[2*k]; ei[k] = im[2*k]; qr[k] = re[2*k+1]; qi[k] = im[2*k+1]; }
+	SDft<16>::apply(er, ei);
+	SDft<16>::apply(qr, qi);
+	const float c32[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+	                       0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+	                       0.19509032201612826785f, 0.f, -0.19509032201612826785f, -0.38268343236508977173f,
+	                       -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+	                       -0.92387953251128675613f, -0.98078528040323044913f};
+	const float s32[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+	                       0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+	                       0.98078528040323044913f, 1.f, 0.98078528040323044913f, 0.92387953251128675613f,
+	                       0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+	                       0.38268343236508977173f, 0.19509032201612826785f};
+#pragma unroll
+	for( int k=0; k<16; ++k ) {
+		const float tr = qr[k] * c32[k] + qi[k] * s32[k];      // q * exp(-2 pi i k / 32)
+		const float ti = qi[k] * c32[k] - qr[k] * s32[k];
+		re[k]      = er[k] + tr;  im[k]      = ei[k] + ti;
+		re[k + 16] = er[k] - tr;  im[k + 16] = ei[k] - ti;
+	}
+}
+
+// Four-step pass A (length N1 = 16 or 32 over a strided axis, inter-pass twiddle
+// on store): one thread owns one line and keeps the whole transform in
+// registers; consecutive threads are consecutive along the contiguous dim on
+// both sides, so loads and stores are coalesced and no shared memory is used.
+template<int KIND, int N1>
+__global__ void __launch_bounds__(256)
+fft_regs_kernel(const __grid_constant__ FftPass<float> P) {
+	const long L = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if( L >= P.nline ) return;
+	long ioff, ooff, twc;
+	fft_line_offsets(P, L, ioff, ooff, twc);
+	const char* iline = (const char*)P.in + ioff;
+	char* oline = (char*)P.out + ooff;
+	const float sc = ((P.shift == 3 && (twc & 1)) ? -1.f : 1.f) * P.scale_in;
+	float vr[N1], vi[N1];
+#pragma unroll
+	for( int m=0; m<N1; ++m ) {
+		const int e = (P.shift == 2) ? (m ^ (N1 / 2)) : m;       // rotate by n1/2
+		const char* q = iline + (long)e * P.in_axis_stride;
+		float r, i;
+		if( KIND == FK_CF32 )      { float2 v = *(const float2*)q; r = v.x; i = v.y; }
+		else if( KIND == FK_CI8 )  { char2 v = *(const char2*)q;   r = v.x; i = v.y; }
+		else                       { short2 v = *(const short2*)q; r = v.x; i = v.y; }
+		vr[m] = r * sc;
+		vi[m] = P.inverse ? -(i * sc) : i * sc;
+	}
+	if( N1 == 16 ) SDft<16>::apply((float*)vr, (float*)vi);
+	else           sdft32((float (&)[32])vr, (float (&)[32])vi);
+#pragma unroll
+	for( int k=0; k<N1; ++k ) {
+		float xr = vr[k], xi = P.inverse ? -vi[k] : vi[k];
+		if( P.post_twiddle ) {
+			const long m = (long)k * twc;                        // < N
+			const float* lo = P.tw_lo + 2 * (m & 4095);
+			const float* hi = P.tw_hi + 2 * (m >> 12);
+			const float wr = lo[0] * hi[0] - lo[1] * hi[1];
+			float wi = lo[0] * hi[1] + lo[1] * hi[0];
+			if( P.inverse ) wi = -wi;
+			const float tr = xr * wr - xi * wi;
+			xi = xr * wi + xi * wr;
+			xr = tr;
+		}
+		*(float2*)(oline + (long)k * P.out_axis_stride) = make_float2(xr, xi);
+	}
+}
+
 // v[m] *= w^m, m = 1..R-1, from the tabulated powers w^(2^i) (R = 2, 4, 8, 16).
 template<int R>
 __device__ __forceinline__ void fast_twiddle(float (&ar)[R], float (&ai)[R], const float2* __restrict__ tbq) {
@@ -719,6 +792,27 @@ BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 	long osize = (out_real ? 1 : 2) * (long)sizeof(T);
 	P.b_fast_in  = std::abs(in.strides[axis])  != isize_in;
 	P.b_fast_out = std::abs(out.strides[axis]) != osize;
+	if( sizeof(T) == 4 && (n == 16 || n == 32) && post_tw && !in_real && !in_herm && !out_real && n_out == n &&
+	    (shift == 0 || shift == 2 || shift == 3) &&
+	    (in.kind == FK_CF32 || in.kind == FK_CI8 || in.kind == FK_CI16) &&
+	    (uintptr_t)in.data % isize_in == 0 && in.strides[axis] % isize_in == 0 && out.strides[axis] % 8 == 0 ) {
+		bool aligned = true;
+		for( int d=0; d<P.nouter; ++d ) aligned = aligned && (P.oistr[d] % isize_in == 0) && (P.oostr[d] % 8 == 0);
+		if( aligned ) {
+			FftPass<float> const& PF = *(FftPass<float> const*)(const void*)&P;
+			unsigned rgrid = (unsigned)div_up<long>(nline, 256);
+#define BFB_FFT_REGS(K_) do { \
+				if( n == 16 ) fft_regs_kernel<K_, 16><<<rgrid, 256, 0, st>>>(PF); \
+				else          fft_regs_kernel<K_, 32><<<rgrid, 256, 0, st>>>(PF); } while(0)
+			if( in.kind == FK_CF32 )     BFB_FFT_REGS(FK_CF32);
+			else if( in.kind == FK_CI8 ) BFB_FFT_REGS(FK_CI8);
+			else                         BFB_FFT_REGS(FK_CI16);
+#undef BFB_FFT_REGS
+			count_launch();
+			BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+			return BF_STATUS_SUCCESS;
+		}
+	}
 	if( sizeof(T) == 4 && n >= 256 && n <= 4096 && is_pow2(n) && !in_real && !in_herm && !out_real && n_out == n && !post_tw &&
 	    shift != 3 && !P.b_fast_in && (!P.b_fast_out || out.strides[axis] % 8 == 0) && out.strides[axis] > 0 &&
 	    (in.kind == FK_CF32 || in.kind == FK_CI8 || in.kind == FK_CI16) &&
@@ -800,7 +894,9 @@ BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
                   cudaStream_t st) {
 	int shift = 0;
 	if( fftshift ) shift = inverse ? 2 : 1;
-	if( n <= FFT_NMAX_SMEM ) {
+	// 8192 fits one generic pass, but two fast passes (16 x 512) are quicker
+	const bool split8192 = n == 8192 && sizeof(T) == 4 && !in_real && !in_herm && !out_real && tmp;
+	if( n <= FFT_NMAX_SMEM && !split8192 ) {
 		return run_pass<T>(plan, ndim, batch_shape, axis, n, in, out, in_real, in_herm,
 		                   out_real, n_out, inverse, shift, st);
 	}
@@ -913,6 +1009,11 @@ BFstatus bfFftInit(BFfft plan, BFarray const* in, BFarray const* out, int rank,
 	}
 	for( int d=0; d<rank; ++d ) {
 		long n = plan->real_in ? in->shape[plan->axes[d]] : out->shape[plan->axes[d]];
+		if( n == 8192 && !plan->fp64 && !plan->real_in && !plan->real_out ) {
+			size_t elems = 1;                     // optional four-step split (run_axis)
+			for( int e=0; e<ndim; ++e ) elems *= out->shape[e];
+			ws = std::max(ws, elems * csize);
+		}
 		if( n > FFT_NMAX_SMEM ) {
 			BFB_ASSERT(is_pow2(n) && !plan->real_in && !plan->real_out, BF_STATUS_UNSUPPORTED_SHAPE);
 			BFB_ASSERT(n / 4096 <= FFT_NMAX_SMEM, BF_STATUS_UNSUPPORTED_SHAPE);
