@@ -837,9 +837,22 @@ BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 				case 8:  BFB_FFT_FAST2(K_, 8);  break; \
 				default: BFB_FFT_FAST2(K_, 16); break; \
 				} } while(0)
-			if( in.kind == FK_CF32 )     BFB_FFT_FAST(FK_CF32);
-			else if( in.kind == FK_CI8 ) BFB_FFT_FAST(FK_CI8);
-			else                         BFB_FFT_FAST(FK_CI16);
+			if( n == 4096 && !P.b_fast_out ) {
+				// the dedicated 4096-point kernel (no line groups, unit-stride store) is ~10 % quicker
+				size_t smem4k = ((size_t)SPEC_PITCH + 8 * 256) * sizeof(float2);
+				unsigned grid4k = (unsigned)std::min<long>(nline, 148L * 16);
+#define BFB_FFT_4K(K_) do { \
+					BFB_CUDA(cudaFuncSetAttribute(fft4096_fast_kernel<K_>, \
+						cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4k), BF_STATUS_INTERNAL_ERROR); \
+					fft4096_fast_kernel<K_><<<grid4k, 256, smem4k, st>>>(PF); } while(0)
+				if( in.kind == FK_CF32 )     BFB_FFT_4K(FK_CF32);
+				else if( in.kind == FK_CI8 ) BFB_FFT_4K(FK_CI8);
+				else                         BFB_FFT_4K(FK_CI16);
+#undef BFB_FFT_4K
+			}
+			else if( in.kind == FK_CF32 ) BFB_FFT_FAST(FK_CF32);
+			else if( in.kind == FK_CI8 )  BFB_FFT_FAST(FK_CI8);
+			else                          BFB_FFT_FAST(FK_CI16);
 #undef BFB_FFT_FAST2
 #undef BFB_FFT_FAST
 			count_launch();

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-timeout 600 python tools/bench_ops.py --ops fdmt,fdmt_scaling,correlate,transpose,fft,detect,reduce,accumulate --nframe 16 > gpurun_out/bench_ops.jsonl 2>&1; tail -12 gpurun_out/bench_ops.jsonl | cut -c1-200
+timeout 600 python tools/bench_ops.py --ops fdmt,fdmt_scaling,correlate,transpose,fft,detect,reduce,accumulate,fftsizes --nframe 16 > gpurun_out/bench_ops.jsonl 2>&1; tail -18 gpurun_out/bench_ops.jsonl | cut -c1-200
 tail -3 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; echo "bench rc=$?"
 cat gpurun_out/bench_r01.json
@@ -20,4 +20,5 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:fdm
   -o gpurun_out/r01_fdmt_tiles -f python tools/profile_fdmt.py 2 > gpurun_out/fdmt_tiles_full.log 2>&1; echo "ncu tiles rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"spectrometer|corr_tc" -s 1 -c 2 \
   -o gpurun_out/r01_spec_corr -f python tools/profile_ops.py > gpurun_out/spec_corr_full.log 2>&1; echo "ncu spec/corr rc=$?"
-ls -la gpurun_out | tail -20
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+ls gpurun_out | wc -l
