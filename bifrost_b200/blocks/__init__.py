@@ -1,6 +1,6 @@
 """Hot-path blocks with the call signatures of ``bifrost.blocks``
 (python/bifrost/blocks/*.py): copy, transpose, fft, detect, reduce,
-accumulate, fdmt, correlate -- plus ``spectrometer`` (the fused chain) and a
+accumulate, fdmt, correlate, unpack -- plus ``spectrometer`` (the fused chain) and a
 ``NumpySourceBlock`` / ``CallbackSinkBlock`` pair for feeding them."""
 from bifrost_b200.blocks.copy import copy, CopyBlock
 from bifrost_b200.blocks.transpose import transpose, TransposeBlock
@@ -10,5 +10,6 @@ from bifrost_b200.blocks.reduce import reduce, ReduceBlock
 from bifrost_b200.blocks.accumulate import accumulate, AccumulateBlock
 from bifrost_b200.blocks.fdmt import fdmt, FdmtBlock
 from bifrost_b200.blocks.correlate import correlate, CorrelateBlock
+from bifrost_b200.blocks.unpack import unpack, UnpackBlock
 from bifrost_b200.blocks.spectrometer import spectrometer, SpectrometerBlock
 from bifrost_b200.blocks.testing import NumpySourceBlock, CallbackSinkBlock, array_source, callback_sink

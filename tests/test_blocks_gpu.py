@@ -115,3 +115,27 @@ def test_config1_transpose_reduce_blocks():
     got = np.concatenate(out.chunks, 0)
     want = x.reshape(512, 8, 64, 4).sum(3).sum(1).reshape(512, 1, 64)
     np.testing.assert_allclose(got, want, rtol=1e-6)
+
+
+def test_unpack_block_ci4_to_ci8():
+    """blocks/unpack.py of the reference: ci4 voltages -> ci8 (gunpack path, bit-exact)."""
+    from oracle import unpack as ounpack
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 256, size=(64, 8, 32), dtype=np.uint8)
+    x = bf.ndarray(raw.view(bf.DataType('ci4').as_numpy_dtype()), dtype='ci4')
+    hdr = {'_tensor': {'dtype': 'ci4', 'shape': [-1, 8, 32], 'labels': ['time', 'freq', 'station'],
+                       'scales': [[0, 1e-3], [100.0, 0.1], None], 'units': ['s', 'MHz', None]},
+           'name': 'u', 'gulp_nframe': 16}
+    out = Collect()
+    with Pipeline() as p:
+        src = blocks.array_source(x, hdr, gulp_nframe=16)
+        b = blocks.copy(src, space='cuda')
+        b = blocks.unpack(b, 'ci8')
+        b = blocks.copy(b, space='system')
+        blocks.callback_sink(b, out.seq, out.data)
+        p.run()
+    assert out.headers[0]['_tensor']['dtype'] == 'ci8'
+    got = np.concatenate(out.chunks, 0)
+    got = np.stack([got['re'], got['im']], -1)
+    want = ounpack.unpack(raw, 4, True, gpu=True).reshape(64, 8, 32, 2)
+    np.testing.assert_array_equal(got, want)
