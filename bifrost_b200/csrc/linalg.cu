@@ -613,6 +613,131 @@ BFstatus correlate(BFdtype utype, const void* udata, long stride_t, long stride_
 
 } // namespace
 
+// ---------------------------------------------------------------------------
+// General product c = alpha a.b + beta c (reference: bfMatMul_ab,
+// src/linalg.cu:479-637, cuBLAS / the beamformer kernel there).  A plain tiled
+// SIMT GEMM with per-element loaders: any strides, conjugated views, and
+// ci8 / ci16 / cf32 / f32 (float accumulation) or f64 / cf64 (double) inputs.
+// It exists for API completeness (beamforming, reference test_linalg.py
+// matmul_ab cases); the tensor-core work of this library is the correlator.
+namespace bfb {
+
+struct AbOperand { const char* p; long sm, sk, sb[BF_MAX_DIMS]; int kind, conj; };   // kind: BFdtype
+struct AbParams {
+	AbOperand a, b;                      // a[m][k], b[k][n] (strides in bytes: sm = row-like, sk = k)
+	char* c; long c_m, c_n, c_b[BF_MAX_DIMS]; int c_kind;
+	int  M, N, K, nb; long bshape[BF_MAX_DIMS];
+	double alpha, beta;
+};
+
+template<typename R>
+__device__ __forceinline__ void ab_load(const char* p, int kind, int conj, R& re, R& im) {
+	switch( kind ) {
+	case BF_DTYPE_CI8:  { char2  v = *(const char2*)p;   re = v.x; im = v.y; break; }
+	case BF_DTYPE_CI16: { short2 v = *(const short2*)p;  re = v.x; im = v.y; break; }
+	case BF_DTYPE_CF32: { float2 v = *(const float2*)p;  re = v.x; im = v.y; break; }
+	case BF_DTYPE_CF64: { double2 v = *(const double2*)p; re = (R)v.x; im = (R)v.y; break; }
+	case BF_DTYPE_F32:  re = *(const float*)p;  im = 0; break;
+	case BF_DTYPE_F64:  re = (R)*(const double*)p; im = 0; break;
+	case BF_DTYPE_I8:   re = *(const signed char*)p; im = 0; break;
+	default:            re = 0; im = 0; break;
+	}
+	if( conj ) im = -im;
+}
+
+template<typename R>
+__global__ void __launch_bounds__(256)
+matmul_ab_kernel(AbParams P) {
+	__shared__ R As[2][16][17], Bs[2][16][17];            // [re/im][m or k][k or n]
+	long bidx = blockIdx.z, aoff = 0, boff = 0, coff = 0;
+	for( int d=P.nb-1; d>=0; --d ) {
+		long r = bidx % P.bshape[d]; bidx /= P.bshape[d];
+		aoff += r * P.a.sb[d]; boff += r * P.b.sb[d]; coff += r * P.c_b[d];
+	}
+	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+	const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+	R accr = 0, acci = 0;
+	for( int k0=0; k0<P.K; k0+=16 ) {
+		R re = 0, im = 0;
+		if( m < P.M && k0 + tx < P.K )
+			ab_load<R>(P.a.p + aoff + (long)m * P.a.sm + (long)(k0 + tx) * P.a.sk, P.a.kind, P.a.conj, re, im);
+		As[0][ty][tx] = re; As[1][ty][tx] = im;
+		re = 0; im = 0;
+		if( n < P.N && k0 + ty < P.K )
+			ab_load<R>(P.b.p + boff + (long)(k0 + ty) * P.b.sk + (long)n * P.b.sm, P.b.kind, P.b.conj, re, im);
+		Bs[0][ty][tx] = re; Bs[1][ty][tx] = im;
+		__syncthreads();
+#pragma unroll
+		for( int k=0; k<16; ++k ) {
+			const R ar = As[0][ty][k], ai = As[1][ty][k], br = Bs[0][k][tx], bi = Bs[1][k][tx];
+			accr += ar * br - ai * bi;
+			acci += ar * bi + ai * br;
+		}
+		__syncthreads();
+	}
+	if( m >= P.M || n >= P.N ) return;
+	char* cp = P.c + coff + (long)m * P.c_m + (long)n * P.c_n;
+	R outr = (R)P.alpha * accr, outi = (R)P.alpha * acci;
+	switch( P.c_kind ) {
+	case BF_DTYPE_CF32: { float2* q = (float2*)cp; if( P.beta != 0 ) { outr += (R)P.beta * q->x; outi += (R)P.beta * q->y; }
+	                      *q = make_float2((float)outr, (float)outi); break; }
+	case BF_DTYPE_CF64: { double2* q = (double2*)cp; if( P.beta != 0 ) { outr += (R)P.beta * (R)q->x; outi += (R)P.beta * (R)q->y; }
+	                      *q = make_double2((double)outr, (double)outi); break; }
+	case BF_DTYPE_F32:  { float* q = (float*)cp; if( P.beta != 0 ) outr += (R)P.beta * *q; *q = (float)outr; break; }
+	default:            { double* q = (double*)cp; if( P.beta != 0 ) outr += (R)P.beta * (R)*q; *q = (double)outr; break; }
+	}
+}
+
+static bool ab_kind_ok(BFdtype t) {
+	return t == BF_DTYPE_CI8 || t == BF_DTYPE_CI16 || t == BF_DTYPE_CF32 || t == BF_DTYPE_CF64 ||
+	       t == BF_DTYPE_F32 || t == BF_DTYPE_F64 || t == BF_DTYPE_I8;
+}
+
+static BFstatus matmul_ab(double alpha, BFarray const* a, BFarray const* b, double beta, BFarray const* c) {
+	BFB_ASSERT(space_on_device(a->space) && space_on_device(b->space), BF_STATUS_UNSUPPORTED_SPACE);
+	int nd = c->ndim;
+	BFB_ASSERT(a->ndim == nd && b->ndim == nd && nd >= 2 && nd <= BF_MAX_DIMS, BF_STATUS_INVALID_SHAPE);
+	BFB_ASSERT(ab_kind_ok(a->dtype) && ab_kind_ok(b->dtype), BF_STATUS_UNSUPPORTED_DTYPE);
+	BFB_ASSERT(c->dtype == BF_DTYPE_CF32 || c->dtype == BF_DTYPE_CF64 || c->dtype == BF_DTYPE_F32 ||
+	           c->dtype == BF_DTYPE_F64, BF_STATUS_UNSUPPORTED_DTYPE);
+	bool cplx_in = dtype_is_complex(a->dtype) || dtype_is_complex(b->dtype);
+	BFB_ASSERT(!cplx_in || dtype_is_complex(c->dtype), BF_STATUS_INVALID_DTYPE);
+	AbParams P;
+	P.M = (int)c->shape[nd-2]; P.N = (int)c->shape[nd-1]; P.K = (int)a->shape[nd-1];
+	BFB_ASSERT(a->shape[nd-2] == P.M && b->shape[nd-1] == P.N && b->shape[nd-2] == P.K, BF_STATUS_INVALID_SHAPE);
+	P.a.p = (const char*)a->data; P.a.sm = a->strides[nd-2]; P.a.sk = a->strides[nd-1];
+	P.a.kind = a->dtype; P.a.conj = a->conjugated ? 1 : 0;
+	P.b.p = (const char*)b->data; P.b.sk = b->strides[nd-2]; P.b.sm = b->strides[nd-1];
+	P.b.kind = b->dtype; P.b.conj = b->conjugated ? 1 : 0;
+	P.c = (char*)c->data; P.c_m = c->strides[nd-2]; P.c_n = c->strides[nd-1]; P.c_kind = c->dtype;
+	P.alpha = alpha; P.beta = beta;
+	P.nb = 0;
+	long nbatch = 1;
+	for( int d=0; d<nd-2; ++d ) {
+		BFB_ASSERT((a->shape[d] == c->shape[d] || a->shape[d] == 1) &&
+		           (b->shape[d] == c->shape[d] || b->shape[d] == 1), BF_STATUS_INVALID_SHAPE);
+		if( c->shape[d] == 1 ) continue;
+		P.bshape[P.nb] = c->shape[d];
+		P.a.sb[P.nb] = a->shape[d] == 1 ? 0 : a->strides[d];
+		P.b.sb[P.nb] = b->shape[d] == 1 ? 0 : b->strides[d];
+		P.c_b[P.nb] = c->strides[d];
+		nbatch *= c->shape[d];
+		++P.nb;
+	}
+	if( P.M == 0 || P.N == 0 || nbatch == 0 ) return BF_STATUS_SUCCESS;
+	BFB_ASSERT(nbatch <= 65535, BF_STATUS_UNSUPPORTED_SHAPE);
+	dim3 grid((unsigned)div_up<int>(P.N, 16), (unsigned)div_up<int>(P.M, 16), (unsigned)nbatch);
+	bool dbl = a->dtype == BF_DTYPE_F64 || a->dtype == BF_DTYPE_CF64 || b->dtype == BF_DTYPE_F64 ||
+	           b->dtype == BF_DTYPE_CF64;
+	if( dbl ) matmul_ab_kernel<double><<<grid, 256, 0, thread_stream()>>>(P);
+	else      matmul_ab_kernel<float ><<<grid, 256, 0, thread_stream()>>>(P);
+	count_launch();
+	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+	return BF_STATUS_SUCCESS;
+}
+
+} // namespace bfb
+
 extern "C" {
 
 BFstatus bfLinAlgCreate(BFlinalg* handle_ptr) {
@@ -634,9 +759,7 @@ BFstatus bfLinAlgMatMul(BFlinalg handle, double alpha, BFarray const* a, BFarray
 	BFB_ASSERT(a || b, BF_STATUS_INVALID_ARGUMENT);
 	BFB_ASSERT(c, BF_STATUS_INVALID_POINTER);
 	BFB_ASSERT(space_on_device(c->space), BF_STATUS_UNSUPPORTED_SPACE);
-	// General a.b products are cuBLAS calls in the reference
-	// (src/linalg.cu:479-637) and are not part of this build's hot path.
-	BFB_ASSERT(!(a && b), BF_STATUS_UNSUPPORTED);
+	if( a && b ) { BFB_TRY(return matmul_ab(alpha, a, b, beta, c)); }
 	BFarray const* x = a ? a : b;
 	BFB_ASSERT(space_on_device(x->space), BF_STATUS_UNSUPPORTED_SPACE);
 	BFB_ASSERT(x->ndim == c->ndim && x->ndim >= 2 && x->ndim <= BF_MAX_DIMS, BF_STATUS_INVALID_SHAPE);

@@ -241,7 +241,9 @@ BFstatus bfFftDestroy(BFfft plan);
 /* ------------------------------------------------------------------ *
  * LinAlg                              (ref: src/bifrost/linalg.h:43-54)
  * c = alpha*a.b + beta*c;  b==NULL: a.a^H;  a==NULL: b^H.b.
- * The a.a^H / b^H.b forms write the lower triangle only.
+ * The a.a^H / b^H.b forms write the lower triangle only (tcgen05 int8 path for
+ * ci8).  a.b is a general strided SIMT product (ci8/ci16/cf32/f32 with float
+ * accumulation, f64/cf64 with double; conjugated views honoured).
  * ------------------------------------------------------------------ */
 typedef struct BFlinalg_impl* BFlinalg;
 

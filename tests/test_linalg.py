@@ -168,13 +168,70 @@ def test_correlate_block_closed_form():
     np.testing.assert_allclose(got[:, il[0], il[1]], np.broadcast_to(expected[il], (nchan, len(il[0]))), rtol=1e-6)
 
 
+def H(x):
+    """Conjugate transpose of the last two axes as a view (test/test_linalg.py:41-43)."""
+    axes = list(range(x.ndim))
+    axes[-1], axes[-2] = axes[-2], axes[-1]
+    return x.transpose(axes).conj()
+
+
 @pytest.mark.gpu
-def test_unsupported_forms_return_status():
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_matmul_ab_float_types(dtype, transpose):
+    """test/test_linalg.py:110-135,275-285: c = a.b for real / complex floats, incl. H views."""
+    rng = np.random.default_rng(7)
+    for shape, k in [((11, 23), 7), ((11, 23), 23), ((5, 11, 23), 11), ((3, 64, 40), 33)]:
+        ashape, bshape = shape[:-2] + (shape[-2], k), shape[:-2] + (k, shape[-1])
+        a = (rng.random(ashape) * 127).astype(dtype)
+        b = (rng.random(bshape) * 127).astype(dtype)
+        if np.iscomplexobj(a):
+            a = a + 1j * (rng.random(ashape) * 50).astype(dtype)
+            b = b - 1j * (rng.random(bshape) * 50).astype(dtype)
+        ga, gb = (np.conj(np.swapaxes(b, -1, -2)), np.conj(np.swapaxes(a, -1, -2))) if transpose else (a, b)
+        want = np.matmul(ga, gb)
+        da, db = bf.asarray(a, space='cuda'), bf.asarray(b, space='cuda')
+        if transpose:
+            da, db = H(db), H(da)
+        dc = bf.asarray(np.zeros_like(want), space='cuda')
+        LinAlg().matmul(1, da, db, 0, dc)
+        np.testing.assert_allclose(np.asarray(dc.copy('system')), want, rtol=1e-4, atol=1e-5 * np.abs(want).max())
+
+
+@pytest.mark.gpu
+def test_matmul_ab_ci8_and_beamformer():
+    """test/test_linalg.py:90-109 (ci8 x ci8) and :136-150 (cf32 weights x ci8 voltages)."""
+    rng = np.random.default_rng(8)
+    m, n, k = 111, 223, 77
+    a = rand_ci8(rng, (m, k))
+    b = rand_ci8(rng, (k, n))
+    af = a['re'].astype(np.float32) + 1j * a['im'].astype(np.float32)
+    bfl = b['re'].astype(np.float32) + 1j * b['im'].astype(np.float32)
+    dc = bf.zeros((m, n), 'cf32', 'cuda')
+    LinAlg().matmul(1, bf.asarray(a, space='cuda'), bf.asarray(b, space='cuda'), 0, dc)
+    np.testing.assert_array_equal(np.asarray(dc.copy('system')), (af @ bfl).astype(np.complex64))
+    ntime, nbeam, nstand, nchan = 64, 5, 32, 3
+    x = rand_ci8(rng, (ntime, nchan, nstand * 2))
+    xf = x['re'].astype(np.float32) + 1j * x['im'].astype(np.float32)
+    w = (rng.integers(-127, 128, size=(nbeam, nchan, nstand * 2)) +
+         1j * rng.integers(-127, 128, size=(nbeam, nchan, nstand * 2))).astype(np.complex64)
+    want = np.matmul(w.transpose(1, 0, 2), xf.transpose(1, 2, 0))
+    d_x, d_w = bf.asarray(x, space='cuda'), bf.asarray(w, space='cuda')
+    d_b = bf.zeros(want.shape, 'cf32', 'cuda')
+    LinAlg().matmul(1, d_w.transpose((1, 0, 2)), d_x.transpose((1, 2, 0)), 0, d_b)
+    np.testing.assert_allclose(np.asarray(d_b.copy('system')), want, rtol=1e-5)
+    # beta path
+    LinAlg().matmul(0.5, d_w.transpose((1, 0, 2)), d_x.transpose((1, 2, 0)), 2.0, d_b)
+    np.testing.assert_allclose(np.asarray(d_b.copy('system')), 2.5 * want, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_invalid_forms_return_status():
     from bifrost_b200.libbifrost import _bf
     a = bf.empty((4, 8), 'cf32', 'cuda')
-    b = bf.empty((8, 4), 'cf32', 'cuda')
+    b = bf.empty((9, 4), 'cf32', 'cuda')
     c = bf.empty((4, 4), 'cf32', 'cuda')
     h = LinAlg()
     assert _bf.bfLinAlgMatMul(h.obj, 1.0, a.as_BFarray(), b.as_BFarray(), 0.0, c.as_BFarray()) == \
-        _bf.BF_STATUS_UNSUPPORTED
+        _bf.BF_STATUS_INVALID_SHAPE
     assert _bf.bfLinAlgMatMul(h.obj, 1.0, None, None, 0.0, c.as_BFarray()) == _bf.BF_STATUS_INVALID_ARGUMENT
