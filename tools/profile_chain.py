@@ -24,6 +24,17 @@ for _ in range(2):
     bf.detect(d_f, d_d, 'stokes', 1)
     bf.reduce(d_d.reshape(nframe, 4, nchan * nfft), d_r, 'sum')
     bf.accumulate(d_r[0:1], d_acc, 1.0)
+# other FFT lengths: 1024 (fast kernel) and 131072 (register pass A + fast pass B)
+for nfft_ in (1024, 131072):
+    nb = (1 << 25) // nfft_
+    xi = raw.reshape(-1)[:nb * nfft_ * 2].reshape(nb, nfft_, 2).view(bf.DataType('ci8').as_numpy_dtype()).reshape(nb, nfft_)
+    d_i = bf.asarray(xi, space='cuda')
+    d_o = bf.empty((nb, nfft_), 'cf32', 'cuda')
+    pl = bf.fft.Fft()
+    pl.init(d_i, d_o, axes=[1])
+    for _ in range(2):
+        pl.execute(d_i, d_o)
+    del d_i, d_o, pl
 # ci4 -> ci8 unpack of a 256 MB packed buffer
 nbyte = 1 << 28
 p8 = bf.asarray(rng.integers(0, 256, size=(nbyte,), dtype=np.uint8), space='cuda')
