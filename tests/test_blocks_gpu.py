@@ -139,3 +139,43 @@ def test_unpack_block_ci4_to_ci8():
     got = np.stack([got['re'], got['im']], -1)
     want = ounpack.unpack(raw, 4, True, gpu=True).reshape(64, 8, 32, 2)
     np.testing.assert_array_equal(got, want)
+
+
+def test_file_to_file_guppi_spectrometer_sigproc(tmp_path):
+    """GUPPI RAW file -> device -> fused spectrometer -> host -> sigproc filterbank
+    (SURVEY 8f.4): the file body equals what a callback sink sees, the header
+    carries the channelisation."""
+    from bifrost_b200 import guppi_raw, sigproc
+    nblock, nchan, nfft = 8, 4, 4096
+    rng = np.random.default_rng(12)
+    data = rng.integers(-100, 100, size=(nblock, nchan, nfft, 2, 2), dtype=np.int8)
+    path = str(tmp_path / 'volt.raw')
+    with open(path, 'wb') as f:
+        for b in range(nblock):
+            guppi_raw.write_header(dict(BACKEND='GUPPI', TELESCOP='GBT', SRC_NAME='FAKE', OBSFREQ=1500.0,
+                                        OBSBW=100.0, OBSNCHAN=nchan, NPOL=4, NBITS=8, BLOCSIZE=nchan * nfft * 4,
+                                        PKTIDX=b, PKTSIZE=nchan * nfft * 4, STT_IMJD=58849, STT_SMJD=0,
+                                        DIRECTIO=1), f)
+            data[b].tofile(f)
+    out = Collect()
+    with Pipeline() as p:
+        src = blocks.read_guppi_raw([path], gulp_nframe=2)
+        b = blocks.copy(src, space='cuda')
+        b = blocks.spectrometer(b, f_avg=4, n_int=4, gulp_nframe=2)
+        b = blocks.copy(b, space='system')
+        blocks.callback_sink(b, out.seq, out.data)
+        blocks.write_sigproc(b, path=str(tmp_path))
+        p.run()
+    want = np.concatenate(out.chunks, 0)
+    assert want.shape == (nblock // 4, 4, nchan * nfft // 4)
+    with open(str(tmp_path / 'volt.raw.fil'), 'rb') as f:
+        h = sigproc.read_header(f)
+        body = np.fromfile(f, dtype=np.float32)
+    assert h['nifs'] == 4 and h['nchans'] == nchan * nfft // 4 and h['nbits'] == 32 and h['data_type'] == 1
+    assert h['foff'] == pytest.approx(100.0 / nchan / nfft * 4) and h['telescope_id'] == 6
+    np.testing.assert_array_equal(body.reshape(want.shape), want)
+    # and the values are the spectrometer's (oracle chain), not just self-consistent
+    x = data.view(bf.DataType('ci8').as_numpy_dtype()).reshape(nblock, nchan, nfft, 2)
+    for i in range(nblock // 4):
+        ref = oracle_chain(x[4 * i:4 * i + 4], 4)
+        assert np.abs(want[i] - ref).max() <= 2e-5 * np.sqrt(np.mean(ref[0] ** 2))
