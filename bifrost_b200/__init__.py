@@ -17,6 +17,7 @@ from bifrost_b200 import fdmt, fft, linalg
 from bifrost_b200.reduce import reduce
 from bifrost_b200.transpose import transpose
 from bifrost_b200.unpack import unpack
+from bifrost_b200.quantize import quantize
 from bifrost_b200.map import map, detect, accumulate
 from bifrost_b200.spectrometer import spectrometer
 from bifrost_b200 import views

@@ -260,6 +260,13 @@ BFstatus bfLinAlgMatMul(BFlinalg handle, double alpha,
 BFstatus bfUnpack(BFarray const* in, BFarray const* out, BFbool align_msb);
 
 /* ------------------------------------------------------------------ *
+ * Quantize                          (ref: src/bifrost/quantize.h:40-42)
+ * out = IntType(rint(clip(in * scale))): f32 / cf32 in, 8/16/32-bit (complex)
+ * integers out, device arrays, contiguous.
+ * ------------------------------------------------------------------ */
+BFstatus bfQuantize(BFarray const* in, BFarray const* out, double scale);
+
+/* ------------------------------------------------------------------ *
  * Map                                  (ref: src/bifrost/map.h:82-94)
  * The reference JIT-compiles `func` with NVRTC.  This build ships fixed
  * sm_100a kernels for the expressions the hot-path blocks emit (detect:
