@@ -2,7 +2,7 @@
 
 A plain numpy / C restatement of the reference's algorithms for the path
 (FDMT, FFT-with-load-callbacks, detect, reduce, accumulate, transpose,
-correlator, unpack).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+correlator, unpack, quantize).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the
 product (``bifrost_b200``) never does and has no CPU fallback.
 
@@ -15,6 +15,7 @@ Pinning status (see DESIGN.md "Oracle"):
   fdmt        pinned against the reference CUDA library built for sm_100 and run
               under gpurun (oracle/ref_build.sh -> oracle/_ref/); golden outputs
               committed under tests/golden/ by tests/golden/make_fdmt_golden.py
+  quantize    pinned by the known answers of test/test_quantize.py:33-50
   detect      parity unpinned by the reference (no test); formulae of
               blocks/detect.py:102-136 are the spec
 """
