@@ -16,26 +16,23 @@ class AccumulateBlock(TransformBlock):
         return ('cuda',)
 
     def on_sequence(self, iseq):
-        ohdr = deepcopy(iseq.header)
-        otensor = ohdr['_tensor']
-        if 'scales' in otensor:
-            fax = otensor['shape'].index(-1)
-            s = otensor['scales'][fax]
-            otensor['scales'][fax] = [s[0], s[1] * self.nframe]
+        self.frame_count = 0                     # frames summed into the open output frame
+        hdr_out = deepcopy(iseq.header)
+        hdr_out['gulp_nframe'] = 1
+        t = hdr_out['_tensor']
         if self.dtype is not None:
-            otensor['dtype'] = self.dtype
-        ohdr['gulp_nframe'] = 1
-        self.frame_count = 0
-        return ohdr
+            t['dtype'] = self.dtype
+        if 'scales' in t:                        # one output frame spans nframe input frames
+            frame_axis = t['shape'].index(-1)
+            start, step = t['scales'][frame_axis]
+            t['scales'][frame_axis] = [start, step * self.nframe]
+        return hdr_out
 
     def on_data(self, ispan, ospan):
-        beta = 0. if self.frame_count == 0 else 1.
-        bf_accumulate(ispan.data, ospan.data, beta)
-        self.frame_count += 1
-        if self.frame_count == self.nframe:
-            self.frame_count = 0
-            return 1
-        return 0
+        # the first frame of an integration overwrites, the others add (b = beta*b + a)
+        bf_accumulate(ispan.data, ospan.data, 0. if self.frame_count == 0 else 1.)
+        self.frame_count = (self.frame_count + 1) % self.nframe
+        return 1 if self.frame_count == 0 else 0
 
 
 def accumulate(iring, nframe, dtype=None, *args, **kwargs):

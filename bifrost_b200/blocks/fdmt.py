@@ -26,47 +26,50 @@ class FdmtBlock(TransformBlock):
     def define_valid_input_spaces(self):
         return ('cuda',)
 
-    def on_sequence(self, iseq):
-        ihdr = iseq.header
-        itensor = ihdr['_tensor']
-        labels = itensor['labels']
-        if labels[-1] != 'time' or labels[-2] != 'freq':
-            raise KeyError("Expected axes [..., 'freq', 'time'], got %s" % labels)
-        nchan = itensor['shape'][-2]
-        f0_, df_ = itensor['scales'][-2]
-        t0_, dt_ = itensor['scales'][-1]
-        f0 = convert_units(f0_, itensor['units'][-2], 'MHz')
-        df = convert_units(df_, itensor['units'][-2], 'MHz')
-        dt = convert_units(dt_, itensor['units'][-1], 's')
-        if self.max_mode == 'diagonal':
-            self.max_mode = 'delay'
-            self.max_value = int(math.ceil(nchan * self.max_value))
-        fac = f0 ** -2 - (f0 + nchan * df) ** -2
-        if self.max_mode == 'dm':
-            max_dm = self.max_value
-            self.max_delay = int(math.ceil(abs(self.kdm / dt * max_dm * fac)))
+    def _dispersion_span(self, nchan, first_MHz, chan_MHz, tsamp_s):
+        """(max_delay in samples, max_dm) from whichever limit the user gave
+        (blocks/fdmt.py:70-93 of the reference: the DM that sweeps max_delay
+        samples between the band edges under the nu^-2 law)."""
+        sweep = first_MHz ** -2 - (first_MHz + nchan * chan_MHz) ** -2
+        limit, mode = self.max_value, self.max_mode
+        if mode == 'diagonal':                       # a slope of `limit` samples per channel
+            self.max_mode, mode = 'delay', 'delay'
+            self.max_value = limit = int(math.ceil(nchan * limit))
+        if mode == 'dm':
+            ndelay = int(math.ceil(abs(self.kdm / tsamp_s * limit * sweep)))
+            dm = limit
         else:
-            self.max_delay = int(self.max_value)
-            max_dm = self.max_delay * dt / (self.kdm * abs(fac))
-        if self.negative_delays:
-            max_dm = -max_dm
+            ndelay = int(limit)
+            dm = ndelay * tsamp_s / (self.kdm * abs(sweep))
+        return ndelay, (-dm if self.negative_delays else dm)
+
+    def on_sequence(self, iseq):
+        hdr_in = iseq.header
+        t_in = hdr_in['_tensor']
+        if list(t_in['labels'][-2:]) != ['freq', 'time']:
+            raise KeyError("Expected axes [..., 'freq', 'time'], got %s" % t_in['labels'])
+        nchan = t_in['shape'][-2]
+        funit, tunit = t_in['units'][-2], t_in['units'][-1]
+        first_raw, chan_raw = t_in['scales'][-2]
+        first_MHz = convert_units(first_raw, funit, 'MHz')
+        chan_MHz = convert_units(chan_raw, funit, 'MHz')
+        tsamp_s = convert_units(t_in['scales'][-1][1], tunit, 's')
+        self.max_delay, max_dm = self._dispersion_span(nchan, first_MHz, chan_MHz, tsamp_s)
         self.dm_step = max_dm / self.max_delay
-        self.fdmt.init(nchan, self.max_delay, f0, df, self.exponent, 'cuda')
-        ohdr = deepcopy(ihdr)
-        refdm = convert_units(ihdr['refdm'], ihdr['refdm_units'], self.dm_units) if 'refdm' in ihdr else 0.
-        ot = ohdr['_tensor']
-        ot['dtype'] = 'f32'
-        ot['shape'][-2] = self.max_delay
-        ot['labels'][-2] = 'dispersion'
-        ot['scales'][-2] = (refdm, self.dm_step)
-        ot['units'][-2] = self.dm_units
-        ohdr['max_dm'] = max_dm
-        ohdr['max_dm_units'] = self.dm_units
-        ohdr['cfreq'] = f0_ + 0.5 * (nchan - 1) * df_
-        ohdr['cfreq_units'] = itensor['units'][-2]
-        ohdr['bw'] = nchan * df_
-        ohdr['bw_units'] = itensor['units'][-2]
-        return ohdr
+        self.fdmt.init(nchan, self.max_delay, first_MHz, chan_MHz, self.exponent, 'cuda')
+        dm0 = 0.
+        if 'refdm' in hdr_in:
+            dm0 = convert_units(hdr_in['refdm'], hdr_in['refdm_units'], self.dm_units)
+        hdr_out = deepcopy(hdr_in)
+        t_out = hdr_out['_tensor']
+        t_out['dtype'] = 'f32'
+        for field, value in (('shape', self.max_delay), ('labels', 'dispersion'),
+                             ('scales', (dm0, self.dm_step)), ('units', self.dm_units)):
+            t_out[field][-2] = value                 # the freq axis becomes the trial axis
+        hdr_out.update(max_dm=max_dm, max_dm_units=self.dm_units,
+                       cfreq=first_raw + 0.5 * (nchan - 1) * chan_raw, cfreq_units=funit,
+                       bw=nchan * chan_raw, bw_units=funit)
+        return hdr_out
 
     def define_input_overlap_nframe(self, iseq):
         return self.max_delay

@@ -27,39 +27,31 @@ class FftBlock(TransformBlock):
         return ('cuda',)
 
     def on_sequence(self, iseq):
-        ihdr = iseq.header
-        itensor = ihdr['_tensor']
-        itype = DataType(itensor['dtype']).as_floating_point()
-        self.axes = [itensor['labels'].index(ax) if isinstance(ax, str) else ax
-                     for ax in self.specified_axes]
-        axes = self.axes
-        shape = [itensor['shape'][ax] for ax in axes]
-        otype = itype.as_real() if self.real_output else itype.as_complex()
-        ohdr = deepcopy(ihdr)
-        otensor = ohdr['_tensor']
-        otensor['dtype'] = str(otype)
-        if itype.is_real and otype.is_complex:
-            self.mode = 'r2c'
-        elif itype.is_complex and otype.is_real:
-            self.mode = 'c2r'
-        else:
-            self.mode = 'c2c'
-        if itensor['shape'].index(-1) in axes:
+        hdr_out = deepcopy(iseq.header)
+        t = hdr_out['_tensor']
+        labels = t.get('labels')
+        self.axes = axes = [labels.index(a) if isinstance(a, str) else a for a in self.specified_axes]
+        if t['shape'].index(-1) in axes:
             raise KeyError("Cannot transform frame axis; reshape the data stream first")
+        t_in = DataType(t['dtype']).as_floating_point()
+        t_res = t_in.as_real() if self.real_output else t_in.as_complex()
+        self.mode = {(True, False): 'r2c', (False, True): 'c2r'}.get((t_in.is_real, t_res.is_real), 'c2c')
+        t['dtype'] = str(t_res)
+        lengths = [t['shape'][a] for a in axes]             # transform lengths (full size for c2r)
+        last = axes[-1]
         if self.mode == 'r2c':
-            otensor['shape'][axes[-1]] = otensor['shape'][axes[-1]] // 2 + 1
+            t['shape'][last] = t['shape'][last] // 2 + 1    # Hermitian half
         elif self.mode == 'c2r':
-            otensor['shape'][axes[-1]] = (otensor['shape'][axes[-1]] - 1) * 2
-            shape[-1] = (shape[-1] - 1) * 2
-        for i, (ax, length) in enumerate(zip(axes, shape)):
-            if 'units' in otensor:
-                otensor['units'][ax] = transform_units(otensor['units'][ax], -1)
-            if 'scales' in otensor:
-                scale = otensor['scales'][ax][1]
-                otensor['scales'][ax] = [0, 1. / (scale * length)]
-            if 'labels' in otensor and i < len(self.axis_labels) and self.axis_labels[i] is not None:
-                otensor['labels'][ax] = self.axis_labels[i]
-        return ohdr
+            lengths[-1] = t['shape'][last] = (t['shape'][last] - 1) * 2
+        for k, (a, n) in enumerate(zip(axes, lengths)):
+            if 'units' in t:
+                t['units'][a] = transform_units(t['units'][a], -1)
+            if 'scales' in t:
+                t['scales'][a] = [0, 1. / (t['scales'][a][1] * n)]   # bin width = 1 / (step * length)
+            new_label = self.axis_labels[k] if k < len(self.axis_labels) else None
+            if labels is not None and new_label is not None:
+                t['labels'][a] = new_label
+        return hdr_out
 
     def on_data(self, ispan, ospan):
         idata, odata = ispan.data, ospan.data

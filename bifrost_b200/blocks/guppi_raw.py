@@ -9,10 +9,6 @@ def _mjd2unix(mjd):
     return (mjd - 40587) * 86400
 
 
-def _get_with_default(obj, key, default=None):
-    return obj[key] if key in obj else default
-
-
 class GuppiRawSourceBlock(SourceBlock):
     def __init__(self, sourcenames, gulp_nframe=1, *args, **kwargs):
         super(GuppiRawSourceBlock, self).__init__(sourcenames, gulp_nframe=gulp_nframe, *args, **kwargs)
@@ -20,45 +16,46 @@ class GuppiRawSourceBlock(SourceBlock):
     def create_reader(self, sourcename):
         return open(sourcename, 'rb')
 
+    # GUPPI card -> (output header key, conversion); cards that are absent give None
+    _PASSTHROUGH = (('AZ', 'az_start', None), ('ZA', 'za_start', None),
+                    ('RA', 'raj', lambda deg: deg * (24. / 360.)),        # degrees -> hours
+                    ('DEC', 'dej', None), ('SRC_NAME', 'source_name', None),
+                    ('CHAN_DM', 'refdm', None), ('TELESCOP', 'telescope', None),
+                    ('BACKEND', 'machine', None))
+
+    @staticmethod
+    def _time_axis(card):
+        """Unix time of the block's first sample and the sample interval (s)."""
+        chan_bw_MHz = card['OBSBW'] / card['OBSNCHAN']
+        tsamp = 1. / chan_bw_MHz / 1e6                   # negative for high -> low channel order
+        bytes_per_sample = card['BLOCSIZE'] / card['NTIME']
+        elapsed = card['PKTIDX'] * card['PKTSIZE'] / (bytes_per_sample / tsamp)
+        mjd = card['STT_IMJD'] + (card['STT_SMJD'] + elapsed) / 86400.
+        return _mjd2unix(mjd), tsamp
+
     def on_sequence(self, reader, sourcename):
-        ihdr = guppi_raw.read_header(reader)
-        nbit = ihdr['NBITS']
-        assert nbit in (4, 8, 16, 32, 64)
-        nchan = ihdr['OBSNCHAN']
-        bw_MHz = ihdr['OBSBW']
-        cfreq_MHz = ihdr['OBSFREQ']
-        df_MHz = bw_MHz / nchan
-        f0_MHz = cfreq_MHz - 0.5 * (nchan - 1) * df_MHz
-        dt_s = 1. / df_MHz / 1e6                 # negative when OBSBW is (high -> low channel order)
-        byte_offset = ihdr['PKTIDX'] * ihdr['PKTSIZE']
-        frame_nbyte = ihdr['BLOCSIZE'] / ihdr['NTIME']
-        offset_secs = byte_offset / (frame_nbyte / dt_s)
-        tstart_mjd = ihdr['STT_IMJD'] + (ihdr['STT_SMJD'] + offset_secs) / 86400.
-        tstart_unix = _mjd2unix(tstart_mjd)
-        self.blocsize = ihdr['BLOCSIZE']
-        ohdr = {
-            '_tensor': {
-                'dtype': 'ci' + str(nbit),
-                'shape': [-1, nchan, ihdr['NTIME'], ihdr['NPOL']],
-                'labels': ['time', 'freq', 'fine_time', 'pol'],
-                'scales': [(tstart_unix, abs(dt_s) * ihdr['NTIME']), (f0_MHz, df_MHz), (0, dt_s), None],
-                'units': ['s', 'MHz', 's', None],
-                'gulp_nframe': 1,
-            },
-            'az_start': _get_with_default(ihdr, 'AZ'),
-            'za_start': _get_with_default(ihdr, 'ZA'),
-            'raj': _get_with_default(ihdr, 'RA', 0.) * (24. / 360.),
-            'dej': _get_with_default(ihdr, 'DEC'),
-            'source_name': _get_with_default(ihdr, 'SRC_NAME'),
-            'refdm': _get_with_default(ihdr, 'CHAN_DM'),
-            'refdm_units': 'pc cm^-3',
-            'telescope': _get_with_default(ihdr, 'TELESCOP'),
-            'machine': _get_with_default(ihdr, 'BACKEND'),
-            'rawdatafile': sourcename,
-            'coord_frame': 'topocentric',
-        }
-        ohdr['time_tag'] = int(round(tstart_unix * 2 ** 32))
-        ohdr['name'] = sourcename
+        card = guppi_raw.read_header(reader)
+        nbit, nchan, ntime = card['NBITS'], card['OBSNCHAN'], card['NTIME']
+        if nbit not in (4, 8, 16, 32, 64):
+            raise ValueError("Unsupported NBITS: %r" % nbit)
+        chan_bw_MHz = card['OBSBW'] / nchan
+        first_chan_MHz = card['OBSFREQ'] - 0.5 * (nchan - 1) * chan_bw_MHz
+        t0, tsamp = self._time_axis(card)
+        self.blocsize = card['BLOCSIZE']
+        tensor = dict(dtype='ci%d' % nbit,
+                      shape=[-1, nchan, ntime, card['NPOL']],
+                      labels=['time', 'freq', 'fine_time', 'pol'],       # 'time' counts blocks
+                      scales=[(t0, abs(tsamp) * ntime), (first_chan_MHz, chan_bw_MHz), (0, tsamp), None],
+                      units=['s', 'MHz', 's', None],
+                      gulp_nframe=1)
+        ohdr = {'_tensor': tensor, 'refdm_units': 'pc cm^-3', 'rawdatafile': sourcename,
+                'coord_frame': 'topocentric', 'name': sourcename,
+                'time_tag': int(round(t0 * 2 ** 32))}                   # 32.32 fixed point
+        for key, okey, conv in self._PASSTHROUGH:
+            val = card.get(key)
+            if key == 'RA' and val is None:
+                val = 0.
+            ohdr[okey] = conv(val) if (conv is not None and val is not None) else val
         self.already_read_header = True
         return [ohdr]
 

@@ -21,10 +21,6 @@ def _unix2mjd(unix):
     return unix / 86400. + 40587
 
 
-def _get_with_default(obj, key, default=None):
-    return obj[key] if key in obj else default
-
-
 def _copy_item_if_exists(dst, src, key, newkey=None):
     if key in src:
         dst[key if newkey is None else newkey] = src[key]
@@ -38,43 +34,32 @@ class SigprocSourceBlock(SourceBlock):
     def create_reader(self, sourcename):
         return sigproc.SigprocFile(sourcename)
 
+    # sigproc keyword -> (output header key, default)
+    _PASSTHROUGH = (('source_name', 'source_name', None), ('rawdatafile', 'rawdatafile', None),
+                    ('az_start', 'az_start', None), ('za_start', 'za_start', None),
+                    ('src_raj', 'raj', None), ('src_dej', 'dej', None), ('refdm', 'refdm', 0.),
+                    ('ibeam', 'ibeam', None), ('nbeams', 'nbeams', None))
+
     def on_sequence(self, ireader, sourcename):
-        ihdr = ireader.header
-        assert ihdr['data_type'] in (1, 2, 6)       # filterbank, time series, dedispersed subbands
-        coord_frame = 'topocentric'
-        for frame in ('pulsarcentric', 'barycentric'):
-            if bool(ihdr.get(frame, 0)):
-                coord_frame = frame
-                break
-        tstart_unix = _mjd2unix(ihdr['tstart'])
-        nbit = ihdr['nbits']
+        sp = ireader.header
+        if sp['data_type'] not in (1, 2, 6):        # filterbank, time series, dedispersed subbands
+            raise ValueError("Unsupported sigproc data_type %r" % sp['data_type'])
+        frames = [f for f in ('pulsarcentric', 'barycentric') if sp.get(f, 0)]
+        t0 = _mjd2unix(sp['tstart'])
+        nbit = sp['nbits']
         # 32-bit sigproc samples are floats (the reference labels them u32/i32)
-        dtype = 'f32' if nbit == 32 else ('i' if ireader.signed else 'u') + str(nbit)
-        ohdr = {
-            '_tensor': {
-                'dtype': dtype,
-                'shape': [-1, ihdr.get('nifs', 1), ihdr['nchans']],
-                'labels': ['time', 'pol', 'freq'],
-                'scales': [(tstart_unix, ihdr['tsamp']), None, (ihdr.get('fch1', 0.), ihdr.get('foff', 0.))],
-                'units': ['s', None, 'MHz'],
-            },
-            'frame_rate': 1. / ihdr['tsamp'],
-            'source_name': _get_with_default(ihdr, 'source_name'),
-            'rawdatafile': _get_with_default(ihdr, 'rawdatafile'),
-            'az_start': _get_with_default(ihdr, 'az_start'),
-            'za_start': _get_with_default(ihdr, 'za_start'),
-            'raj': _get_with_default(ihdr, 'src_raj'),
-            'dej': _get_with_default(ihdr, 'src_dej'),
-            'refdm': _get_with_default(ihdr, 'refdm', 0.),
-            'refdm_units': 'pc cm^-3',
-            'telescope': sigproc.id2telescope(_get_with_default(ihdr, 'telescope_id')),
-            'machine': sigproc.id2machine(_get_with_default(ihdr, 'machine_id')),
-            'ibeam': _get_with_default(ihdr, 'ibeam'),
-            'nbeams': _get_with_default(ihdr, 'nbeams'),
-            'coord_frame': coord_frame,
-        }
-        ohdr['time_tag'] = int(round(tstart_unix * 2 ** 32))
-        ohdr['name'] = sourcename
+        sample_type = 'f32' if nbit == 32 else '%s%d' % ('i' if ireader.signed else 'u', nbit)
+        tensor = dict(dtype=sample_type, shape=[-1, sp.get('nifs', 1), sp['nchans']],
+                      labels=['time', 'pol', 'freq'],
+                      scales=[(t0, sp['tsamp']), None, (sp.get('fch1', 0.), sp.get('foff', 0.))],
+                      units=['s', None, 'MHz'])
+        ohdr = {'_tensor': tensor, 'frame_rate': 1. / sp['tsamp'], 'refdm_units': 'pc cm^-3',
+                'telescope': sigproc.id2telescope(sp.get('telescope_id')),
+                'machine': sigproc.id2machine(sp.get('machine_id')),
+                'coord_frame': frames[0] if frames else 'topocentric',
+                'time_tag': int(round(t0 * 2 ** 32)), 'name': sourcename}
+        for key, okey, default in self._PASSTHROUGH:
+            ohdr[okey] = sp.get(key, default)
         return [ohdr]
 
     def on_data(self, reader, ospans):
