@@ -107,3 +107,21 @@ def test_sharded_final_pass_equals_full_band_transform():
         got = np.array([cells[t] for t in ts], F32)
         np.testing.assert_array_equal(got.view(np.uint32), states[last][row][ts].view(np.uint32))
     assert len(written) == plan.nrow[last]
+
+
+def test_two_rank_gloo_exchange():
+    """The same decomposition as two gloo processes: local passes on the own
+    sub-band, all-gather of the split-step rows (the future NVLink peer reads),
+    each rank's share of the final programs, assembled bank == oracle."""
+    import socket
+    import subprocess
+    sock = socket.socket()
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fdmt_shard_worker.py')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), worker],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'SHARDED_FDMT_OK' in out.stdout
