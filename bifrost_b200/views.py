@@ -35,6 +35,19 @@ def reinterpret_axis(block, axis, label, scale=None, units=None):
     return block_view(block, transform)
 
 
+def reverse_scale(block, axis):
+    """Flip the sign of the step of `axis` (label or index).  The reference
+    (views/basic_views.py:67-75) only acts when the axis is given by label; an
+    index works here too."""
+    def transform(hdr):
+        t = hdr['_tensor']
+        ax = _axis(t, axis)
+        start, step = t['scales'][ax]
+        t['scales'][ax] = [start, -step]
+        return hdr
+    return block_view(block, transform)
+
+
 def add_axis(block, axis, label=None, scale=None, units=None):
     def transform(hdr):
         t = hdr['_tensor']

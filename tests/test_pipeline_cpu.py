@@ -139,6 +139,34 @@ def test_views_rewrite_headers_without_moving_data():
     np.testing.assert_array_equal(np.concatenate(out2.chunks, 0), data.reshape(6, 4, 4, 2))
 
 
+def test_remaining_views_add_delete_reverse_astype_reinterpret():
+    """views/basic_views.py:51-145 of the reference: header-only transforms."""
+    data = np.arange(4 * 1 * 6, dtype=np.float32).reshape(4, 1, 6)
+    hdr = header([-1, 1, 6], labels=['time', 'pol', 'freq'])
+    hdr['_tensor']['scales'] = [[0, 1.0], [0, 1], [1500.0, -0.5]]
+    hdr['_tensor']['units'] = ['s', None, 'MHz']
+    out = Collect()
+    with Pipeline() as p:
+        src = array_source(data, hdr, gulp_nframe=2)
+        v = bf.views.delete_axis(src, 'pol')
+        v = bf.views.reverse_scale(v, 'freq')
+        v = bf.views.add_axis(v, 1, label='beam', scale=[0, 1], units=None)
+        v = bf.views.reinterpret_axis(v, 'freq', label='chan', scale=[7.0, 2.0], units='kHz')
+        callback_sink(v, out.seq, out.data)
+        p.run()
+    t = out.headers[0]['_tensor']
+    assert t['shape'] == [-1, 1, 6] and t['labels'] == ['time', 'beam', 'chan']
+    assert t['scales'][2] == [7.0, 2.0] and t['units'][2] == 'kHz'
+    np.testing.assert_array_equal(np.concatenate(out.chunks, 0), data)
+    out2 = Collect()
+    with Pipeline() as p:
+        src = array_source(data, hdr, gulp_nframe=4)
+        v = bf.views.reverse_scale(src, 2)
+        callback_sink(v, out2.seq, out2.data)
+        p.run()
+    assert out2.headers[0]['_tensor']['scales'][2] == [1500.0, 0.5]
+
+
 def test_block_scope_and_space_validation():
     data = np.zeros((4, 2), np.float32)
     with Pipeline() as p:
