@@ -224,3 +224,39 @@ def test_item_tables_respect_the_alignment_rules():
             assert (m[:, 0] % 4 == 0).all()
             assert (m[:, 0] + 4 * (m[:, 3] & 0xFFFF) <= tp['smem']).all()
         assert (m[:, 2] + 4 * (m[:, 3] & 0xFFFF) + 4 <= tp['smem'] + 16).all()
+
+
+def test_random_plans_and_passes_reproduce_the_oracle():
+    """Seeded fuzz over plan geometry (odd channel counts, reversed bands, low
+    frequencies with long step-0 windows), pass ranges, delay-block sizes, warp
+    counts, raw and float passes; the first, last and a random tile of each."""
+    rng = np.random.default_rng(20240922)
+    ncase = 0
+    while ncase < 120:
+        nchan = int(rng.integers(2, 160))
+        md = int(rng.integers(1, 120))
+        f0 = float(rng.uniform(30, 3000))
+        bw = float(rng.uniform(5, f0 * 0.6)) * (1 if rng.random() < 0.8 else -1)
+        df = bw / nchan
+        ntime = int(rng.integers(md + 5, md + 700))
+        n = ctypes.c_int(0)
+        if _bf.bfFdmtPlanQuery(nchan, md, f0, df, -2.0, -1, ctypes.byref(n), None) != 0 or n.value < 2:
+            continue
+        nstep = n.value
+        x = rng.integers(-128, 128, size=(nchan, ntime), dtype=np.int8)
+        plan, states = oracle_states(x, md, f0, df)
+        s0 = int(rng.integers(1, nstep))
+        s1 = int(rng.integers(s0, nstep))
+        raw = s0 == 1 and rng.random() < 0.7
+        if s0 == 1 and not raw:
+            s0 = 2
+            if s0 > s1:
+                continue
+        tp = query(nchan, md, f0, df, s0, s1, int(rng.choice([4, 8, 16, 32])), int(rng.choice([1, 2, 4, 8])), raw)
+        if tp is None:
+            continue
+        ntile = -(-ntime // tp['T'])
+        tiles = sorted({0, ntile - 1, int(rng.integers(0, ntile))})
+        written = run_pass(tp, None if raw else states[s0 - 1], x if raw else None, ntime, tiles)
+        assert check(tp, states[s1], written, ntime, tiles) == plan.nrow[s1]
+        ncase += 1
