@@ -428,7 +428,8 @@ def main():
     peaks, peak_kind = measured_peaks()
     alg_bytes = ntime * (nchan * 1 + md * 4)
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-    roofline = dict(bound='hbm', kernel='bfFdmtExecute (all launches of one call)',
+    roofline = dict(bound='hbm', kernel='bfFdmtExecute = 3 x fdmt_tile_kernel (raw head 1..5, pass 6..9, final pass 10..12); '
+                           'bytes and time are those of the whole call',
                     achieved=achieved, peak=peaks['hbm_gbs'], peak_source=peak_kind,
                     unit='GB/s', frac=achieved / peaks['hbm_gbs'],
                     algorithmic_bytes=alg_bytes, traffic=None)
