@@ -459,6 +459,7 @@ fdmt_tail_kernel(const float* __restrict__ prev, long pstride, long pbatchstride
 } // namespace bfb
 
 #include "fdmt_tiles.cuh"
+#include "fdmt_chain.cuh"
 
 using namespace bfb;
 
@@ -497,6 +498,8 @@ struct BFfdmt_impl {
 	TilePass head_pass;                  // steps 1..K straight from 1-byte input
 	bool   head_pass_ok = false;
 	int    cfg_tile_d = 24, cfg_tile_smem_kb = 110, cfg_tile_threads = 256;
+	// integer chain schedule for 1-byte inputs (fdmt_chain.cuh); empty = n/a
+	std::vector<ChainPass> chain;
 	// exec workspace
 	void*  own_exec_storage = nullptr;
 	size_t own_exec_size = 0;
@@ -522,6 +525,12 @@ struct BFfdmt_impl {
 		if( head_pass.d_aux )   cudaFree(head_pass.d_aux);
 		head_pass = TilePass();
 		head_pass_ok = false;
+		for( ChainPass& cp : chain ) {
+			if( cp.d_ops ) cudaFree(cp.d_ops);
+			if( cp.d_src ) cudaFree(cp.d_src);
+			if( cp.d_hdr ) cudaFree(cp.d_hdr);
+		}
+		chain.clear();
 	}
 };
 
@@ -664,6 +673,180 @@ static void build_tail_passes(BFfdmt_impl* plan) {
 	}
 }
 
+
+// ---------------------------------------------------------------------------
+// Integer chain schedule (fdmt_chain.cuh): pass list, geometry, launch
+// ---------------------------------------------------------------------------
+static std::vector<int> env_int_list(const char* name) {
+	std::vector<int> v;
+	if( const char* e = getenv(name) ) {
+		for( const char* q=e; *q; ) {
+			v.push_back(atoi(q));
+			while( *q && *q != ',' ) ++q;
+			if( *q == ',' ) ++q;
+		}
+	}
+	return v;
+}
+
+// Cuts steps 1..S into passes (16-bit passes up to the first step whose
+// sub-bands overflow 16 bits, fp32 passes above) and builds their tables.
+// Returns false when the schedule does not apply to this plan.
+static bool build_chain_schedule(FdmtPlan const& P, std::vector<ChainPass>* passes_) {
+	std::vector<ChainPass>& passes = *passes_;
+	passes.clear();
+	if( env_int("BFB_FDMT_CHAIN", 1) == 0 ) return false;
+	std::vector<std::vector<char> > used;
+	fdmt_used_rows(P, &used);
+	if( !fdmt_integer_safe(P, used) ) return false;
+	const int S = P.nstep() - 1;
+	if( S < 1 ) return false;
+	const int S16 = fdmt_last_u16_step(P);
+	const int U = std::min(S, S16 + 1);            // last step of the 16-bit part
+	std::vector<int> ends = env_int_list("BFB_FDMT_CHAIN_SPLIT");
+	if( ends.empty() ) {
+		int npu = div_up<int>(U, CH_MAXLEV);
+		for( int k=1; k<=npu; ++k ) ends.push_back(std::min(U, div_up<int>(U * k, npu)));
+		// (uneven splits put the longer pass first: the lowest steps are the cheapest)
+		int nf = S - U, npf = div_up<int>(nf, 3);
+		for( int k=1; k<=npf; ++k ) ends.push_back(U + div_up<int>(nf * k, npf));
+	} else {
+		std::vector<int> e2;
+		for( int v : ends ) if( v >= 1 && v < S && (e2.empty() || v > e2.back()) ) e2.push_back(v);
+		// a pass may not straddle the 16-bit limit except with its top level
+		if( std::find(e2.begin(), e2.end(), U) == e2.end() && U < S ) e2.push_back(U);
+		std::sort(e2.begin(), e2.end());
+		e2.push_back(S);
+		ends = e2;
+	}
+	std::vector<int> Ds   = env_int_list("BFB_FDMT_CHAIN_D");
+	std::vector<int> JRs  = env_int_list("BFB_FDMT_CHAIN_JR");
+	std::vector<int> NWs  = env_int_list("BFB_FDMT_CHAIN_WARPS");
+	std::vector<int> SMs  = env_int_list("BFB_FDMT_CHAIN_SMEM_KB");
+	std::vector<int> TCs  = env_int_list("BFB_FDMT_CHAIN_TCAP");
+	// step-0 row -> input channel
+	std::vector<int> src_index(P.nrow(0), -1);
+	for( size_t c=0; c<P.bands[0].size(); ++c )
+		src_index[P.bands[0][c].row0] = P.reverse_band ? P.nchan - 1 - (int)c : (int)c;
+	int s0 = 1;
+	for( size_t k=0; k<ends.size(); ++k ) {
+		const int s1 = ends[k];
+		if( s1 < s0 ) continue;
+		const bool fin = (s1 == S);
+		const int esize = (s0 <= U) ? 2 : 4;
+		if( esize == 2 && s1 > U ) return false;
+		if( esize == 2 && s1 > S16 && !(s1 == U) ) return false;
+		const int src_kind = (s0 == 1) ? CH_SRC_BYTES : CH_SRC_SAME;
+		int dst_kind = fin ? CH_DST_FINAL : CH_DST_SAME;
+		if( !fin && esize == 2 && s1 == U ) dst_kind = CH_DST_CVT;   // the next pass is fp32
+		std::vector<int> out_index(P.nrow(s1), -1);
+		int nout = 0;
+		for( int r=0; r<P.nrow(s1); ++r ) if( used[s1][r] ) out_index[r] = fin ? r : nout++;
+		ChainCfg cfg;
+		const size_t pi = passes.size();
+		cfg.D       = pi < Ds.size()  ? Ds[pi]  : (s0 == 1 ? 64 : 24);
+		cfg.JR      = pi < JRs.size() ? JRs[pi] : 4;
+		cfg.nwarp   = std::max(1, std::min(8, pi < NWs.size() ? NWs[pi] : 8));
+		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : 110);
+		cfg.tcap    = pi < TCs.size() ? std::max(64, TCs[pi]) : (1 << 20);
+		ChainPass cp;
+		bool ok = false;
+		for( int D=cfg.D; D>=2 && !ok; D=(D*2)/3 ) {
+			ChainCfg c2 = cfg; c2.D = D;
+			ok = build_chain_pass(P, used, s0, s1, esize, src_kind, dst_kind, src_index, out_index, c2, &cp);
+		}
+		if( !ok ) { passes.clear(); return false; }
+		cp.nrow_out = fin ? P.nrow(s1) : nout;
+		passes.push_back(cp);
+		src_index = out_index;
+		s0 = s1 + 1;
+	}
+	if( passes.empty() || passes.back().s1 != S ) { passes.clear(); return false; }
+	return true;
+}
+
+static bool upload_chain(std::vector<ChainPass>* passes) {
+	for( ChainPass& cp : *passes ) {
+		struct { std::vector<int4>* h; int4** d; } t[3] = {{&cp.ops, &cp.d_ops}, {&cp.src, &cp.d_src}, {&cp.hdr, &cp.d_hdr}};
+		for( int i=0; i<3; ++i ) {
+			size_t bytes = t[i].h->size() * sizeof(int4);
+			if( cudaMalloc((void**)t[i].d, bytes) != cudaSuccess ) return false;
+			if( cudaMemcpy(*t[i].d, t[i].h->data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess ) return false;
+		}
+	}
+	return true;
+}
+
+struct ChainGeom { long tb, nt, te, stride; size_t offset; };
+
+// Time range of every pass for a gulp of `ntime` samples: the last pass covers
+// [0, ntime); pass k covers everything pass k+1 reads, starting before t = 0
+// by that pass's backward reach (samples before t = 0 are zeros, so no pass
+// needs an edge path).
+static size_t chain_geometry(std::vector<ChainPass> const& passes, long ntime, long nbatch,
+                             std::vector<ChainGeom>* geom_) {
+	std::vector<ChainGeom>& g = *geom_;
+	const int n = (int)passes.size();
+	g.assign(n, ChainGeom());
+	g[n-1].tb = 0;
+	g[n-1].nt = div_up<long>(ntime, passes[n-1].T);
+	g[n-1].te = g[n-1].nt * passes[n-1].T;
+	for( int k=n-2; k>=0; --k ) {
+		g[k].tb = -round_up<long>(passes[k+1].lookback - g[k+1].tb, 8);
+		g[k].nt = div_up<long>(g[k+1].te - g[k].tb, passes[k].T);
+		g[k].te = g[k].tb + g[k].nt * passes[k].T;
+	}
+	size_t off = 0;
+	for( int k=0; k<n-1; ++k ) {
+		g[k].stride = round_up<long>(g[k].te - g[k].tb, 64);
+		g[k].offset = off;
+		size_t esz = (passes[k].dst_kind == CH_DST_CVT) ? 4 : passes[k].esize;
+		off += round_up<size_t>((size_t)nbatch * passes[k].nrow_out * g[k].stride * esz, 512);
+	}
+	return std::max<size_t>(off, 512);
+}
+
+template<int ESZ, int SRCK, int DSTK, int NLMAX>
+static cudaError_t launch_chain_kernel(ChainParams const& q, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+	static size_t attr_smem = 0;
+	if( smem > attr_smem ) {
+		cudaError_t e = cudaFuncSetAttribute(fdmt_chain_kernel<ESZ, SRCK, DSTK, NLMAX>,
+		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if( e != cudaSuccess ) return e;
+		attr_smem = smem;
+	}
+	fdmt_chain_kernel<ESZ, SRCK, DSTK, NLMAX><<<grid, threads, smem, st>>>(q);
+	return cudaGetLastError();
+}
+
+static BFstatus launch_chain_pass(ChainPass const& cp, ChainParams const& q, long nbatch, cudaStream_t st) {
+	dim3 grid((unsigned)std::min<long>(q.ntile, 1L << 20), (unsigned)cp.nprog, (unsigned)nbatch);
+	const int threads = cp.nwarp * 32;
+	const size_t smem = cp.smem_bytes();
+	cudaError_t e = cudaErrorInvalidValue;
+#define BFB_CH_LAUNCH(E_, S_, D_) \
+	e = (cp.nlev <= 3) ? launch_chain_kernel<E_, S_, D_, 3>(q, grid, threads, smem, st) \
+	                   : launch_chain_kernel<E_, S_, D_, 5>(q, grid, threads, smem, st)
+	if( cp.esize == 2 ) {
+		if( cp.src_kind == CH_SRC_BYTES ) {
+			if(      cp.dst_kind == CH_DST_SAME ) BFB_CH_LAUNCH(2, CH_SRC_BYTES, CH_DST_SAME);
+			else if( cp.dst_kind == CH_DST_CVT  ) BFB_CH_LAUNCH(2, CH_SRC_BYTES, CH_DST_CVT);
+			else                                  BFB_CH_LAUNCH(2, CH_SRC_BYTES, CH_DST_FINAL);
+		} else {
+			if(      cp.dst_kind == CH_DST_SAME ) BFB_CH_LAUNCH(2, CH_SRC_SAME, CH_DST_SAME);
+			else if( cp.dst_kind == CH_DST_CVT  ) BFB_CH_LAUNCH(2, CH_SRC_SAME, CH_DST_CVT);
+			else                                  BFB_CH_LAUNCH(2, CH_SRC_SAME, CH_DST_FINAL);
+		}
+	} else {
+		if( cp.dst_kind == CH_DST_SAME ) BFB_CH_LAUNCH(4, CH_SRC_SAME, CH_DST_SAME);
+		else                             BFB_CH_LAUNCH(4, CH_SRC_SAME, CH_DST_FINAL);
+	}
+#undef BFB_CH_LAUNCH
+	BFB_CUDA(e, BF_STATUS_INTERNAL_ERROR);
+	count_launch();
+	return BF_STATUS_SUCCESS;
+}
+
 extern "C" {
 
 BFstatus bfFdmtCreate(BFfdmt* plan_ptr) {
@@ -766,6 +949,20 @@ BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
 	                         cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
 	BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
 	BFB_TRY(build_tail_passes(plan));
+	BFB_TRY({
+		std::vector<ChainPass> cps;
+		if( build_chain_schedule(P, &cps) ) {
+			plan->chain.swap(cps);
+			if( !upload_chain(&plan->chain) ) {
+				for( ChainPass& cp : plan->chain ) {
+					if( cp.d_ops ) cudaFree(cp.d_ops);
+					if( cp.d_src ) cudaFree(cp.d_src);
+					if( cp.d_hdr ) cudaFree(cp.d_hdr);
+				}
+				plan->chain.clear();
+			}
+		}
+	});
 	return BF_STATUS_SUCCESS;
 }
 
@@ -786,6 +983,33 @@ BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	header[7] = (int)tp.items.size();
 	if( items ) memcpy(items, tp.items.data(), tp.items.size() * sizeof(int4));
 	if( aux && !tp.aux.empty() ) memcpy(aux, tp.aux.data(), tp.aux.size() * sizeof(int4));
+	return BF_STATUS_SUCCESS;
+}
+
+// Test hook: the tables of pass `pass` of the integer chain schedule
+// (pass < 0: only header[0] = number of passes, 0 when the schedule does not
+// apply).  tests/test_fdmt_chain_cpu.py interprets them with numpy.
+BFstatus bfFdmtChainQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+                          double exponent, int pass, int* header,
+                          int* ops, int* src, int* hdr) {
+	BFB_ASSERT(header, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(nchan > 1 && max_delay >= 1, BF_STATUS_INVALID_ARGUMENT);
+	FdmtPlan P;
+	bool ok = false;
+	BFB_TRY(ok = P.build((int)nchan, (int)max_delay, f0, df, exponent));
+	BFB_ASSERT(ok, BF_STATUS_INTERNAL_ERROR);
+	std::vector<ChainPass> cps;
+	BFB_TRY(ok = build_chain_schedule(P, &cps));
+	if( pass < 0 ) { header[0] = ok ? (int)cps.size() : 0; return BF_STATUS_SUCCESS; }
+	BFB_ASSERT(ok && pass < (int)cps.size(), BF_STATUS_INVALID_ARGUMENT);
+	ChainPass const& cp = cps[pass];
+	int h[16] = { cp.s0, cp.s1, cp.nlev, cp.esize, cp.src_kind, cp.dst_kind, cp.T, cp.nprog,
+	              cp.nwarp, cp.slots, cp.src_slots, cp.smem_elems, cp.lookback, cp.nrow_out,
+	              (int)cp.smem_bytes(), (int)std::min<long>(cp.nops, 1L << 30) };
+	memcpy(header, h, sizeof(h));
+	if( ops ) memcpy(ops, cp.ops.data(), cp.ops.size() * sizeof(int4));
+	if( src ) memcpy(src, cp.src.data(), cp.src.size() * sizeof(int4));
+	if( hdr ) memcpy(hdr, cp.hdr.data(), cp.hdr.size() * sizeof(int4));
 	return BF_STATUS_SUCCESS;
 }
 
@@ -947,6 +1171,11 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	int  nbuf = fused ? 3 : 2;
 	size_t need = (size_t)nbuf * (size_t)nbatch * sbatchstride * sizeof(float);
 	if( need == 0 ) need = 512;
+	// 1-byte inputs take the integer chain schedule (its own, smaller workspace)
+	const bool use_chain = !plan->chain.empty() && !negative_delays && !plan->cfg_force_v1 &&
+	                       (in->dtype == BF_DTYPE_I8 || in->dtype == BF_DTYPE_U8);
+	std::vector<ChainGeom> geom;
+	if( use_chain ) { BFB_TRY(need = chain_geometry(plan->chain, ntime, nbatch, &geom)); }
 	if( exec_storage_size ) {
 		if( !exec_storage ) { *exec_storage_size = need; return BF_STATUS_SUCCESS; }
 		BFB_ASSERT(*exec_storage_size >= need, BF_STATUS_INSUFFICIENT_STORAGE);
@@ -977,6 +1206,34 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	BFB_ASSERT(nbatch <= 65535 && P.nrow_max <= 65535, BF_STATUS_UNSUPPORTED_SHAPE);
 	long istride = in->strides[ndim-2] / isize,  ibatch = ibatchbytes / isize;
 	long ostride = out->strides[ndim-2] / 4,     obatch = obatchbytes / 4;
+
+	if( use_chain ) {
+		cudaStream_t cst = plan->get_stream();
+		char* ws = (char*)exec_storage;
+		const int npass = (int)plan->chain.size();
+		for( int k=0; k<npass; ++k ) {
+			ChainPass const& cp = plan->chain[k];
+			ChainParams q;
+			memset(&q, 0, sizeof(q));
+			if( k > 0 ) {
+				q.src = ws + geom[k-1].offset; q.sstride = geom[k-1].stride;
+				q.sbatch = (long)plan->chain[k-1].nrow_out * geom[k-1].stride; q.src_tb = geom[k-1].tb;
+			}
+			if( k == npass - 1 ) { q.dst = out->data; q.dstride = ostride; q.dbatch = obatch; q.dst_tb = 0; }
+			else {
+				q.dst = ws + geom[k].offset; q.dstride = geom[k].stride;
+				q.dbatch = (long)cp.nrow_out * geom[k].stride; q.dst_tb = geom[k].tb;
+			}
+			q.ops = cp.d_ops; q.srcs = cp.d_src; q.hdr = cp.d_hdr;
+			q.raw = in->data; q.rstride = istride; q.rbatch = ibatch;
+			q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
+			q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
+			q.is_signed = (in->dtype == BF_DTYPE_I8);
+			BFstatus ls = launch_chain_pass(cp, q, nbatch, cst);
+			if( ls != BF_STATUS_SUCCESS ) return ls;
+		}
+		return BF_STATUS_SUCCESS;
+	}
 
 	float* buf_a = (float*)exec_storage;
 	float* buf_b = buf_a + (size_t)nbatch * sbatchstride;

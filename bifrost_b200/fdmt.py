@@ -18,9 +18,11 @@ class Fdmt(BifrostObject):
                                  asarray(odata).as_BFarray(), negative_delays, None, None))
         return odata
 
-    def get_workspace_size(self, idata, odata):
+    def get_workspace_size(self, idata, odata, negative_delays=False):
+        # the workspace depends on the schedule, and negative_delays takes the
+        # step-by-step one: query with the flag the execute call will carry
         return _get(_bf.bfFdmtExecute, self.obj, asarray(idata).as_BFarray(),
-                    asarray(odata).as_BFarray(), False, None)
+                    asarray(odata).as_BFarray(), negative_delays, None)
 
     def execute_workspace(self, idata, odata, workspace_ptr, workspace_size,
                           negative_delays=False):

@@ -327,6 +327,18 @@ BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                          double exponent, int s0, int s1, int block_rows, int nwarp,
                          int raw, int* header, int* items, int* aux);
 
+/* B200 extension (test hook, host only): the tables of pass `pass` of the
+ * integer "chain" FDMT schedule that bfFdmtExecute runs for 1-byte inputs --
+ * see csrc/fdmt_chain.cuh for the op layout.  pass < 0: header[0] = number of
+ * passes (0: the schedule does not apply to this plan).  Otherwise
+ * header[16] = {s0, s1, nlev, esize, src_kind, dst_kind, T, nprog, nwarp,
+ * slots, src_slots, smem_elems, lookback, nrow_out, smem_bytes, nops};
+ * ops receives 4*nprog*nlev*nwarp*slots ints, src 4*nprog*src_slots ints,
+ * hdr 4*nprog ints (each may be NULL). */
+BFstatus bfFdmtChainQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+                          double exponent, int pass, int* header,
+                          int* ops, int* src, int* hdr);
+
 /* Number of kernels this library has launched since load (all threads). */
 BFstatus bfGetLaunchCount(unsigned long long* count);
 

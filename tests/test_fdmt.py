@@ -118,19 +118,29 @@ def test_reference_smoke_semantics(ntime, nchan, md, batch):
     assert_same_bits(o1, want)
 
 
+_OLD = dict(BFB_FDMT_CHAIN='0')     # the float schedules: switch the integer chain schedule off
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("knob", [dict(BFB_FDMT_V1='1'), dict(BFB_FDMT_K='2'), dict(BFB_FDMT_K='4', BFB_FDMT_SMEM_KB='48'),
-                                  dict(BFB_FDMT_K='8'), dict(BFB_FDMT_TAIL_TILE='1024', BFB_FDMT_TAIL_ROWS='3'),
-                                  dict(BFB_FDMT_THREADS='128'),
-                                  dict(BFB_FDMT_TILES='0'), dict(BFB_FDMT_RAWTILES='0'),
-                                  dict(BFB_FDMT_TILE_D='8', BFB_FDMT_SPLIT='7,9'),
-                                  dict(BFB_FDMT_TILE_D='64', BFB_FDMT_TILES_PER_CTA='3'),
-                                  dict(BFB_FDMT_K='3', BFB_FDMT_TILE_THREADS='128'),
-                                  dict(BFB_FDMT_K='1', BFB_FDMT_SPLIT='2,3,5,8')])
+@pytest.mark.parametrize("knob", [dict(BFB_FDMT_V1='1'), dict(_OLD), dict(_OLD, BFB_FDMT_K='2'),
+                                  dict(_OLD, BFB_FDMT_K='4', BFB_FDMT_SMEM_KB='48'),
+                                  dict(_OLD, BFB_FDMT_K='8'), dict(_OLD, BFB_FDMT_TAIL_TILE='1024', BFB_FDMT_TAIL_ROWS='3'),
+                                  dict(_OLD, BFB_FDMT_THREADS='128'),
+                                  dict(_OLD, BFB_FDMT_TILES='0'), dict(_OLD, BFB_FDMT_RAWTILES='0'),
+                                  dict(_OLD, BFB_FDMT_TILE_D='8', BFB_FDMT_SPLIT='7,9'),
+                                  dict(_OLD, BFB_FDMT_TILE_D='64', BFB_FDMT_TILES_PER_CTA='3'),
+                                  dict(_OLD, BFB_FDMT_K='3', BFB_FDMT_TILE_THREADS='128'),
+                                  dict(_OLD, BFB_FDMT_K='1', BFB_FDMT_SPLIT='2,3,5,8'),
+                                  # integer chain schedule (fdmt_chain.cuh): default and reshaped
+                                  dict(), dict(BFB_FDMT_CHAIN_SPLIT='3,6'), dict(BFB_FDMT_CHAIN_SPLIT='2,4,6,8'),
+                                  dict(BFB_FDMT_CHAIN_D='8,8,8', BFB_FDMT_CHAIN_JR='2,3,1'),
+                                  dict(BFB_FDMT_CHAIN_WARPS='4,2,1', BFB_FDMT_CHAIN_JR='16,16,16'),
+                                  dict(BFB_FDMT_CHAIN_TCAP='128,200,64', BFB_FDMT_CHAIN_D='5,100,7')])
 def test_every_schedule_gives_the_same_bits(knob):
-    """The step-by-step schedule (v1), the fused head + row-blocked tail (v2)
-    and the shared-memory tile passes (default; fdmt_tiles.cuh) at several
-    split levels / block sizes must agree bit for bit with the oracle."""
+    """The step-by-step schedule (v1), the fused head + row-blocked tail (v2),
+    the shared-memory tile passes (fdmt_tiles.cuh) and the integer chain
+    schedule (default for 1-byte inputs; fdmt_chain.cuh) at several split
+    levels / block sizes must agree bit for bit with the oracle."""
     rng = np.random.default_rng(21)
     old = {k: os.environ.get(k) for k in knob}
     os.environ.update(knob)
