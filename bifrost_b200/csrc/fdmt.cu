@@ -724,6 +724,7 @@ static bool build_chain_schedule(FdmtPlan const& P, std::vector<ChainPass>* pass
 	std::vector<int> NWs  = env_int_list("BFB_FDMT_CHAIN_WARPS");
 	std::vector<int> SMs  = env_int_list("BFB_FDMT_CHAIN_SMEM_KB");
 	std::vector<int> TCs  = env_int_list("BFB_FDMT_CHAIN_TCAP");
+	std::vector<int> KDs  = env_int_list("BFB_FDMT_CHAIN_KD");
 	// step-0 row -> input channel
 	std::vector<int> src_index(P.nrow(0), -1);
 	for( size_t c=0; c<P.bands[0].size(); ++c )
@@ -749,6 +750,7 @@ static bool build_chain_schedule(FdmtPlan const& P, std::vector<ChainPass>* pass
 		cfg.nwarp   = std::max(1, std::min(8, pi < NWs.size() ? NWs[pi] : 8));
 		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : 110);
 		cfg.tcap    = pi < TCs.size() ? std::max(64, TCs[pi]) : (1 << 20);
+		cfg.KD      = pi < KDs.size() ? std::max(1, KDs[pi]) : 1;
 		ChainPass cp;
 		bool ok = false;
 		for( int D=cfg.D; D>=2 && !ok; D=(D*2)/3 ) {
@@ -820,13 +822,26 @@ static cudaError_t launch_chain_kernel(ChainParams const& q, dim3 grid, int thre
 }
 
 static BFstatus launch_chain_pass(ChainPass const& cp, ChainParams const& q, long nbatch, cudaStream_t st) {
-	dim3 grid((unsigned)std::min<long>(q.ntile, 1L << 20), (unsigned)cp.nprog, (unsigned)nbatch);
+	// CTAs walk their program's tiles with a stride: about `waves` launch waves
+	// of 2 CTAs per SM in total, so the op tables are copied to shared memory a
+	// few times per program instead of once per tile.
+	static int sm_count = 0;
+	if( !sm_count ) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if( cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0 ) sm_count = 148;
+	}
+	const long waves = std::max(1, env_int("BFB_FDMT_CHAIN_WAVES", 4));
+	long gx = div_up<long>(2L * sm_count * waves, (long)cp.nprog * nbatch);
+	gx = std::max<long>(1, std::min<long>(gx, q.ntile));
+	gx = div_up<long>(q.ntile, div_up<long>(q.ntile, gx));      // equal shares
+	dim3 grid((unsigned)gx, (unsigned)cp.nprog, (unsigned)nbatch);
 	const int threads = cp.nwarp * 32;
 	const size_t smem = cp.smem_bytes();
 	cudaError_t e = cudaErrorInvalidValue;
 #define BFB_CH_LAUNCH(E_, S_, D_) \
-	e = (cp.nlev <= 3) ? launch_chain_kernel<E_, S_, D_, 3>(q, grid, threads, smem, st) \
-	                   : launch_chain_kernel<E_, S_, D_, 5>(q, grid, threads, smem, st)
+	e = cp.chains ? launch_chain_kernel<E_, S_, D_, CH_MAXLEV>(q, grid, threads, smem, st) \
+	              : launch_chain_kernel<E_, S_, D_, 0>(q, grid, threads, smem, st)
 	if( cp.esize == 2 ) {
 		if( cp.src_kind == CH_SRC_BYTES ) {
 			if(      cp.dst_kind == CH_DST_SAME ) BFB_CH_LAUNCH(2, CH_SRC_BYTES, CH_DST_SAME);

@@ -54,6 +54,7 @@ enum {
 	CH_NVEC_SHIFT = 16,
 	CH_MAXLEV  = 5,
 	CH_LV      = 3,          // 16-byte vectors per lane per row
+	CH_BYTE_WORDS = 6,       // 32-bit words per lane of the longest 1-byte source row (768 samples)
 };
 enum { CH_SRC_BYTES = 0, CH_SRC_SAME = 1 };
 enum { CH_DST_SAME = 0, CH_DST_CVT = 1, CH_DST_FINAL = 2 };
@@ -61,6 +62,7 @@ enum { CH_DST_SAME = 0, CH_DST_CVT = 1, CH_DST_FINAL = 2 };
 struct ChainCfg {
 	int D = 24;              // output delays per program
 	int JR = 6;              // head rows per chain job
+	int KD = 1;              // chain depth: levels a job keeps in registers (1: every row goes through shared memory)
 	int nwarp = 8;
 	int smem_cap = 110 * 1024;
 	int tcap = 1 << 20;      // upper bound on T
@@ -69,6 +71,7 @@ struct ChainCfg {
 struct ChainPass {
 	int s0 = 0, s1 = 0, nlev = 0;
 	int esize = 2;           // 2: packed u16 accumulators, 4: fp32
+	bool chains = false;     // some op takes its a operand from registers
 	int src_kind = CH_SRC_SAME, dst_kind = CH_DST_SAME;
 	int T = 0, nprog = 0, nwarp = 0, slots = 0, src_slots = 0;
 	int smem_elems = 0;      // data region (elements of esize bytes)
@@ -155,6 +158,7 @@ inline bool build_chain_pass(FdmtPlan const& P, std::vector<std::vector<char> > 
 	const int nlev = s1 - s0 + 1;
 	const int VS = 16 / esize, LS = CH_LV * VS, WLEN = 32 * LS;
 	const int nwarp = cfg.nwarp;
+	const int KD = std::max(1, std::min(cfg.KD, nlev));
 	// row -> band per step of the pass
 	std::vector<std::vector<int> > row_band(nlev + 1);
 	for( int li=0; li<=nlev; ++li ) {
@@ -180,9 +184,15 @@ inline bool build_chain_pass(FdmtPlan const& P, std::vector<std::vector<char> > 
 		}
 	}
 	if( progs.empty() ) return false;
+	// heavy programs (many rows) first: their CTAs start first and the light
+	// ones fill the tail of the launch
+	std::stable_sort(progs.begin(), progs.end(), [&](Prog const& a, Prog const& b) {
+		return P.bands[s1][a.band].ndelay * 64 + (int)a.rows.size() > P.bands[s1][b.band].ndelay * 64 + (int)b.rows.size();
+	});
 	struct Plan { std::vector<std::vector<Job> > jobs; std::map<int, Win> src; };
 	std::vector<Plan> plans(progs.size());
 	int max_spread = 0, lookback = 0;
+	bool any_reg = false;
 	for( size_t p=0; p<progs.size(); ++p ) {
 		Plan& pl = plans[p];
 		pl.jobs.assign(nlev + 1, std::vector<Job>());
@@ -195,7 +205,8 @@ inline bool build_chain_pass(FdmtPlan const& P, std::vector<std::vector<char> > 
 				by_band[row_band[li][it->first]].push_back(it->first);
 			for( std::map<int, std::vector<int> >::iterator bt=by_band.begin(); bt!=by_band.end(); ++bt ) {
 				std::vector<int>& rows = bt->second;          // ascending
-				int njob = std::max(1, div_up<int>((int)rows.size(), cfg.JR));
+				int jr   = (KD == 1) ? 1 : cfg.JR;            // without chains every row is its own job
+				int njob = std::max(1, div_up<int>((int)rows.size(), jr));
 				int per  = div_up<int>((int)rows.size(), njob);
 				for( size_t i=0; i<rows.size(); i+=per ) {
 					Job job; job.level = li;
@@ -205,26 +216,31 @@ inline bool build_chain_pass(FdmtPlan const& P, std::vector<std::vector<char> > 
 					job.w.lo = floor_to(lo, VS); job.w.hi = ceil_to(hi, VS);
 					max_spread = std::max(max_spread, job.w.hi - job.w.lo);
 					// generate the chain: rows of level li in order, low-frequency
-					// descendants on demand
+					// descendants on demand down to KD levels, from shared memory below
 					std::vector<int> cur(nlev + 1, -1);
 					struct Gen {
-						FdmtPlan const& P; int s0; Job& job; std::vector<int>& cur;
-						std::vector<std::map<int, Win> >& req;
-						void row(int l, int r, bool head) {
+						FdmtPlan const& P; int s0, KD; Job& job; std::vector<int>& cur;
+						std::vector<std::map<int, Win> >& req; bool& any_reg;
+						void row(int l, int r, int depth) {
 							FdmtRow const& fr = P.rows[s0 - 1 + l][r];
 							SymOp op; op.level = l; op.row = r; op.flags = 0;
 							op.a_row = fr.src0; op.b_row = fr.src1; op.delay = fr.delay;
 							if( fr.src0 < 0 ) op.flags |= CH_NO_A;
-							else if( l == 1 ) { op.flags |= CH_LOADA; grow(req[0], fr.src0, job.w.lo, job.w.hi); }
-							else if( cur[l-1] != fr.src0 ) row(l - 1, fr.src0, false);
+							else if( l == 1 || depth + 1 >= KD ) {
+								op.flags |= CH_LOADA;
+								grow(req[l-1], fr.src0, job.w.lo, job.w.hi);
+							} else {
+								any_reg = true;
+								if( cur[l-1] != fr.src0 ) row(l - 1, fr.src0, depth + 1);
+							}
 							if( fr.src1 < 0 ) op.flags |= CH_NO_B;
 							else grow(req[l-1], fr.src1, job.w.lo + fr.delay, job.w.hi + fr.delay);
-							if( head ) op.flags |= CH_STORE_S;     // refined to _G at encode time
+							if( depth == 0 ) op.flags |= CH_STORE_S;     // refined to _G at encode time
 							job.ops.push_back(op);
 							cur[l] = r;
 						}
-					} gen = {P, s0, job, cur, req};
-					for( int r : job.rows ) gen.row(li, r, true);
+					} gen = {P, s0, KD, job, cur, req, any_reg};
+					for( int r : job.rows ) gen.row(li, r, 0);
 					pl.jobs[li].push_back(job);
 				}
 			}
@@ -236,10 +252,10 @@ inline bool build_chain_pass(FdmtPlan const& P, std::vector<std::vector<char> > 
 			lookback = std::max(lookback, w.hi);
 		}
 	}
-	int T = std::min(cfg.tcap, WLEN - max_spread) / 8 * 8;
+	int T = std::min(cfg.tcap, WLEN - max_spread) / 16 * 16;
 	if( T < 64 ) return false;
 	cp->s0 = s0; cp->s1 = s1; cp->nlev = nlev; cp->esize = esize;
-	cp->src_kind = src_kind; cp->dst_kind = dst_kind;
+	cp->src_kind = src_kind; cp->dst_kind = dst_kind; cp->chains = any_reg;
 	cp->T = T; cp->nprog = (int)progs.size(); cp->nwarp = nwarp; cp->lookback = lookback;
 	// warp assignment (longest job first onto the least loaded warp) and list lengths
 	int slots = 1, src_slots = 1;
@@ -264,33 +280,62 @@ inline bool build_chain_pass(FdmtPlan const& P, std::vector<std::vector<char> > 
 	cp->ops.assign((size_t)cp->nprog * nlev * nwarp * slots, make_int4(0, 0, 0, 0));
 	cp->src.assign((size_t)cp->nprog * src_slots, make_int4(0, 0, 0, 0));
 	cp->hdr.assign((size_t)cp->nprog, make_int4(0, 0, 0, 0));
+	// Shared-memory layout: level li lives in region li % nreg.  Rows of level li
+	// are last read by chains headed at level li + KD and first overwritten in
+	// phase li + nreg, so nreg = KD + 1 regions rotate safely.
+	const int nreg = std::min(KD + 1, nlev);
 	int smem_max = 0;
 	for( size_t p=0; p<progs.size(); ++p ) {
 		Plan& pl = plans[p];
-		// storage: source rows, then every chain head below the top level
-		int off = 0;
-		std::map<int, int> src_off;
-		long staged = 0;
-		int k = 0;
-		for( std::map<int, Win>::iterator it=pl.src.begin(); it!=pl.src.end(); ++it, ++k ) {
-			int len = T + it->second.hi - it->second.lo;
-			if( len > WLEN ) return false;
-			src_off[it->first] = off;
-			if( it->first >= (int)src_index.size() || src_index[it->first] < 0 ) return false;
-			cp->src[p * src_slots + k] = make_int4(src_index[it->first], -it->second.hi, off, len);
-			staged += (long)len * esize;
-			off += len + 2 * VS;
-		}
 		std::vector<std::map<int, int> > row_off(nlev + 1), row_job(nlev + 1);
-		for( int li=1; li<nlev; ++li )
+		std::vector<int> level_size(nlev, 0);
+		// pass 1: offsets inside each level
+		{
+			int off = 0;
+			for( std::map<int, Win>::iterator it=pl.src.begin(); it!=pl.src.end(); ++it ) {
+				int len = T + it->second.hi - it->second.lo;
+				if( len > WLEN ) return false;
+				row_off[0][it->first] = off;
+				off += len + 2 * VS;
+			}
+			level_size[0] = off;
+		}
+		for( int li=1; li<nlev; ++li ) {
+			int off = 0;
 			for( size_t j=0; j<pl.jobs[li].size(); ++j ) {
 				Job const& job = pl.jobs[li][j];
 				int len = T + job.w.hi - job.w.lo;
 				if( len > WLEN ) return false;
 				for( int r : job.rows ) { row_off[li][r] = off; row_job[li][r] = (int)j; off += len + 2 * VS; }
 			}
-		smem_max = std::max(smem_max, off);
+			level_size[li] = off;
+		}
+		std::vector<int> region_size(nreg, 0), region_base(nreg, 0);
+		for( int li=0; li<nlev; ++li ) region_size[li % nreg] = std::max(region_size[li % nreg], level_size[li]);
+		for( int r=1; r<nreg; ++r ) region_base[r] = region_base[r-1] + region_size[r-1];
+		smem_max = std::max(smem_max, region_base[nreg-1] + region_size[nreg-1]);
+		for( int li=0; li<nlev; ++li )
+			for( std::map<int, int>::iterator it=row_off[li].begin(); it!=row_off[li].end(); ++it )
+				it->second += region_base[li % nreg];
+		// source table
+		long staged = 0;
+		int k = 0;
+		for( std::map<int, Win>::iterator it=pl.src.begin(); it!=pl.src.end(); ++it, ++k ) {
+			int len = T + it->second.hi - it->second.lo;
+			if( it->first >= (int)src_index.size() || src_index[it->first] < 0 ) return false;
+			cp->src[p * src_slots + k] = make_int4(src_index[it->first], -it->second.hi, row_off[0][it->first], len);
+			staged += (long)len * esize;
+		}
 		cp->hdr[p] = make_int4(P.bands[s1][progs[p].band].nchan, (int)pl.src.size(), (int)staged, 0);
+		// where a materialised row lives: offset, window
+		struct Loc { int base, hi, len; };
+		auto locate = [&](int li, int row) -> Loc {
+			Loc L;
+			L.base = row_off[li][row];
+			if( li == 0 ) { Win const& sw = pl.src[row]; L.hi = sw.hi; L.len = T + sw.hi - sw.lo; }
+			else { Job const& j = pl.jobs[li][row_job[li][row]]; L.hi = j.w.hi; L.len = T + j.w.hi - j.w.lo; }
+			return L;
+		};
 		std::vector<int> fill((size_t)nlev * nwarp, 0);
 		for( int li=1; li<=nlev; ++li )
 			for( Job const& job : pl.jobs[li] ) {
@@ -299,23 +344,16 @@ inline bool build_chain_pass(FdmtPlan const& P, std::vector<std::vector<char> > 
 					int4 op = make_int4(0, 0, 0, 0);
 					int flags = so.flags;
 					if( flags & CH_LOADA ) {
-						Win const& sw = pl.src[so.a_row];
-						int ea = sw.hi - job.w.hi;
-						if( ea < 0 || ea % VS || ea + len > T + sw.hi - sw.lo ) return false;
-						op.y = src_off[so.a_row] + ea;
+						Loc a = locate(so.level - 1, so.a_row);
+						int ea = a.hi - job.w.hi;
+						if( ea < 0 || ea % VS || ea + len > a.len ) return false;
+						op.y = a.base + ea;
 					}
 					if( !(flags & CH_NO_B) ) {
-						int base, bhi, blen;
-						if( so.level == 1 ) {
-							Win const& sw = pl.src[so.b_row];
-							base = src_off[so.b_row]; bhi = sw.hi; blen = T + sw.hi - sw.lo;
-						} else {
-							Job const& bj = pl.jobs[so.level - 1][row_job[so.level - 1][so.b_row]];
-							base = row_off[so.level - 1][so.b_row]; bhi = bj.w.hi; blen = T + bj.w.hi - bj.w.lo;
-						}
-						int eb = bhi - job.w.hi - so.delay;
-						if( eb < 0 || eb + len > blen ) return false;
-						op.z = base + eb;
+						Loc b = locate(so.level - 1, so.b_row);
+						int eb = b.hi - job.w.hi - so.delay;
+						if( eb < 0 || eb + len > b.len ) return false;
+						op.z = b.base + eb;
 					}
 					if( flags & CH_STORE_S ) {
 						if( so.level == nlev ) {
@@ -385,6 +423,71 @@ __device__ __forceinline__ void ch_shift(const uint32_t (&bw)[16], int hbits, ui
 }
 } // namespace chain_dev
 
+// A finished row of the pass's top level -> pass output (same element type),
+// or, for an fp32 pass that ends the plan, the diagonal store of fdmt.cu:141-147.
+template<int ESZ, int DSTK>
+__device__ __forceinline__ void ch_store_out(const uint32_t (&o)[12], const int4& op, int nvec,
+                                             const ChainParams& P, long t0, float* scratch, int lane, int warp) {
+	constexpr int VS = 16 / ESZ, LS = CH_LV * VS;
+	if( DSTK == CH_DST_FINAL ) {
+		float* sc = scratch + (size_t)warp * 32 * LS;
+		__syncwarp();
+#pragma unroll
+		for( int j=0; j<CH_LV; ++j )
+			*(uint4*)(sc + LS * lane + 4 * j) = make_uint4(o[4*j], o[4*j+1], o[4*j+2], o[4*j+3]);
+		__syncwarp();
+		const long d = op.x;
+		float* g = (float*)P.dst + (long)blockIdx.z * P.dbatch + d * P.dstride - d + t0;
+#pragma unroll 4
+		for( int i=lane; i<P.T; i+=32 ) {
+			const long t = t0 + i;
+			if( t >= d && t < P.ntime ) g[i] = sc[i];
+		}
+	} else {
+		unsigned char* g = (unsigned char*)P.dst +
+			((long)blockIdx.z * P.dbatch + (long)op.x * P.dstride + (t0 - P.dst_tb)) * ESZ;
+		uint4* d = (uint4*)g + CH_LV * lane;
+#pragma unroll
+		for( int j=0; j<CH_LV; ++j )
+			if( CH_LV * lane + j < nvec ) d[j] = make_uint4(o[4*j], o[4*j+1], o[4*j+2], o[4*j+3]);
+	}
+}
+// Top level of a 16-bit pass with fp32 output: halves added in 32 bits, bias
+// removed, converted (exact), stored to the fp32 workspace or diagonally.
+template<int DSTK>
+__device__ __forceinline__ void ch_store_wide(const uint32_t (&av)[12], const uint32_t (&bt)[12], const int4& op,
+                                              int nvec, int bias, const ChainParams& P, long t0,
+                                              float* scratch, int lane, int warp) {
+	constexpr int LS = CH_LV * 8;
+	float f[2 * 12];
+#pragma unroll
+	for( int k=0; k<12; ++k ) {
+		int lo = (int)(av[k] & 0xFFFFu) + (int)(bt[k] & 0xFFFFu) - bias;
+		int hi = (int)(av[k] >> 16)     + (int)(bt[k] >> 16)     - bias;
+		f[2*k] = (float)lo; f[2*k+1] = (float)hi;
+	}
+	if( DSTK == CH_DST_CVT ) {
+		float* g = (float*)P.dst + (long)blockIdx.z * P.dbatch + (long)op.x * P.dstride + (t0 - P.dst_tb) + LS * lane;
+#pragma unroll
+		for( int j=0; j<2*CH_LV; ++j )
+			if( 2 * (CH_LV * lane) + j < 2 * nvec )
+				*(float4*)(g + 4 * j) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
+	} else {
+		float* sc = scratch + (size_t)warp * 32 * LS;
+		__syncwarp();
+#pragma unroll
+		for( int j=0; j<2*CH_LV; ++j ) *(float4*)(sc + LS * lane + 4 * j) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
+		__syncwarp();
+		const long d = op.x;
+		float* g = (float*)P.dst + (long)blockIdx.z * P.dbatch + d * P.dstride - d + t0;
+#pragma unroll 4
+		for( int i=lane; i<P.T; i+=32 ) {
+			const long t = t0 + i;
+			if( t >= d && t < P.ntime ) g[i] = sc[i];
+		}
+	}
+}
+
 // Fetch / produce one level's registers with compile-time indices.
 template<int L, int NLMAX>
 __device__ __forceinline__ void ch_get(const uint32_t (&R)[NLMAX + 1][12], uint32_t (&av)[12]) {
@@ -442,8 +545,81 @@ __device__ __forceinline__ void ch_level(uint32_t (&R)[NLMAX + 1][12], const uin
 	}
 }
 
-template<int ESZ, int SRCK, int DSTK, int NLMAX>
-__global__ void __launch_bounds__(256, 2)
+// One op of a pass without register chains: row = a + shift(b), both from
+// shared memory, to shared memory or to the pass output.
+template<int ESZ, int DSTK>
+__device__ __forceinline__ void ch_row_op(const int4& op, unsigned char* dbase, const ChainParams& P, long t0,
+                                          int bias, float* scratch, int lane, int warp) {
+	using namespace chain_dev;
+	constexpr int VS = 16 / ESZ;
+	const int nvec = op.w >> CH_NVEC_SHIFT;
+	uint32_t av[12], bw[16];
+	if( op.w & (CH_NO_A | CH_NO_B) ) {
+		// absent parent (odd band counts): zeros stand in
+		if( op.w & CH_NO_A ) {
+#pragma unroll
+			for( int k=0; k<12; ++k ) av[k] = 0u;
+		} else {
+			const uint4* a = (const uint4*)(dbase + (size_t)op.y * ESZ) + CH_LV * lane;
+#pragma unroll
+			for( int j=0; j<CH_LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
+		}
+		if( op.w & CH_NO_B ) {
+#pragma unroll
+			for( int k=0; k<16; ++k ) bw[k] = 0u;
+		} else {
+			const int sub = op.z & (VS - 1);
+			const uint4* b = (const uint4*)(dbase + (size_t)(op.z - sub) * ESZ) + CH_LV * lane;
+#pragma unroll
+			for( int j=0; j<CH_LV+1; ++j ) { uint4 v = b[j]; bw[4*j] = v.x; bw[4*j+1] = v.y; bw[4*j+2] = v.z; bw[4*j+3] = v.w; }
+		}
+	} else {
+		const uint4* a = (const uint4*)(dbase + (size_t)op.y * ESZ) + CH_LV * lane;
+		const int sub = op.z & (VS - 1);
+		const uint4* b = (const uint4*)(dbase + (size_t)(op.z - sub) * ESZ) + CH_LV * lane;
+#pragma unroll
+		for( int j=0; j<CH_LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
+#pragma unroll
+		for( int j=0; j<CH_LV+1; ++j ) { uint4 v = b[j]; bw[4*j] = v.x; bw[4*j+1] = v.y; bw[4*j+2] = v.z; bw[4*j+3] = v.w; }
+	}
+	const int sub = (op.w & CH_NO_B) ? 0 : (op.z & (VS - 1));
+	const int wo = (ESZ == 2) ? (sub >> 1) : sub;
+	const int hbits = (ESZ == 2) ? (sub & 1) * 16 : 0;
+	if( (ESZ == 2) && (DSTK != CH_DST_SAME) && (op.w & CH_STORE_G) ) {
+		// top level of a 16-bit pass whose output is fp32: the sum may exceed
+		// 16 bits, add the halves in 32 bits and drop the bias
+		uint32_t bt[12];
+		switch( wo ) {
+		case 0:  ch_shift<ESZ, 0>(bw, hbits, bt); break;
+		case 1:  ch_shift<ESZ, 1>(bw, hbits, bt); break;
+		case 2:  ch_shift<ESZ, 2>(bw, hbits, bt); break;
+		default: ch_shift<ESZ, 3>(bw, hbits, bt); break;
+		}
+		ch_store_wide<DSTK>(av, bt, op, nvec, bias, P, t0, scratch, lane, warp);
+		return;
+	}
+	switch( wo ) {
+#define BFB_CH_CASE(W_) \
+		_Pragma("unroll") for( int k=0; k<12; ++k ) \
+			av[k] = ch_add<ESZ>(av[k], (ESZ == 2) ? __funnelshift_r(bw[k + W_], bw[k + W_ + 1], hbits) : bw[k + W_]);
+	case 0:  BFB_CH_CASE(0) break;
+	case 1:  BFB_CH_CASE(1) break;
+	case 2:  BFB_CH_CASE(2) break;
+	default: BFB_CH_CASE(3) break;
+#undef BFB_CH_CASE
+	}
+	if( op.w & CH_STORE_S ) {
+		uint4* d = (uint4*)(dbase + (size_t)op.x * ESZ) + CH_LV * lane;
+#pragma unroll
+		for( int j=0; j<CH_LV; ++j )
+			if( CH_LV * lane + j < nvec ) d[j] = make_uint4(av[4*j], av[4*j+1], av[4*j+2], av[4*j+3]);
+	} else {
+		ch_store_out<ESZ, DSTK>(av, op, nvec, P, t0, scratch, lane, warp);
+	}
+}
+
+template<int ESZ, int SRCK, int DSTK, int NLMAX>     // NLMAX == 0: no op keeps a row in registers
+__global__ void __launch_bounds__(256, NLMAX == 0 ? 3 : 2)
 fdmt_chain_kernel(const __grid_constant__ ChainParams P) {
 	using namespace chain_dev;
 	constexpr int VS = 16 / ESZ;           // elements per 16-byte vector
@@ -479,33 +655,60 @@ fdmt_chain_kernel(const __grid_constant__ ChainParams P) {
 		const long t0 = P.t_begin + tile * P.T;
 		// ---- stage the source rows
 		if( SRCK == CH_SRC_BYTES ) {
+			// Two rows per warp at a time, all of their global loads issued before
+			// the first is consumed (the loads come from HBM: ~1 us each).
 			uint16_t* data = (uint16_t*)dbase;
 			const uint32_t flip = P.is_signed ? 0x80808080u : 0u;
-			for( int k=warp; k<hdr.y; k+=nwarp ) {
-				const int4 e = ssrc[k];
-				const long ts = t0 + e.y;
-				const unsigned char* g = rin + (long)e.x * P.rstride + ts;
-				uint16_t* srow = data + e.z;
-				const int nword = e.w >> 2;
-				if( ts >= 4 && ts + e.w + 8 <= P.ntime ) {
-					const unsigned mis = (unsigned)((uintptr_t)g & 3);
-					const uint32_t* ga = (const uint32_t*)(g - mis);
-					for( int j=lane; j<nword; j+=32 ) {
-						uint32_t w0 = __ldg(ga + j), w1 = __ldg(ga + j + 1);
-						uint32_t w = __funnelshift_r(w0, w1, mis * 8) ^ flip;
-						*(uint2*)(srow + 4 * j) = make_uint2(__byte_perm(w, 0, 0x4140), __byte_perm(w, 0, 0x4342));
-					}
-				} else {
-					for( int j=lane; j<nword; j+=32 ) {
-						uint32_t w = 0;
+			for( int k0=warp; k0<hdr.y; k0+=2*nwarp ) {
+				uint32_t w[2][CH_BYTE_WORDS + 1];
+				int4 e[2]; bool fast[2];
 #pragma unroll
-						for( int q=0; q<4; ++q ) {
-							long t = ts + 4 * j + q;
-							uint32_t v = (t >= 0 && t < P.ntime) ? (uint32_t)g[4 * j + q] : 0u;
-							w |= v << (8 * q);
+				for( int q=0; q<2; ++q ) {
+					const int k = k0 + q * nwarp;
+					e[q] = (k < hdr.y) ? ssrc[k] : make_int4(0, 0, 0, 0);
+					const long ts = t0 + e[q].y;
+					const unsigned char* g = rin + (long)e[q].x * P.rstride + ts;
+					fast[q] = e[q].w > 0 && ts >= 4 && ts + e[q].w + 4 <= P.ntime;
+					const uint32_t* ga = (const uint32_t*)(g - ((uintptr_t)g & 3));
+					const int nword = e[q].w >> 2;
+#pragma unroll
+					for( int i=0; i<=CH_BYTE_WORDS; ++i ) {
+						const int j = lane + 32 * i;
+						w[q][i] = (fast[q] && j <= nword) ? __ldg(ga + j) : 0u;
+					}
+				}
+#pragma unroll
+				for( int q=0; q<2; ++q ) {
+					if( e[q].w == 0 ) continue;
+					const long ts = t0 + e[q].y;
+					const unsigned char* g = rin + (long)e[q].x * P.rstride + ts;
+					uint16_t* srow = data + e[q].z;
+					const int nword = e[q].w >> 2;
+					if( fast[q] ) {
+						const unsigned mis = (unsigned)((uintptr_t)g & 3);
+#pragma unroll
+						for( int i=0; i<CH_BYTE_WORDS; ++i ) {
+							const int j = lane + 32 * i;
+							uint32_t hi = __shfl_down_sync(0xffffffffu, w[q][i], 1);
+							const uint32_t nx = __shfl_sync(0xffffffffu, w[q][i + 1], 0);
+							if( lane == 31 ) hi = nx;
+							if( j < nword ) {
+								const uint32_t v = __funnelshift_r(w[q][i], hi, mis * 8) ^ flip;
+								*(uint2*)(srow + 4 * j) = make_uint2(__byte_perm(v, 0, 0x4140), __byte_perm(v, 0, 0x4342));
+							}
 						}
-						w ^= flip;
-						*(uint2*)(srow + 4 * j) = make_uint2(__byte_perm(w, 0, 0x4140), __byte_perm(w, 0, 0x4342));
+					} else {
+						for( int j=lane; j<nword; j+=32 ) {
+							uint32_t v = 0;
+#pragma unroll
+							for( int b=0; b<4; ++b ) {
+								const long t = ts + 4 * j + b;
+								const uint32_t x = (t >= 0 && t < P.ntime) ? (uint32_t)g[4 * j + b] : 0u;
+								v |= x << (8 * b);
+							}
+							v ^= flip;
+							*(uint2*)(srow + 4 * j) = make_uint2(__byte_perm(v, 0, 0x4140), __byte_perm(v, 0, 0x4342));
+						}
 					}
 				}
 			}
@@ -525,6 +728,19 @@ fdmt_chain_kernel(const __grid_constant__ ChainParams P) {
 		__syncthreads();
 
 		// ---- merge levels
+		if constexpr( NLMAX == 0 ) {
+			for( int lev=1; lev<=P.nlev; ++lev ) {
+				const int4* list = sops + ((size_t)(lev - 1) * nwarp + warp) * P.slots;
+				int4 nxt = list[0];
+				for( int m=0; m<P.slots; ++m ) {
+					const int4 op = nxt;
+					if( op.w == 0 ) break;
+					nxt = list[m + 1];                     // the last slot of a list is always a terminator
+					ch_row_op<ESZ, DSTK>(op, dbase, P, t0, bias, scratch, lane, warp);
+				}
+				__syncthreads();
+			}
+		} else {
 		uint32_t R[NLMAX + 1][12];
 		for( int lev=1; lev<=P.nlev; ++lev ) {
 			const int4* list = sops + ((size_t)(lev - 1) * nwarp + warp) * P.slots;
@@ -614,6 +830,7 @@ fdmt_chain_kernel(const __grid_constant__ ChainParams P) {
 			}
 			__syncthreads();
 		}
+		}   // chains
 	}
 }
 
