@@ -279,33 +279,41 @@ class _ConsumerMixin(object):
         return self.gulp_nframe or self._iseq.header.get('gulp_nframe') or 1
 
     def _push(self, iseq, data, frame_offset):
+        """Cuts the pushed span into gulps of gulp + overlap frames.  Gulps are
+        *views* of one buffer walked with a read cursor; only the tail that is
+        left over (fewer than gulp + overlap frames) is copied, once per push,
+        in front of the next span -- so the work is linear in the frames pushed
+        even when the consumer's gulp is much smaller than the producer's."""
         fax = self._ifax
         gulp, ovl = self._gulp(), self._overlap
         if self._pending is None and ovl == 0 and data.shape[fax] == gulp:
             self._process(data, frame_offset)                 # zero-copy fast path
             return
         if self._pending is None:
-            self._pending, self._pending_offset = data, frame_offset
+            buf, self._pending_offset = data, frame_offset
         else:
+            n0, n1 = self._pending.shape[fax], data.shape[fax]
             shape = list(self._pending.shape)
-            shape[fax] += data.shape[fax]
-            merged = empty(shape, dtype=self._pending.bf.dtype, space=self._pending.bf.space)
-            n0 = self._pending.shape[fax]
-            copy_array(_slice_frames(merged, fax, 0, n0), self._pending)
-            copy_array(_slice_frames(merged, fax, n0, shape[fax]), data)
-            self._pending = merged
-        while self._pending is not None and self._pending.shape[fax] >= gulp + ovl:
-            chunk = _slice_frames(self._pending, fax, 0, gulp + ovl)
-            self._process(chunk, self._pending_offset)
-            rest = self._pending.shape[fax] - gulp
-            if rest > 0:
-                keep = _slice_frames(self._pending, fax, gulp, gulp + rest)
-                fresh = empty(keep.shape, dtype=keep.bf.dtype, space=keep.bf.space)
-                copy_array(fresh, keep)
-                self._pending = fresh
-            else:
-                self._pending = None
+            shape[fax] = n0 + n1
+            buf = empty(shape, dtype=self._pending.bf.dtype, space=self._pending.bf.space)
+            copy_array(_slice_frames(buf, fax, 0, n0), self._pending)
+            copy_array(_slice_frames(buf, fax, n0, n0 + n1), data)
+        nbuf, pos = buf.shape[fax], 0
+        while nbuf - pos >= gulp + ovl:
+            self._process(_slice_frames(buf, fax, pos, pos + gulp + ovl), self._pending_offset)
+            pos += gulp
             self._pending_offset += gulp
+        if pos == nbuf:
+            self._pending = None
+        elif pos == 0 and buf is not data:
+            self._pending = buf
+        else:
+            # own copy of the tail: `data` belongs to the producer, and a view
+            # would keep the whole span alive
+            tail = _slice_frames(buf, fax, pos, nbuf)
+            keep = empty(tail.shape, dtype=tail.bf.dtype, space=tail.bf.space)
+            copy_array(keep, tail)
+            self._pending = keep
 
     def _end_sequence(self, iseq):
         fax = self._ifax

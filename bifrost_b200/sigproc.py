@@ -27,9 +27,14 @@ def id2telescope(id_):
 
 
 def telescope2id(name):
+    """Name -> id; 'unknown' (what id2telescope gives a file without the card)
+    maps back to None so that write_header leaves the card out again, as the
+    reference's defaultdict round trip does (sigproc2.py:106-149)."""
     for k, v in _telescopes.items():
         if v == name:
             return k
+    if name == 'unknown':
+        return None
     raise ValueError("Unknown telescope: %r" % name)
 
 
@@ -41,6 +46,8 @@ def machine2id(name):
     for k, v in _machines.items():
         if v == name:
             return k
+    if name == 'unknown':
+        return None
     raise ValueError("Unknown machine: %r" % name)
 
 

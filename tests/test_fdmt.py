@@ -280,6 +280,49 @@ def test_schedules_agree_bit_for_bit_at_baseline_sizes(md, f0, bw):
     assert_same_bits(got, want)
 
 
+def _oracle_windows(x, md, f0, df, got, windows):
+    """Compares output columns [a, a+w) of a long gulp with the C oracle run on
+    the input slice those columns depend on (columns a .. a+w+md: row r at
+    column c sums input times c .. c+r).  The slice's own t < 0 edge never
+    reaches the compared columns except for a == 0, where it is the gulp's."""
+    from oracle import fdmt_c
+    assert fdmt_c.available()
+    nchan, ntime = x.shape
+    plan = fdmt_c.Plan(nchan, md, f0, df)
+    for a, w in windows:
+        b = min(ntime, a + w + md)
+        xs = np.ascontiguousarray(x[:, a:b])
+        want = np.full((md, b - a), SENTINEL, np.float32)
+        plan.execute(xs, want)
+        n = min(w, b - a)
+        # cells the reference leaves unwritten (column >= ntime - r) exist only in
+        # the window that touches the end of the gulp; there both hold the sentinel
+        assert_same_bits(got[:, a:a + n], want[:, :n])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("md,f0,bw", [(794, 1000., 400.), (204, 1000., 400.), (1621, 1200., 300.)])
+def test_baseline_gulp_matches_the_oracle_at_full_size(md, f0, bw):
+    """VALUE check of the exact gulp bench.py times (BASELINE config 2: 4096 chan x
+    131072+max_delay int8 with the three injected pulses; plus SURVEY 8d's
+    max_delay 204 / 1621 variants): five disjoint 8192-column windows, both
+    edges included, bit for bit against oracle/fdmt_c.c."""
+    import bench
+    nchan = 4096
+    w = dict(nchan=nchan, ntime=131072 + md, max_delay=md, f0=f0, df=bw / nchan)
+    x = bench.make_input(w, 1234)
+    got = run_gpu(x, md, f0, bw / nchan)
+    ntime = w['ntime']
+    wins = [(0, 8192), (40000, 8192), (65536 + 3, 8192), (100001, 8192), (ntime - 8192 - md, 8192 + md)]
+    _oracle_windows(x, md, f0, bw / nchan, got, wins)
+    if md == 794:
+        # the injected pulses come out in their DM rows
+        for frac, t0 in ((0.2, ntime // 5), (0.5, ntime // 2), (0.9, (3 * ntime) // 4)):
+            d = int(round(frac * (md - 1)))
+            blk = got[max(0, d - 2):d + 3, t0 - 3:t0 + 4]
+            assert blk.max() > 0.5 * 100 * nchan
+
+
 def test_plan_that_leaves_its_parent_band_is_rejected():
     """nchan=256, max_delay=300 at 1000-1400 MHz makes a source row index fall
     outside its parent band (step 7); the reference hits assert() and aborts

@@ -124,6 +124,35 @@ def test_sigproc_filterbank_round_trip(tmp_path, dtype, npdt):
     np.testing.assert_array_equal(np.concatenate(out.chunks, 0), x)
 
 
+def test_sigproc_file_without_id_cards_round_trips(tmp_path):
+    """read_sigproc -> write_sigproc of a file that has no telescope_id / machine_id
+    card: the ids come back as 'unknown' and the sink leaves the cards out again
+    (the reference's defaultdict round trip, sigproc2.py:106-154)."""
+    x = (np.arange(40 * 8).reshape(40, 1, 8) % 100).astype(np.uint8)
+    src_path = str(tmp_path / 'noid.fil')
+    with open(src_path, 'wb') as f:
+        sigproc.write_header(dict(data_type=1, nchans=8, nifs=1, nbits=8, tstart=58000.0, tsamp=1e-3,
+                                  fch1=1500.0, foff=-0.5, source_name='X'), f)
+        x.tofile(f)
+    outdir = tmp_path / 'out'
+    outdir.mkdir()
+    with Pipeline() as p:
+        src = blocks.read_sigproc([src_path], gulp_nframe=16)
+        blocks.write_sigproc(src, path=str(outdir))
+        p.run()
+    written = sorted(os.listdir(str(outdir)))
+    assert len(written) == 1 and written[0].startswith('noid')
+    with open(str(outdir / written[0]), 'rb') as f:
+        h = sigproc.read_header(f)
+        body = np.fromfile(f, dtype=np.uint8)
+    assert 'telescope_id' not in h and 'machine_id' not in h
+    assert h['nchans'] == 8 and h['source_name'] == 'X'
+    np.testing.assert_array_equal(body.reshape(x.shape), x)
+    assert sigproc.telescope2id('unknown') is None and sigproc.machine2id('unknown') is None
+    with pytest.raises(ValueError):
+        sigproc.telescope2id('Atlantis')
+
+
 def test_sigproc_dispersion_trials_one_tim_per_dm(tmp_path):
     """[dispersion, time, pol] -- the FDMT block's output -- becomes one time series per trial."""
     rng = np.random.default_rng(4)

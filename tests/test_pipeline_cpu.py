@@ -44,6 +44,29 @@ def test_copy_chain_with_mixed_gulp_sizes():
     assert out.headers[0]['_tensor']['shape'] == [-1, 3]
 
 
+def test_small_gulps_after_a_large_span_copy_linearly(monkeypatch):
+    """A gulp-1 consumer behind a 600-frame producer: gulps are views walked
+    with a cursor, so the frames copied stay O(frames pushed), not O(n^2)."""
+    from bifrost_b200 import pipeline as pl
+    copied = [0]
+    real = pl.copy_array
+
+    def counting(dst, src):
+        copied[0] += int(np.prod(src.shape))
+        return real(dst, src)
+
+    monkeypatch.setattr(pl, 'copy_array', counting)
+    data = np.arange(600 * 2, dtype=np.float32).reshape(600, 2)
+    out = Collect()
+    with Pipeline() as p:
+        src = array_source(data, header([-1, 2]), gulp_nframe=600)
+        b = copy(src, gulp_nframe=1)
+        callback_sink(b, out.seq, out.data, gulp_nframe=7)
+        p.run()
+    np.testing.assert_array_equal(np.concatenate(out.chunks, axis=0), data)
+    assert copied[0] < 20 * data.size
+
+
 class MovingSum(TransformBlock):
     """Needs `overlap` frames of history, like FdmtBlock (blocks/fdmt.py:112-124)."""
     overlap = 3
