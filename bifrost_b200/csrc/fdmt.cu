@@ -459,7 +459,7 @@ fdmt_tail_kernel(const float* __restrict__ prev, long pstride, long pbatchstride
 } // namespace bfb
 
 #include "fdmt_tiles.cuh"
-#include "fdmt_chain.cuh"
+#include "fdmt_packed.cuh"
 
 using namespace bfb;
 
@@ -498,8 +498,15 @@ struct BFfdmt_impl {
 	TilePass head_pass;                  // steps 1..K straight from 1-byte input
 	bool   head_pass_ok = false;
 	int    cfg_tile_d = 24, cfg_tile_smem_kb = 110, cfg_tile_threads = 256;
-	// integer chain schedule for 1-byte inputs (fdmt_chain.cuh); empty = n/a
-	std::vector<ChainPass> chain;
+	// packed-integer schedule for 1-byte inputs (fdmt_packed.cuh); empty = n/a
+	std::vector<PackedPass> packed;
+	// its persistent single-launch form (fdmt_packed_mega_kernel)
+	bool   mega_ok = false;
+	long   mega_chunk = 0;
+	int    mega_lag = 0, mega_ipr = 0;
+	int*   d_mega_tmpl = nullptr;
+	int*   d_mega_counters = nullptr;
+	size_t mega_counters_cap = 0;
 	// exec workspace
 	void*  own_exec_storage = nullptr;
 	size_t own_exec_size = 0;
@@ -525,12 +532,15 @@ struct BFfdmt_impl {
 		if( head_pass.d_aux )   cudaFree(head_pass.d_aux);
 		head_pass = TilePass();
 		head_pass_ok = false;
-		for( ChainPass& cp : chain ) {
+		for( PackedPass& cp : packed ) {
 			if( cp.d_ops ) cudaFree(cp.d_ops);
 			if( cp.d_src ) cudaFree(cp.d_src);
 			if( cp.d_hdr ) cudaFree(cp.d_hdr);
 		}
-		chain.clear();
+		packed.clear();
+		if( d_mega_tmpl ) cudaFree(d_mega_tmpl);
+		if( d_mega_counters ) cudaFree(d_mega_counters);
+		d_mega_tmpl = nullptr; d_mega_counters = nullptr; mega_counters_cap = 0; mega_ok = false;
 	}
 };
 
@@ -675,7 +685,7 @@ static void build_tail_passes(BFfdmt_impl* plan) {
 
 
 // ---------------------------------------------------------------------------
-// Integer chain schedule (fdmt_chain.cuh): pass list, geometry, launch
+// Packed-integer schedule (fdmt_packed.cuh): pass list, geometry, launch
 // ---------------------------------------------------------------------------
 static std::vector<int> env_int_list(const char* name) {
 	std::vector<int> v;
@@ -692,39 +702,15 @@ static std::vector<int> env_int_list(const char* name) {
 // Cuts steps 1..S into passes (16-bit passes up to the first step whose
 // sub-bands overflow 16 bits, fp32 passes above) and builds their tables.
 // Returns false when the schedule does not apply to this plan.
-static bool build_chain_schedule(FdmtPlan const& P, std::vector<ChainPass>* passes_) {
-	std::vector<ChainPass>& passes = *passes_;
+static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char> > const& used,
+                                int S, int S16, int U, std::vector<int> const& ends,
+                                std::vector<PackedPass>* passes_) {
+	std::vector<PackedPass>& passes = *passes_;
 	passes.clear();
-	if( env_int("BFB_FDMT_CHAIN", 1) == 0 ) return false;
-	std::vector<std::vector<char> > used;
-	fdmt_used_rows(P, &used);
-	if( !fdmt_integer_safe(P, used) ) return false;
-	const int S = P.nstep() - 1;
-	if( S < 1 ) return false;
-	const int S16 = fdmt_last_u16_step(P);
-	const int U = std::min(S, S16 + 1);            // last step of the 16-bit part
-	std::vector<int> ends = env_int_list("BFB_FDMT_CHAIN_SPLIT");
-	if( ends.empty() ) {
-		int npu = div_up<int>(U, CH_MAXLEV);
-		for( int k=1; k<=npu; ++k ) ends.push_back(std::min(U, div_up<int>(U * k, npu)));
-		// (uneven splits put the longer pass first: the lowest steps are the cheapest)
-		int nf = S - U, npf = div_up<int>(nf, 3);
-		for( int k=1; k<=npf; ++k ) ends.push_back(U + div_up<int>(nf * k, npf));
-	} else {
-		std::vector<int> e2;
-		for( int v : ends ) if( v >= 1 && v < S && (e2.empty() || v > e2.back()) ) e2.push_back(v);
-		// a pass may not straddle the 16-bit limit except with its top level
-		if( std::find(e2.begin(), e2.end(), U) == e2.end() && U < S ) e2.push_back(U);
-		std::sort(e2.begin(), e2.end());
-		e2.push_back(S);
-		ends = e2;
-	}
-	std::vector<int> Ds   = env_int_list("BFB_FDMT_CHAIN_D");
-	std::vector<int> JRs  = env_int_list("BFB_FDMT_CHAIN_JR");
-	std::vector<int> NWs  = env_int_list("BFB_FDMT_CHAIN_WARPS");
-	std::vector<int> SMs  = env_int_list("BFB_FDMT_CHAIN_SMEM_KB");
-	std::vector<int> TCs  = env_int_list("BFB_FDMT_CHAIN_TCAP");
-	std::vector<int> KDs  = env_int_list("BFB_FDMT_CHAIN_KD");
+	std::vector<int> Ds   = env_int_list("BFB_FDMT_PACKED_D");
+	std::vector<int> NWs  = env_int_list("BFB_FDMT_PACKED_WARPS");
+	std::vector<int> SMs  = env_int_list("BFB_FDMT_PACKED_SMEM_KB");
+	std::vector<int> TCs  = env_int_list("BFB_FDMT_PACKED_TCAP");
 	// step-0 row -> input channel
 	std::vector<int> src_index(P.nrow(0), -1);
 	for( size_t c=0; c<P.bands[0].size(); ++c )
@@ -737,25 +723,30 @@ static bool build_chain_schedule(FdmtPlan const& P, std::vector<ChainPass>* pass
 		const int esize = (s0 <= U) ? 2 : 4;
 		if( esize == 2 && s1 > U ) return false;
 		if( esize == 2 && s1 > S16 && !(s1 == U) ) return false;
-		const int src_kind = (s0 == 1) ? CH_SRC_BYTES : CH_SRC_SAME;
-		int dst_kind = fin ? CH_DST_FINAL : CH_DST_SAME;
-		if( !fin && esize == 2 && s1 == U ) dst_kind = CH_DST_CVT;   // the next pass is fp32
+		if( s1 - s0 + 1 > PK_MAXLEV ) return false;
+		const int src_kind = (s0 == 1) ? PK_SRC_BYTES : PK_SRC_SAME;
+		int dst_kind = fin ? PK_DST_FINAL : PK_DST_SAME;
+		if( !fin && esize == 2 && s1 == U ) dst_kind = PK_DST_CVT;   // the next pass is fp32
 		std::vector<int> out_index(P.nrow(s1), -1);
 		int nout = 0;
 		for( int r=0; r<P.nrow(s1); ++r ) if( used[s1][r] ) out_index[r] = fin ? r : nout++;
-		ChainCfg cfg;
+		PackedCfg cfg;
 		const size_t pi = passes.size();
 		cfg.D       = pi < Ds.size()  ? Ds[pi]  : (s0 == 1 ? 64 : 24);
-		cfg.JR      = pi < JRs.size() ? JRs[pi] : 4;
 		cfg.nwarp   = std::max(1, std::min(8, pi < NWs.size() ? NWs[pi] : 8));
-		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : 110);
+		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : 74);
 		cfg.tcap    = pi < TCs.size() ? std::max(64, TCs[pi]) : (1 << 20);
-		cfg.KD      = pi < KDs.size() ? std::max(1, KDs[pi]) : 1;
-		ChainPass cp;
+		PackedPass cp;
 		bool ok = false;
-		for( int D=cfg.D; D>=2 && !ok; D=(D*2)/3 ) {
-			ChainCfg c2 = cfg; c2.D = D;
-			ok = build_chain_pass(P, used, s0, s1, esize, src_kind, dst_kind, src_index, out_index, c2, &cp);
+		// smaller delay blocks first (more programs, a little more redundancy),
+		// then shorter tiles (idle lanes), until the program fits its shared memory
+		const int tcaps[5] = { cfg.tcap, 512, 384, 256, 128 };
+		for( int ti=0; ti<5 && !ok; ++ti ) {
+			if( ti > 0 && tcaps[ti] >= cfg.tcap ) continue;
+			for( int D=cfg.D; D>=2 && !ok; D-=std::max(1, D/8) ) {
+				PackedCfg c2 = cfg; c2.D = D; c2.tcap = tcaps[ti];
+				ok = build_packed_pass(P, used, s0, s1, esize, src_kind, dst_kind, src_index, out_index, c2, &cp);
+			}
 		}
 		if( !ok ) { passes.clear(); return false; }
 		cp.nrow_out = fin ? P.nrow(s1) : nout;
@@ -767,8 +758,42 @@ static bool build_chain_schedule(FdmtPlan const& P, std::vector<ChainPass>* pass
 	return true;
 }
 
-static bool upload_chain(std::vector<ChainPass>* passes) {
-	for( ChainPass& cp : *passes ) {
+static bool build_packed_schedule(FdmtPlan const& P, std::vector<PackedPass>* passes) {
+	passes->clear();
+	if( env_int("BFB_FDMT_PACKED", 1) == 0 ) return false;
+	std::vector<std::vector<char> > used;
+	fdmt_used_rows(P, &used);
+	if( !fdmt_integer_safe(P, used) ) return false;
+	const int S = P.nstep() - 1;
+	if( S < 1 ) return false;
+	const int S16 = fdmt_last_u16_step(P);
+	const int U = std::min(S, S16 + 1);            // last step of the 16-bit part
+	std::vector<int> ends = env_int_list("BFB_FDMT_PACKED_SPLIT");
+	if( !ends.empty() ) {
+		std::vector<int> e2;
+		for( int v : ends ) if( v >= 1 && v < S && (e2.empty() || v > e2.back()) ) e2.push_back(v);
+		// a pass may not straddle the 16-bit limit except with its top level
+		if( std::find(e2.begin(), e2.end(), U) == e2.end() && U < S ) e2.push_back(U);
+		std::sort(e2.begin(), e2.end());
+		e2.push_back(S);
+		return build_packed_passes(P, used, S, S16, U, e2, passes);
+	}
+	// default: 16-bit passes of up to 5 steps, fp32 passes of up to 3; more,
+	// shorter passes when a program does not fit its shared memory
+	for( int extra=0; extra<4; ++extra ) {
+		ends.clear();
+		int npu = std::min(U, div_up<int>(U, 5) + extra);
+		for( int k=1; k<=npu; ++k ) ends.push_back(std::min(U, div_up<int>(U * k, npu)));
+		// (uneven splits put the longer pass first: the lowest steps are the cheapest)
+		int nf = S - U, npf = nf ? std::min(nf, div_up<int>(nf, 3) + extra) : 0;
+		for( int k=1; k<=npf; ++k ) ends.push_back(U + div_up<int>(nf * k, npf));
+		if( build_packed_passes(P, used, S, S16, U, ends, passes) ) return true;
+	}
+	return false;
+}
+
+static bool upload_packed(std::vector<PackedPass>* passes) {
+	for( PackedPass& cp : *passes ) {
 		struct { std::vector<int4>* h; int4** d; } t[3] = {{&cp.ops, &cp.d_ops}, {&cp.src, &cp.d_src}, {&cp.hdr, &cp.d_hdr}};
 		for( int i=0; i<3; ++i ) {
 			size_t bytes = t[i].h->size() * sizeof(int4);
@@ -779,17 +804,17 @@ static bool upload_chain(std::vector<ChainPass>* passes) {
 	return true;
 }
 
-struct ChainGeom { long tb, nt, te, stride; size_t offset; };
+struct PackedGeom { long tb, nt, te, stride; size_t offset; };
 
 // Time range of every pass for a gulp of `ntime` samples: the last pass covers
 // [0, ntime); pass k covers everything pass k+1 reads, starting before t = 0
 // by that pass's backward reach (samples before t = 0 are zeros, so no pass
 // needs an edge path).
-static size_t chain_geometry(std::vector<ChainPass> const& passes, long ntime, long nbatch,
-                             std::vector<ChainGeom>* geom_) {
-	std::vector<ChainGeom>& g = *geom_;
+static size_t packed_geometry(std::vector<PackedPass> const& passes, long ntime, long nbatch,
+                             std::vector<PackedGeom>* geom_) {
+	std::vector<PackedGeom>& g = *geom_;
 	const int n = (int)passes.size();
-	g.assign(n, ChainGeom());
+	g.assign(n, PackedGeom());
 	g[n-1].tb = 0;
 	g[n-1].nt = div_up<long>(ntime, passes[n-1].T);
 	g[n-1].te = g[n-1].nt * passes[n-1].T;
@@ -802,26 +827,26 @@ static size_t chain_geometry(std::vector<ChainPass> const& passes, long ntime, l
 	for( int k=0; k<n-1; ++k ) {
 		g[k].stride = round_up<long>(g[k].te - g[k].tb, 64);
 		g[k].offset = off;
-		size_t esz = (passes[k].dst_kind == CH_DST_CVT) ? 4 : passes[k].esize;
+		size_t esz = (passes[k].dst_kind == PK_DST_CVT) ? 4 : passes[k].esize;
 		off += round_up<size_t>((size_t)nbatch * passes[k].nrow_out * g[k].stride * esz, 512);
 	}
 	return std::max<size_t>(off, 512);
 }
 
-template<int ESZ, int SRCK, int DSTK, int NLMAX>
-static cudaError_t launch_chain_kernel(ChainParams const& q, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+template<int ESZ, int SRCK, int DSTK>
+static cudaError_t launch_packed_kernel(PackedParams const& q, dim3 grid, int threads, size_t smem, cudaStream_t st) {
 	static size_t attr_smem = 0;
 	if( smem > attr_smem ) {
-		cudaError_t e = cudaFuncSetAttribute(fdmt_chain_kernel<ESZ, SRCK, DSTK, NLMAX>,
+		cudaError_t e = cudaFuncSetAttribute(fdmt_packed_kernel<ESZ, SRCK, DSTK>,
 		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if( e != cudaSuccess ) return e;
 		attr_smem = smem;
 	}
-	fdmt_chain_kernel<ESZ, SRCK, DSTK, NLMAX><<<grid, threads, smem, st>>>(q);
+	fdmt_packed_kernel<ESZ, SRCK, DSTK><<<grid, threads, smem, st>>>(q);
 	return cudaGetLastError();
 }
 
-static BFstatus launch_chain_pass(ChainPass const& cp, ChainParams const& q, long nbatch, cudaStream_t st) {
+static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, long nbatch, cudaStream_t st) {
 	// CTAs walk their program's tiles with a stride: about `waves` launch waves
 	// of 2 CTAs per SM in total, so the op tables are copied to shared memory a
 	// few times per program instead of once per tile.
@@ -831,7 +856,7 @@ static BFstatus launch_chain_pass(ChainPass const& cp, ChainParams const& q, lon
 		cudaGetDevice(&dev);
 		if( cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0 ) sm_count = 148;
 	}
-	const long waves = std::max(1, env_int("BFB_FDMT_CHAIN_WAVES", 4));
+	const long waves = std::max(1, env_int("BFB_FDMT_PACKED_WAVES", 4));
 	long gx = div_up<long>(2L * sm_count * waves, (long)cp.nprog * nbatch);
 	gx = std::max<long>(1, std::min<long>(gx, q.ntile));
 	gx = div_up<long>(q.ntile, div_up<long>(q.ntile, gx));      // equal shares
@@ -839,22 +864,20 @@ static BFstatus launch_chain_pass(ChainPass const& cp, ChainParams const& q, lon
 	const int threads = cp.nwarp * 32;
 	const size_t smem = cp.smem_bytes();
 	cudaError_t e = cudaErrorInvalidValue;
-#define BFB_CH_LAUNCH(E_, S_, D_) \
-	e = cp.chains ? launch_chain_kernel<E_, S_, D_, CH_MAXLEV>(q, grid, threads, smem, st) \
-	              : launch_chain_kernel<E_, S_, D_, 0>(q, grid, threads, smem, st)
+#define BFB_CH_LAUNCH(E_, S_, D_) e = launch_packed_kernel<E_, S_, D_>(q, grid, threads, smem, st)
 	if( cp.esize == 2 ) {
-		if( cp.src_kind == CH_SRC_BYTES ) {
-			if(      cp.dst_kind == CH_DST_SAME ) BFB_CH_LAUNCH(2, CH_SRC_BYTES, CH_DST_SAME);
-			else if( cp.dst_kind == CH_DST_CVT  ) BFB_CH_LAUNCH(2, CH_SRC_BYTES, CH_DST_CVT);
-			else                                  BFB_CH_LAUNCH(2, CH_SRC_BYTES, CH_DST_FINAL);
+		if( cp.src_kind == PK_SRC_BYTES ) {
+			if(      cp.dst_kind == PK_DST_SAME ) BFB_CH_LAUNCH(2, PK_SRC_BYTES, PK_DST_SAME);
+			else if( cp.dst_kind == PK_DST_CVT  ) BFB_CH_LAUNCH(2, PK_SRC_BYTES, PK_DST_CVT);
+			else                                  BFB_CH_LAUNCH(2, PK_SRC_BYTES, PK_DST_FINAL);
 		} else {
-			if(      cp.dst_kind == CH_DST_SAME ) BFB_CH_LAUNCH(2, CH_SRC_SAME, CH_DST_SAME);
-			else if( cp.dst_kind == CH_DST_CVT  ) BFB_CH_LAUNCH(2, CH_SRC_SAME, CH_DST_CVT);
-			else                                  BFB_CH_LAUNCH(2, CH_SRC_SAME, CH_DST_FINAL);
+			if(      cp.dst_kind == PK_DST_SAME ) BFB_CH_LAUNCH(2, PK_SRC_SAME, PK_DST_SAME);
+			else if( cp.dst_kind == PK_DST_CVT  ) BFB_CH_LAUNCH(2, PK_SRC_SAME, PK_DST_CVT);
+			else                                  BFB_CH_LAUNCH(2, PK_SRC_SAME, PK_DST_FINAL);
 		}
 	} else {
-		if( cp.dst_kind == CH_DST_SAME ) BFB_CH_LAUNCH(4, CH_SRC_SAME, CH_DST_SAME);
-		else                             BFB_CH_LAUNCH(4, CH_SRC_SAME, CH_DST_FINAL);
+		if( cp.dst_kind == PK_DST_SAME ) BFB_CH_LAUNCH(4, PK_SRC_SAME, PK_DST_SAME);
+		else                             BFB_CH_LAUNCH(4, PK_SRC_SAME, PK_DST_FINAL);
 	}
 #undef BFB_CH_LAUNCH
 	BFB_CUDA(e, BF_STATUS_INTERNAL_ERROR);
@@ -862,6 +885,71 @@ static BFstatus launch_chain_pass(ChainPass const& cp, ChainParams const& q, lon
 	return BF_STATUS_SUCCESS;
 }
 
+
+// ---- persistent single-launch form -------------------------------------------
+static int mega_kind(PackedPass const& cp) {
+	return cp.esize == 2 ? cp.src_kind * 3 + cp.dst_kind : (cp.dst_kind == PK_DST_FINAL ? 7 : 6);
+}
+// Items of one round: every (pass, program, tile slot of a chunk), ordered by
+// the slot's time offset so the passes advance together (the final pass, which
+// streams the output to HBM, first among equals).
+static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int* lag_, std::vector<int>* tmpl_) {
+	if( cps.empty() || (int)cps.size() > PK_MAXPASS || env_int("BFB_FDMT_PACKED_MEGA", 0) == 0 ) return false;
+	int tmax = 0;
+	for( PackedPass const& cp : cps ) tmax = std::max(tmax, cp.T);
+	long C = std::max<long>(env_int("BFB_FDMT_PACKED_CHUNK", 2048), tmax);
+	struct Item { long key; int k, slot, prog; };
+	std::vector<Item> items;
+	for( size_t k=0; k<cps.size(); ++k ) {
+		int smax = (int)(C / cps[k].T) + 2;
+		if( smax > 31 || cps[k].nprog >= (1 << 24) ) return false;
+		for( int sl=0; sl<smax; ++sl )
+			for( int p=0; p<cps[k].nprog; ++p ) {
+				Item it = { (long)sl * cps[k].T * 16 + (long)(cps.size() - 1 - k), (int)k, sl, p };
+				items.push_back(it);
+			}
+	}
+	std::stable_sort(items.begin(), items.end(), [](Item const& a, Item const& b) { return a.key < b.key; });
+	tmpl_->resize(items.size());
+	for( size_t i=0; i<items.size(); ++i ) (*tmpl_)[i] = (items[i].k << 29) | (items[i].slot << 24) | items[i].prog;
+	*C_ = C;
+	*lag_ = 1 + (int)div_up<long>(tmax, C);
+	return true;
+}
+static bool build_mega_template(BFfdmt_impl* plan) {
+	plan->mega_ok = false;
+	std::vector<int> tmpl;
+	if( !mega_template_host(plan->packed, &plan->mega_chunk, &plan->mega_lag, &tmpl) ) return false;
+	if( cudaMalloc((void**)&plan->d_mega_tmpl, tmpl.size() * sizeof(int)) != cudaSuccess ) return false;
+	if( cudaMemcpy(plan->d_mega_tmpl, tmpl.data(), tmpl.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ) return false;
+	plan->mega_ipr = (int)tmpl.size();
+	plan->mega_ok = true;
+	return true;
+}
+
+struct MegaGeom { long ring[PK_MAXPASS]; size_t offset[PK_MAXPASS]; int nchunk; };
+
+// Ring lengths of the workspaces between the passes and the bytes they take.
+static size_t mega_geometry(std::vector<PackedPass> const& cps, long C, int lag,
+                            std::vector<PackedGeom> const& geom, MegaGeom* mg) {
+	const int n = (int)cps.size();
+	int tmax = 0, lbmax = 0;
+	for( PackedPass const& cp : cps ) { tmax = std::max(tmax, cp.T); lbmax = std::max(lbmax, cp.lookback); }
+	// a writer must find its readers claimed in an earlier round (fdmt_packed.cuh)
+	const long want = C * (lag + div_up<long>(tmax + lbmax, C) + 1 + std::max(0, env_int("BFB_FDMT_PACKED_RING_EXTRA", 0)));
+	long te = 0;
+	for( int k=0; k<n; ++k ) te = std::max(te, geom[k].te);
+	mg->nchunk = (int)div_up<long>(te - geom[0].tb, C);
+	size_t off = 0;
+	for( int k=0; k<n-1; ++k ) {
+		long width = geom[k].te - geom[k].tb;
+		mg->ring[k] = round_up<long>(std::min(width, want), 64);
+		mg->offset[k] = off;
+		size_t esz = (cps[k].dst_kind == PK_DST_CVT) ? 4 : cps[k].esize;
+		off += round_up<size_t>((size_t)cps[k].nrow_out * mg->ring[k] * esz, 512);
+	}
+	return std::max<size_t>(off, 512);
+}
 extern "C" {
 
 BFstatus bfFdmtCreate(BFfdmt* plan_ptr) {
@@ -965,16 +1053,17 @@ BFstatus bfFdmtInit(BFfdmt plan, BFsize nchan, BFsize max_delay,
 	BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
 	BFB_TRY(build_tail_passes(plan));
 	BFB_TRY({
-		std::vector<ChainPass> cps;
-		if( build_chain_schedule(P, &cps) ) {
-			plan->chain.swap(cps);
-			if( !upload_chain(&plan->chain) ) {
-				for( ChainPass& cp : plan->chain ) {
+		std::vector<PackedPass> cps;
+		if( build_packed_schedule(P, &cps) ) {
+			plan->packed.swap(cps);
+			if( upload_packed(&plan->packed) ) build_mega_template(plan);
+			else {
+				for( PackedPass& cp : plan->packed ) {
 					if( cp.d_ops ) cudaFree(cp.d_ops);
 					if( cp.d_src ) cudaFree(cp.d_src);
 					if( cp.d_hdr ) cudaFree(cp.d_hdr);
 				}
-				plan->chain.clear();
+				plan->packed.clear();
 			}
 		}
 	});
@@ -1001,10 +1090,10 @@ BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	return BF_STATUS_SUCCESS;
 }
 
-// Test hook: the tables of pass `pass` of the integer chain schedule
+// Test hook: the tables of pass `pass` of the packed-integer schedule
 // (pass < 0: only header[0] = number of passes, 0 when the schedule does not
-// apply).  tests/test_fdmt_chain_cpu.py interprets them with numpy.
-BFstatus bfFdmtChainQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+// apply).  tests/test_fdmt_packed_cpu.py interprets them with numpy.
+BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                           double exponent, int pass, int* header,
                           int* ops, int* src, int* hdr) {
 	BFB_ASSERT(header, BF_STATUS_INVALID_POINTER);
@@ -1013,18 +1102,49 @@ BFstatus bfFdmtChainQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	bool ok = false;
 	BFB_TRY(ok = P.build((int)nchan, (int)max_delay, f0, df, exponent));
 	BFB_ASSERT(ok, BF_STATUS_INTERNAL_ERROR);
-	std::vector<ChainPass> cps;
-	BFB_TRY(ok = build_chain_schedule(P, &cps));
+	std::vector<PackedPass> cps;
+	BFB_TRY(ok = build_packed_schedule(P, &cps));
 	if( pass < 0 ) { header[0] = ok ? (int)cps.size() : 0; return BF_STATUS_SUCCESS; }
 	BFB_ASSERT(ok && pass < (int)cps.size(), BF_STATUS_INVALID_ARGUMENT);
-	ChainPass const& cp = cps[pass];
+	PackedPass const& cp = cps[pass];
 	int h[16] = { cp.s0, cp.s1, cp.nlev, cp.esize, cp.src_kind, cp.dst_kind, cp.T, cp.nprog,
-	              cp.nwarp, cp.slots, cp.src_slots, cp.smem_elems, cp.lookback, cp.nrow_out,
+	              cp.nwarp, cp.slots, cp.src_slots, cp.data_bytes, cp.lookback, cp.nrow_out,
 	              (int)cp.smem_bytes(), (int)std::min<long>(cp.nops, 1L << 30) };
 	memcpy(header, h, sizeof(h));
 	if( ops ) memcpy(ops, cp.ops.data(), cp.ops.size() * sizeof(int4));
 	if( src ) memcpy(src, cp.src.data(), cp.src.size() * sizeof(int4));
 	if( hdr ) memcpy(hdr, cp.hdr.data(), cp.hdr.size() * sizeof(int4));
+	return BF_STATUS_SUCCESS;
+}
+
+// Test hook: geometry of the persistent single-launch form for a gulp of
+// `ntime` samples.  header[0] = 0 when it does not apply, else header =
+// {1, npass, lag, ipr, nchunk, C, t_ref, then per pass: tb, nt, ring length
+// of its output workspace (0 for the last pass)}; tmpl (may be NULL) receives
+// ipr ints.
+BFstatus bfFdmtPackedMegaQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+                              double exponent, long ntime, long* header, int* tmpl) {
+	BFB_ASSERT(header, BF_STATUS_INVALID_POINTER);
+	FdmtPlan P;
+	bool ok = false;
+	BFB_TRY(ok = P.build((int)nchan, (int)max_delay, f0, df, exponent));
+	BFB_ASSERT(ok, BF_STATUS_INTERNAL_ERROR);
+	std::vector<PackedPass> cps;
+	std::vector<int> t;
+	long C = 0; int lag = 0;
+	header[0] = 0;
+	BFB_TRY(ok = build_packed_schedule(P, &cps) && mega_template_host(cps, &C, &lag, &t));
+	if( !ok ) return BF_STATUS_SUCCESS;
+	std::vector<PackedGeom> geom;
+	MegaGeom mg;
+	BFB_TRY(packed_geometry(cps, ntime, 1, &geom); mega_geometry(cps, C, lag, geom, &mg));
+	header[0] = 1; header[1] = (long)cps.size(); header[2] = lag; header[3] = (long)t.size();
+	header[4] = mg.nchunk; header[5] = C; header[6] = geom[0].tb;
+	for( size_t k=0; k<cps.size(); ++k ) {
+		header[7 + 3*k] = geom[k].tb; header[8 + 3*k] = geom[k].nt;
+		header[9 + 3*k] = (k + 1 < cps.size()) ? mg.ring[k] : 0;
+	}
+	if( tmpl ) memcpy(tmpl, t.data(), t.size() * sizeof(int));
 	return BF_STATUS_SUCCESS;
 }
 
@@ -1186,11 +1306,16 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	int  nbuf = fused ? 3 : 2;
 	size_t need = (size_t)nbuf * (size_t)nbatch * sbatchstride * sizeof(float);
 	if( need == 0 ) need = 512;
-	// 1-byte inputs take the integer chain schedule (its own, smaller workspace)
-	const bool use_chain = !plan->chain.empty() && !negative_delays && !plan->cfg_force_v1 &&
+	// 1-byte inputs take the packed-integer schedule (its own, smaller workspace)
+	const bool use_packed = !plan->packed.empty() && !negative_delays && !plan->cfg_force_v1 &&
 	                       (in->dtype == BF_DTYPE_I8 || in->dtype == BF_DTYPE_U8);
-	std::vector<ChainGeom> geom;
-	if( use_chain ) { BFB_TRY(need = chain_geometry(plan->chain, ntime, nbatch, &geom)); }
+	std::vector<PackedGeom> geom;
+	MegaGeom mgeom;
+	const bool use_mega = use_packed && plan->mega_ok;
+	if( use_packed ) {
+		BFB_TRY(need = packed_geometry(plan->packed, ntime, nbatch, &geom));
+		if( use_mega ) { BFB_TRY(need = mega_geometry(plan->packed, plan->mega_chunk, plan->mega_lag, geom, &mgeom)); }
+	}
 	if( exec_storage_size ) {
 		if( !exec_storage ) { *exec_storage_size = need; return BF_STATUS_SUCCESS; }
 		BFB_ASSERT(*exec_storage_size >= need, BF_STATUS_INSUFFICIENT_STORAGE);
@@ -1222,17 +1347,81 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	long istride = in->strides[ndim-2] / isize,  ibatch = ibatchbytes / isize;
 	long ostride = out->strides[ndim-2] / 4,     obatch = obatchbytes / 4;
 
-	if( use_chain ) {
+	if( use_mega ) {
+		// one persistent launch per batch entry; the ring workspaces are shared
 		cudaStream_t cst = plan->get_stream();
 		char* ws = (char*)exec_storage;
-		const int npass = (int)plan->chain.size();
+		const int npass = (int)plan->packed.size();
+		const size_t ncount = 2 + (size_t)npass * mgeom.nchunk;
+		if( plan->mega_counters_cap < ncount ) {
+			if( plan->d_mega_counters ) cudaFree(plan->d_mega_counters);
+			plan->d_mega_counters = nullptr; plan->mega_counters_cap = 0;
+			BFB_CUDA(cudaMalloc((void**)&plan->d_mega_counters, ncount * sizeof(int)), BF_STATUS_MEM_ALLOC_FAILED);
+			BFB_CUDA(cudaMemset(plan->d_mega_counters, 0, ncount * sizeof(int)), BF_STATUS_MEM_OP_FAILED);
+			plan->mega_counters_cap = ncount;
+		}
+		static int mega_blocks_per_sm = 0, mega_sms = 0;
+		static size_t mega_attr_smem = 0;
+		size_t smem = 0;
+		for( PackedPass const& cp : plan->packed ) smem = std::max(smem, cp.smem_bytes());
+		if( smem > mega_attr_smem ) {
+			BFB_CUDA(cudaFuncSetAttribute(fdmt_packed_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+			         BF_STATUS_INTERNAL_ERROR);
+			mega_attr_smem = smem;
+			mega_blocks_per_sm = 0;
+		}
+		if( !mega_blocks_per_sm ) {
+			int dev = 0;
+			cudaGetDevice(&dev);
+			BFB_CUDA(cudaDeviceGetAttribute(&mega_sms, cudaDevAttrMultiProcessorCount, dev), BF_STATUS_INTERNAL_ERROR);
+			BFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mega_blocks_per_sm, fdmt_packed_mega_kernel, 256, smem),
+			         BF_STATUS_INTERNAL_ERROR);
+			BFB_ASSERT(mega_blocks_per_sm >= 1, BF_STATUS_INTERNAL_ERROR);
+		}
+		for( long b=0; b<nbatch; ++b ) {
+			MegaParams M;
+			memset(&M, 0, sizeof(M));
+			M.npass = npass; M.lag = plan->mega_lag; M.nchunk = mgeom.nchunk; M.ipr = plan->mega_ipr;
+			M.t_ref = geom[0].tb; M.C = plan->mega_chunk;
+			M.total = (long)(mgeom.nchunk + (long)plan->mega_lag * (npass - 1)) * plan->mega_ipr;
+			M.tmpl = plan->d_mega_tmpl; M.counters = plan->d_mega_counters;
+			for( int k=0; k<npass; ++k ) {
+				PackedPass const& cp = plan->packed[k];
+				MegaPass& mp = M.pass[k];
+				PackedParams& q = mp.p;
+				if( k > 0 ) {
+					q.src = ws + mgeom.offset[k-1]; q.sstride = mgeom.ring[k-1]; q.src_tb = geom[k-1].tb; q.src_rl = mgeom.ring[k-1];
+				} else q.src_rl = 1;
+				if( k == npass - 1 ) {
+					q.dst = (float*)out->data + b * obatch; q.dstride = ostride; q.dst_tb = 0; q.dst_rl = 1L << 62;
+				} else {
+					q.dst = ws + mgeom.offset[k]; q.dstride = mgeom.ring[k]; q.dst_tb = geom[k].tb; q.dst_rl = mgeom.ring[k];
+				}
+				q.ops = cp.d_ops; q.srcs = cp.d_src; q.hdr = cp.d_hdr;
+				q.raw = (const char*)in->data + b * ibatch * isize; q.rstride = istride;
+				q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
+				q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
+				q.is_signed = (in->dtype == BF_DTYPE_I8);
+				mp.kind = mega_kind(cp); mp.nprog = cp.nprog; mp.lookback = cp.lookback; mp.nt = geom[k].nt;
+			}
+			long grid = std::min<long>(M.total, (long)mega_blocks_per_sm * mega_sms);
+			fdmt_packed_mega_kernel<<<(unsigned)grid, 256, smem, cst>>>(M);
+			count_launch();
+		}
+		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+		return BF_STATUS_SUCCESS;
+	}
+	if( use_packed ) {
+		cudaStream_t cst = plan->get_stream();
+		char* ws = (char*)exec_storage;
+		const int npass = (int)plan->packed.size();
 		for( int k=0; k<npass; ++k ) {
-			ChainPass const& cp = plan->chain[k];
-			ChainParams q;
+			PackedPass const& cp = plan->packed[k];
+			PackedParams q;
 			memset(&q, 0, sizeof(q));
 			if( k > 0 ) {
 				q.src = ws + geom[k-1].offset; q.sstride = geom[k-1].stride;
-				q.sbatch = (long)plan->chain[k-1].nrow_out * geom[k-1].stride; q.src_tb = geom[k-1].tb;
+				q.sbatch = (long)plan->packed[k-1].nrow_out * geom[k-1].stride; q.src_tb = geom[k-1].tb;
 			}
 			if( k == npass - 1 ) { q.dst = out->data; q.dstride = ostride; q.dbatch = obatch; q.dst_tb = 0; }
 			else {
@@ -1244,7 +1433,9 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 			q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
 			q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
 			q.is_signed = (in->dtype == BF_DTYPE_I8);
-			BFstatus ls = launch_chain_pass(cp, q, nbatch, cst);
+			q.src_rl = k > 0 ? geom[k-1].stride : 1;           // linear workspaces: the rings never wrap
+			q.dst_rl = k == npass - 1 ? (1L << 62) : geom[k].stride;
+			BFstatus ls = launch_packed_pass(cp, q, nbatch, cst);
 			if( ls != BF_STATUS_SUCCESS ) return ls;
 		}
 		return BF_STATUS_SUCCESS;

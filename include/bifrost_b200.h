@@ -328,16 +328,25 @@ BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                          int raw, int* header, int* items, int* aux);
 
 /* B200 extension (test hook, host only): the tables of pass `pass` of the
- * integer "chain" FDMT schedule that bfFdmtExecute runs for 1-byte inputs --
- * see csrc/fdmt_chain.cuh for the op layout.  pass < 0: header[0] = number of
+ * packed-integer FDMT schedule that bfFdmtExecute runs for 1-byte inputs --
+ * see csrc/fdmt_packed.cuh for the op layout.  pass < 0: header[0] = number of
  * passes (0: the schedule does not apply to this plan).  Otherwise
  * header[16] = {s0, s1, nlev, esize, src_kind, dst_kind, T, nprog, nwarp,
- * slots, src_slots, smem_elems, lookback, nrow_out, smem_bytes, nops};
+ * slots, src_slots, data_bytes, lookback, nrow_out, smem_bytes, nops};
  * ops receives 4*nprog*nlev*nwarp*slots ints, src 4*nprog*src_slots ints,
  * hdr 4*nprog ints (each may be NULL). */
-BFstatus bfFdmtChainQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                           double exponent, int pass, int* header,
                           int* ops, int* src, int* hdr);
+
+/* B200 extension (test hook, host only): geometry of the persistent
+ * single-launch form of the packed-integer schedule for a gulp of `ntime` samples.
+ * header[0] = 0 when it does not apply, else header = {1, npass, lag, ipr,
+ * nchunk, C, t_ref, then per pass: tb, nt, ring length of its output workspace
+ * (0 for the last pass)} (7 + 3*npass longs; pass 32); tmpl (may be NULL)
+ * receives ipr ints: pass << 29 | tile slot in chunk << 24 | program. */
+BFstatus bfFdmtPackedMegaQuery(BFsize nchan, BFsize max_delay, double f0, double df,
+                              double exponent, long ntime, long* header, int* tmpl);
 
 /* Number of kernels this library has launched since load (all threads). */
 BFstatus bfGetLaunchCount(unsigned long long* count);

@@ -118,7 +118,7 @@ def test_reference_smoke_semantics(ntime, nchan, md, batch):
     assert_same_bits(o1, want)
 
 
-_OLD = dict(BFB_FDMT_CHAIN='0')     # the float schedules: switch the integer chain schedule off
+_OLD = dict(BFB_FDMT_PACKED='0')     # the float schedules: switch the packed-integer schedule off
 
 
 @pytest.mark.gpu
@@ -131,15 +131,19 @@ _OLD = dict(BFB_FDMT_CHAIN='0')     # the float schedules: switch the integer ch
                                   dict(_OLD, BFB_FDMT_TILE_D='64', BFB_FDMT_TILES_PER_CTA='3'),
                                   dict(_OLD, BFB_FDMT_K='3', BFB_FDMT_TILE_THREADS='128'),
                                   dict(_OLD, BFB_FDMT_K='1', BFB_FDMT_SPLIT='2,3,5,8'),
-                                  # integer chain schedule (fdmt_chain.cuh): default and reshaped
-                                  dict(), dict(BFB_FDMT_CHAIN_SPLIT='3,6'), dict(BFB_FDMT_CHAIN_SPLIT='2,4,6,8'),
-                                  dict(BFB_FDMT_CHAIN_D='8,8,8', BFB_FDMT_CHAIN_JR='2,3,1'),
-                                  dict(BFB_FDMT_CHAIN_WARPS='4,2,1', BFB_FDMT_CHAIN_JR='16,16,16'),
-                                  dict(BFB_FDMT_CHAIN_TCAP='128,200,64', BFB_FDMT_CHAIN_D='5,100,7')])
+                                  # packed-integer schedule (fdmt_packed.cuh): default and reshaped,
+                                  # pass per launch and as the one persistent kernel
+                                  dict(), dict(BFB_FDMT_PACKED_SPLIT='3,6'), dict(BFB_FDMT_PACKED_SPLIT='2,4,6,8'),
+                                  dict(BFB_FDMT_PACKED_D='8,8,8', BFB_FDMT_PACKED_SMEM_KB='100,50,40'),
+                                  dict(BFB_FDMT_PACKED_WARPS='4,2,1'),
+                                  dict(BFB_FDMT_PACKED_TCAP='128,200,64', BFB_FDMT_PACKED_D='5,100,7'),
+                                  dict(BFB_FDMT_PACKED_MEGA='1'),
+                                  dict(BFB_FDMT_PACKED_MEGA='1', BFB_FDMT_PACKED_CHUNK='300', BFB_FDMT_PACKED_TCAP='128,96,64'),
+                                  dict(BFB_FDMT_PACKED_MEGA='1', BFB_FDMT_PACKED_SPLIT='2,4,6,8', BFB_FDMT_PACKED_CHUNK='1000')])
 def test_every_schedule_gives_the_same_bits(knob):
     """The step-by-step schedule (v1), the fused head + row-blocked tail (v2),
-    the shared-memory tile passes (fdmt_tiles.cuh) and the integer chain
-    schedule (default for 1-byte inputs; fdmt_chain.cuh) at several split
+    the shared-memory tile passes (fdmt_tiles.cuh) and the packed-integer
+    schedule (default for 1-byte inputs; fdmt_packed.cuh) at several split
     levels / block sizes must agree bit for bit with the oracle."""
     rng = np.random.default_rng(21)
     old = {k: os.environ.get(k) for k in knob}

@@ -1,0 +1,232 @@
+"""CPU check of the packed-integer FDMT schedule (csrc/fdmt_packed.cuh).
+
+bfFdmtPackedQuery returns the very tables bfFdmtExecute uploads for 1-byte
+inputs; this file interprets them with numpy -- staging, per-warp register
+rows, shared-memory rows, workspaces, bias removal, diagonal store -- and
+compares the result with the oracle bit for bit.  Shared memory and the
+workspaces start out poisoned, so an op that reads a sample no earlier op (or
+staging) wrote shows up as a wrong output.  No GPU needed.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from bifrost_b200.libbifrost import _bf
+from oracle import fdmt as ofdmt
+
+NO_A, NO_B, STORE_G, BYTES = 1, 2, 4, 8
+WO_SHIFT, H_SHIFT, NVEC_SHIFT = 8, 10, 16
+POISON = -(1 << 40)
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def query(nchan, md, f0, df):
+    hdr = np.zeros(16, np.int32)
+    assert _bf.bfFdmtPackedQuery(nchan, md, f0, df, -2.0, -1, _ip(hdr), None, None, None) == 0
+    passes = []
+    for k in range(int(hdr[0])):
+        h = np.zeros(16, np.int32)
+        assert _bf.bfFdmtPackedQuery(nchan, md, f0, df, -2.0, k, _ip(h), None, None, None) == 0
+        keys = ('s0 s1 nlev esize src_kind dst_kind T nprog nwarp slots src_slots data_bytes '
+                'lookback nrow_out smem_bytes nops').split()
+        p = dict(zip(keys, (int(v) for v in h)))
+        ops = np.zeros((p['nprog'], p['nlev'], p['nwarp'], p['slots'], 4), np.int32)
+        src = np.zeros((p['nprog'], p['src_slots'], 4), np.int32)
+        ph = np.zeros((p['nprog'], 4), np.int32)
+        assert _bf.bfFdmtPackedQuery(nchan, md, f0, df, -2.0, k, _ip(h), _ip(ops), _ip(src), _ip(ph)) == 0
+        p.update(ops=ops, src=src, hdr=ph)
+        passes.append(p)
+    return passes
+
+
+def geometry(passes, ntime):
+    n = len(passes)
+    g = [dict() for _ in range(n)]
+    g[-1]['tb'] = 0
+    g[-1]['nt'] = -(-ntime // passes[-1]['T'])
+    g[-1]['te'] = g[-1]['nt'] * passes[-1]['T']
+    for k in range(n - 2, -1, -1):
+        g[k]['tb'] = -((passes[k + 1]['lookback'] - g[k + 1]['tb'] + 7) // 8 * 8)
+        g[k]['nt'] = -(-(g[k + 1]['te'] - g[k]['tb']) // passes[k]['T'])
+        g[k]['te'] = g[k]['tb'] + g[k]['nt'] * passes[k]['T']
+    return g
+
+
+class Machine(object):
+    """State of one pass: interprets a (program, tile) exactly as the kernel
+    does -- shared memory is a byte-addressed array of elements (one int64 /
+    float64 cell per element, POISON / NaN where nothing was written)."""
+
+    def __init__(self, p, g, x, xi, signed, ws_prev, tb_prev, ring_prev, ws, ring, out):
+        self.p, self.g, self.x, self.xi, self.signed = p, g, x, xi, signed
+        self.ws_prev, self.tb_prev, self.ring_prev = ws_prev, tb_prev, ring_prev
+        self.ws, self.ring, self.out = ws, ring, out
+        self.ntime = x.shape[1]
+
+    def run(self, prog, tile):
+        p, g, ntime, signed = self.p, self.g, self.ntime, self.signed
+        esz = p['esize']
+        VS = 16 // esz
+        final = p['dst_kind'] == 2
+        nchan_band, nsrc, staged, _ = (int(v) for v in p['hdr'][prog])
+        bias = 128 * nchan_band if signed else 0
+        t0 = g['tb'] + tile * p['T']
+        nelem = p['data_bytes']          # one cell per BYTE offset keeps byte and word rows in one array
+        data = np.full(nelem, POISON, np.int64) if esz == 2 else np.full(nelem, np.nan, np.float64)
+        srcs = p['src'][prog]
+        nbytes = 0
+        for e in srcs[:nsrc]:
+            row, y, z, w = (int(v) for v in e)
+            assert w > 0 and w % VS == 0 and z % 16 == 0
+            ts = t0 + y
+            if p['src_kind'] == 0:
+                t = np.arange(ts, ts + w)
+                ok = (t >= 0) & (t < ntime)
+                vals = np.full(w, 128 if signed else 0, np.int64)
+                vals[ok] = self.xi[row, t[ok]]
+                data[z:z + w] = vals                       # one byte per cell, misalignment 0 in this model
+            else:
+                c0 = ts - self.tb_prev
+                assert c0 >= 0 and c0 % VS == 0 and c0 + w <= self.ws_prev_width
+                cols = (c0 + np.arange(w)) % self.ring_prev
+                vals = self.ws_prev[row, cols]
+                data[z:z + w * esz:esz] = vals
+                nbytes += w * esz
+        if p['src_kind'] != 0:
+            assert nbytes == staged
+        if nsrc < p['src_slots']:
+            assert srcs[nsrc][3] == 0
+        for lev in range(1, p['nlev'] + 1):
+            for warp in range(p['nwarp']):
+                for op in p['ops'][prog, lev - 1, warp]:
+                    dst, ay, bz, ctl = (int(v) for v in op)
+                    if ctl == 0:
+                        break
+                    n = (ctl >> NVEC_SHIFT) * VS
+                    assert n <= 32 * 3 * VS
+                    if ctl & BYTES:
+                        assert p['src_kind'] == 0 and lev == 1
+                        def rd(field):
+                            k, e = field & 0xFFF, (field & 0xFFFFFFFF) >> 12
+                            assert k < nsrc
+                            base = int(srcs[k][2])
+                            assert e + n <= int(srcs[k][3])
+                            return data[base + e: base + e + n]
+                        a = np.zeros(n, np.int64) if ctl & NO_A else rd(ay)
+                        b = np.zeros(n, np.int64) if ctl & NO_B else rd(bz)
+                    else:
+                        sub = ((ctl >> WO_SHIFT) & 3) * (4 // esz) + ((ctl >> H_SHIFT) & 1)
+                        if esz == 4:
+                            assert (ctl >> H_SHIFT) & 1 == 0
+                        assert ay % 16 == 0 and bz % 16 == 0
+                        a = np.zeros(n, data.dtype) if ctl & NO_A else data[ay: ay + n * esz: esz]
+                        b = np.zeros(n, data.dtype) if ctl & NO_B else data[bz + sub * esz: bz + (sub + n) * esz: esz]
+                    if esz == 4:
+                        r = (a.astype(np.float32) + b.astype(np.float32)).astype(np.float64)
+                    else:
+                        r = a + b
+                    if not (ctl & STORE_G):
+                        assert dst % 16 == 0 and lev < p['nlev']
+                        if esz == 2:
+                            assert (r >= 0).all() and (r < 65536).all()
+                        data[dst: dst + n * esz: esz] = r
+                        continue
+                    assert n == p['T'] and lev == p['nlev']
+                    if esz == 2:
+                        assert (r >= 0).all()
+                        if p['dst_kind'] == 0:
+                            assert (r < 65536).all()
+                            val = r
+                        else:
+                            val = (r - bias).astype(np.float64)
+                    else:
+                        val = r
+                    if final:
+                        d = dst
+                        t = np.arange(t0, t0 + n)
+                        ok = (t >= d) & (t < ntime)
+                        assert not np.isnan(val[ok]).any()
+                        self.out[d, t[ok] - d] = val[ok].astype(np.float32)
+                    else:
+                        cols = (t0 - g['tb'] + np.arange(n)) % self.ring
+                        self.ws[dst, cols] = val
+
+
+def run_schedule(x, passes, out):
+    """x [nchan, ntime] int8/uint8 -> writes out [max_delay, ntime] float32,
+    pass by pass over linear workspaces (the separate-launch form)."""
+    nchan, ntime = x.shape
+    signed = x.dtype == np.int8
+    geo = geometry(passes, ntime)
+    xi = x.astype(np.int64) + (128 if signed else 0)
+    ws_prev, tb_prev, width_prev = None, 0, 0
+    for k, p in enumerate(passes):
+        g = geo[k]
+        width = g['te'] - g['tb']
+        is_float = p['dst_kind'] == 1 or p['esize'] == 4
+        ws = None
+        if p['dst_kind'] != 2:
+            ws = np.full((p['nrow_out'], width), np.nan if is_float else POISON, np.float64 if is_float else np.int64)
+        m = Machine(p, g, x, xi, signed, ws_prev, tb_prev, max(width_prev, 1), ws, max(width, 1), out)
+        m.ws_prev_width = width_prev
+        for prog in range(p['nprog']):
+            for tile in range(g['nt']):
+                m.run(prog, tile)
+        ws_prev, tb_prev, width_prev = ws, g['tb'], width
+    return out
+
+
+CASES = [
+    # nchan, max_delay, f0, df, ntime, dtype
+    (16, 12, 1000.0, 10.0, 300, np.int8),
+    (17, 9, 60.0, -0.5, 257, np.uint8),          # odd channel count, reversed band
+    (64, 50, 1200.0, 3.0, 1500, np.int8),
+    (100, 37, 400.0, 0.25, 900, np.uint8),
+    (256, 130, 1000.0, 1.5, 1100, np.int8),
+    (1024, 300, 1000.0, 400. / 1024, 800, np.int8),   # crosses the 16-bit limit (steps 9, 10 in fp32)
+]
+
+
+@pytest.mark.parametrize("nchan,md,f0,df,ntime,dtype", CASES)
+def test_packed_tables_reproduce_the_oracle(nchan, md, f0, df, ntime, dtype):
+    passes = query(nchan, md, f0, df)
+    if not passes:
+        pytest.skip("integer schedule does not apply to this plan")
+    rng = np.random.default_rng(nchan * 7 + md)
+    info = np.iinfo(dtype)
+    x = rng.integers(info.min, info.max + 1, size=(nchan, ntime)).astype(dtype)
+    x[:, :5] = info.min          # extremes next to the t < 0 edge
+    x[::3, 7:40] = info.max
+    gold = np.full((md, ntime), -12345.0, np.float32)
+    ofdmt.fdmt(x, md, f0, df, out=gold)
+    got = np.full((md, ntime), -12345.0, np.float32)
+    run_schedule(x, passes, got)
+    assert np.array_equal(got.view(np.uint32), gold.view(np.uint32))
+
+
+def test_packed_schedule_of_the_baseline_plan():
+    """Config 2's plan (4096 chan, max_delay 794): structure + one short gulp."""
+    nchan, md, f0, df = 4096, 794, 1000.0, 400. / 4096
+    passes = query(nchan, md, f0, df)
+    assert [(p['s0'], p['s1'], p['esize']) for p in passes] == [(1, 5, 2), (6, 9, 2), (10, 12, 4)]
+    assert passes[0]['src_kind'] == 0 and passes[1]['dst_kind'] == 1 and passes[2]['dst_kind'] == 2
+    for p in passes:
+        assert p['smem_bytes'] <= 75 * 1024 and p['T'] >= 256      # three CTAs per SM
+    ntime = 1200
+    rng = np.random.default_rng(5)
+    x = rng.integers(-128, 128, size=(nchan, ntime)).astype(np.int8)
+    gold = np.zeros((md, ntime), np.float32)
+    ofdmt.fdmt(x, md, f0, df, out=gold)
+    got = np.zeros((md, ntime), np.float32)
+    run_schedule(x, passes, got)
+    assert np.array_equal(got.view(np.uint32), gold.view(np.uint32))
+
+
+def test_plans_beyond_exact_fp32_integers_keep_the_float_schedule():
+    # 255 * nchan must stay below 2**24 for the integer argument to hold
+    assert query(70000, 8, 1000.0, 0.001) == []
+    assert query(65536, 8, 1000.0, 0.001) != []
