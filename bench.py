@@ -1,23 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native Bifrost hot path.
 
-Metric (BASELINE.json): Msamples/s through the FDMT on a synthetic 4096-chan
-int8 filterbank (config 2: max_dm=100 -> max_delay=794, 131072 output samples
-per gulp), plus % of the HBM roofline.  One "step" = one gulp through
-bfFdmtExecute.  `value` is timed with the input resident in HBM; `e2e` is the
-same call made from HOST buffers (pinned) with the H2D copy of the gulp and
-the D2H read of the dispersion bank inside the timed region.  The second half
-of the metric (FFT -> detect -> reduce -> accumulate on the ci8 GUPPI gulp,
-config 3) is reported in the `chain` object (one fused kernel).
+Metric (BASELINE.json): Msamples/s through FDMT + FFT->detect->reduce on a
+4096-chan ci8/int8 stream, and % of the HBM roofline.
+
+  N = 1  (BASELINE config 2)  one "step" = one gulp of 4096 chan x 131072(+794)
+         int8 samples through bfFdmtExecute (max_dm = 100 -> max_delay = 794).
+         `value`: input resident in HBM, CUDA events on the launching stream.
+         `e2e`:   the same call from pinned HOST buffers, H2D of the gulp and D2H
+                  of the dispersion bank inside the timed region.
+         `roofline`: algorithmic bytes / time / measured HBM peak; `traffic` is
+                  measured in this run (a short ncu child process of this file).
+         `chain`: the second half of the metric (config 3, fused GUPPI
+                  spectrometer) with its own roofline object.
+         `gpu_reference`: the reference's own CUDA kernels (oracle/_ref) timed on
+                  the same box -- the "kernel to beat".
+         `parity`: the timed gulp's output value-checked against the C oracle.
+  N > 1  (BASELINE config 5, under torchrun)  STRONG scaling of that one gulp:
+         rank 0 holds the 4096-chan gulp, NCCL scatters 4096/N-chan sub-bands,
+         every rank runs bfFdmtInit(4096/N, max_delay_g, f0_g, df) + execute,
+         NCCL gathers the [max_delay_g, ntime] banks to rank 0.  time = max over
+         ranks including both collectives.  `replicas` keeps the weak-scaling
+         figure (every rank its own full 4096-chan gulp, no collective).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1 (under torchrun): rank g processes its own 4096-channel sub-band (weak
-scaling, no data-path collective -- SURVEY 8e); time = max over ranks.
 `--impl reference` times the CPU restatement of the reference algorithm
-(oracle/) on the host cores of this box on a bounded sample of the workload.
-`--dry-run` exercises the multi-rank host logic (sharding, barrier, max over
-ranks) on the gloo backend with no GPU work (tests/test_bench_cpu.py).
+(oracle/fdmt_c.c, all host threads) on a bounded sample of the same gulp.
+`--dry-run` exercises the multi-rank host logic on gloo with no GPU work.
 """
 import argparse
 import json
@@ -51,10 +61,21 @@ def max_delay_for(f0, df, nchan, dt, max_dm):
 
 
 def workload(rank=0):
+    """Replica workload: rank r's own 4096-channel band above the previous one."""
     df = BW_MHZ / NCHAN
     f0 = F0_MHZ + rank * NCHAN * df
     md = max_delay_for(F0_MHZ, df, NCHAN, DT_S, MAX_DM)      # same bank depth on every rank
     return dict(nchan=NCHAN, ntime=NTIME_OUT + md, max_delay=md, f0=f0, df=df)
+
+
+def subband(g, n):
+    """Config 5: sub-band g of n of the one 4096-chan gulp, with the header a
+    reference pipeline reading that sub-band file would carry."""
+    w = workload(0)
+    nc = NCHAN // n
+    f0 = w['f0'] + g * nc * w['df']
+    md = max_delay_for(f0, w['df'], nc, DT_S, MAX_DM)
+    return dict(nchan=nc, chan0=g * nc, ntime=w['ntime'], max_delay=md, f0=f0, df=w['df'])
 
 
 def make_input(w, seed, ntime=None):
@@ -144,6 +165,30 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), 'fallback'
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process (and the pinned host pages it allocates afterwards,
+    first touch) to the CPUs of the NUMA node the GPU hangs off."""
+    try:
+        bus = subprocess.run(['nvidia-smi', '-i', str(index), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith('0000'):
+            bus = bus[4:]                                   # sysfs uses a 4-digit domain
+        node = int(open(f'/sys/bus/pci/devices/{bus}/numa_node').read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return dict(numa_node=node, cpus=len(cpus))
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------- CPU arm
 def cpu_fdmt_sample(w, ntime_sample, threads=None):
     """Times the oracle (CPU restatement of the reference algorithm) on a
@@ -177,6 +222,10 @@ def cpu_fdmt_sample(w, ntime_sample, threads=None):
 
 
 def run_reference_arm(args, rank, world):
+    """The reference has no CPU implementation of this path; its algorithm
+    restated in C (oracle/fdmt_c.c) runs on all host threads of this box.  The
+    workload is the one gulp of config 2 / config 5 whatever N is (the GPU arm
+    scales strongly), so rank 0 alone runs it."""
     if rank != 0:
         return
     w = workload(0)
@@ -193,10 +242,11 @@ def run_reference_arm(args, rank, world):
               f"(1/{NTIME_OUT // ntime_sample} of the gulp) per step, {cores} threads")
     line = dict(impl='reference', metric=METRIC, value=value, unit='Msamples/s', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=float(np.mean(secs) * 1e3),
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic',
+                higher_is_better=True, scaling='strong' if args.gpus > 1 else 'weak', vs_baseline=None,
+                dtype='f32', data='synthetic',
                 config=dict(workload='BASELINE config 2: FDMT max_dm=100 on 4096-chan x 128k-sample '
-                                     'int8 filterbank (bounded sample, see cpu_baseline.sample)'),
+                                     'int8 filterbank (bounded sample, see cpu_baseline.sample); the same one '
+                                     'gulp at every N (the GPU arm scales strongly), CPU threads do not grow with N'),
                 cpu_baseline=dict(value=value, unit='Msamples/s', cores=cores, kind='port',
                                   sample=sample),
                 e2e=dict(value=value, unit='Msamples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -205,26 +255,39 @@ def run_reference_arm(args, rank, world):
 
 # --------------------------------------------------------------------------- dry run
 def run_dry(args, rank, world):
-    """Multi-rank host logic without a GPU: sharding, barrier, max over ranks."""
+    """Multi-rank host logic without a GPU: the config-5 split (sub-band
+    headers, bank offsets), barrier, max over ranks, gather of the banks."""
     import torch
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group('gloo')
-    w = workload(rank)
+    sb = subband(rank, world)
     ms = 1.0 + 0.5 * rank                      # pretend rank r needs 1 + r/2 ms per step
-    f0s = [w['f0']]
+    subs = [subband(g, world) for g in range(world)]
+    offs = np.concatenate([[0], np.cumsum([s['max_delay'] for s in subs])])
+    gathered = None
     if world > 1:
         dist.barrier()
         t = torch.tensor([ms])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
-        dist.all_gather(parts, torch.tensor([w['f0']], dtype=torch.float64))
-        f0s = [float(p.item()) for p in parts]
+        # a token "bank" per rank: md_g rows of the value g, gathered into rank 0's bank
+        mine = torch.full((sb['max_delay'], 4), float(rank))
+        if rank == 0:
+            bank = torch.full((int(offs[-1]), 4), -1.0)
+            bank[:sb['max_delay']] = mine
+            reqs = [dist.irecv(bank[int(offs[g]):int(offs[g + 1])], g) for g in range(1, world)]
+            for r in reqs:
+                r.wait()
+            gathered = [float(bank[int(offs[g])][0]) for g in range(world)] + [float(bank.min())]
+        else:
+            dist.isend(mine, 0).wait()
     if rank == 0:
-        print(json.dumps(dict(dry_run=True, n_gpus=world, ms_per_step=ms,
-                              value=w['nchan'] * NTIME_OUT * world / (ms * 1e-3) / 1e6,
-                              subband_f0_mhz=f0s, max_delay=w['max_delay'])))
+        print(json.dumps(dict(dry_run=True, n_gpus=world, ms_per_step=ms, scaling='strong' if world > 1 else 'weak',
+                              value=NCHAN * NTIME_OUT / (ms * 1e-3) / 1e6,
+                              subband_f0_mhz=[s['f0'] for s in subs], subband_nchan=[s['nchan'] for s in subs],
+                              subband_max_delay=[s['max_delay'] for s in subs], bank_offsets=[int(o) for o in offs],
+                              gathered=gathered)))
     if world > 1:
         dist.destroy_process_group()
 
@@ -235,6 +298,80 @@ def log(*a):
         print('[bench]', *a, file=sys.stderr, flush=True)
 
 
+def traffic_probe():
+    """Child mode (run under ncu by measure_traffic): a few resident steps."""
+    import bifrost_b200 as bf
+    from bifrost_b200.fdmt import Fdmt
+    w = workload(0)
+    x = make_input(w, 1234)
+    d_in = bf.asarray(x, space='cuda')
+    d_out = bf.empty((w['max_delay'], w['ntime']), dtype='f32', space='cuda')
+    plan = Fdmt()
+    plan.init(w['nchan'], w['max_delay'], w['f0'], w['df'])
+    for _ in range(3):
+        plan.execute(d_in, d_out)
+    bf.device.stream_synchronize()
+
+
+def measure_traffic(launches_per_step):
+    """DRAM bytes of one bfFdmtExecute, measured now: ncu replays this file's
+    --traffic-probe mode with the two dram__bytes counters.  None when ncu (or
+    the permission to read counters) is not there."""
+    import shutil
+    ncu = shutil.which('ncu') or '/usr/local/cuda/bin/ncu'
+    if not os.path.exists(ncu):
+        return None, 'ncu not found'
+    cmd = [ncu, '--metrics', 'dram__bytes_read.sum,dram__bytes_write.sum', '--clock-control', 'none',
+           '-k', 'regex:fdmt', '--csv', sys.executable, os.path.abspath(__file__), '--traffic-probe']
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300).stdout
+    except Exception as e:
+        return None, f'ncu failed: {e}'
+    import csv
+    rows = [r for r in csv.reader(out.splitlines()) if len(r) > 8]
+    if not rows or 'Metric Value' not in rows[0]:
+        return None, 'ncu printed no metrics (no permission to read counters?)'
+    h = rows[0]
+    iv, iu, iid = h.index('Metric Value'), h.index('Metric Unit'), h.index('ID')
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    per = {}
+    for r in rows[1:]:
+        try:
+            per.setdefault(int(r[iid]), 0.0)
+            per[int(r[iid])] += float(r[iv].replace(',', '')) * scale.get(r[iu], 1)
+        except (ValueError, IndexError):
+            continue
+    ids = sorted(per)
+    if len(ids) < launches_per_step:
+        return None, 'too few launches captured'
+    last = ids[-launches_per_step:]                     # the last (warm) step
+    return float(sum(per[i] for i in last)), f'ncu dram__bytes_read+write.sum over the {launches_per_step} launch(es) of one warm step, this run'
+
+
+def oracle_window_check(x, got_fn, w, windows):
+    """Bit-for-bit check of output columns [a, a+n) against the C oracle run on
+    the input slice those columns depend on."""
+    from oracle import fdmt_c
+    if not fdmt_c.available():
+        return dict(ok=None, note='oracle/libfdmt_oracle.so not built')
+    md, ntime = w['max_delay'], x.shape[1]
+    plan = fdmt_c.Plan(w['nchan'], md, w['f0'], w['df'])
+    bad = 0
+    for a, n in windows:
+        b = min(ntime, a + n + md)
+        want = np.zeros((md, b - a), np.float32)
+        plan.execute(np.ascontiguousarray(x[:, a:b]), want)
+        m = min(n, b - a)
+        got = got_fn(a, m)
+        # cells past ntime - r are never written by either side; compare written ones
+        r = np.arange(md)[:, None]
+        c = np.arange(m)[None, :] + a
+        valid = c < ntime - r
+        bad += int(((got.view(np.uint32) != want[:, :m].view(np.uint32)) & valid).sum())
+    return dict(ok=bad == 0, mismatches=bad, windows=len(windows),
+                how='output columns of the timed gulp vs oracle/fdmt_c.c on the input slices they depend on, bit for bit')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -243,7 +380,10 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-chain', action='store_true')
+    ap.add_argument('--no-traffic', action='store_true')
+    ap.add_argument('--no-gpu-reference', action='store_true')
     ap.add_argument('--dry-run', action='store_true')
+    ap.add_argument('--traffic-probe', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -251,6 +391,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
 
+    if args.traffic_probe:
+        traffic_probe()
+        return
     if args.impl == 'reference':
         run_reference_arm(args, rank, world)
         return
@@ -258,6 +401,7 @@ def main():
         run_dry(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa_node(local_rank)           # before any pinned allocation
     import torch
     import torch.distributed as dist
     import bifrost_b200 as bf
@@ -269,36 +413,19 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     stream = torch.cuda.current_stream()
     bf.device.set_stream(stream.cuda_stream)
-
-    log('torch/bf imported, device set')
-    w = workload(rank)
-    nchan, ntime, md = w['nchan'], w['ntime'], w['max_delay']
-    x_host = make_input(w, 1234 + rank)
-    pinned_in = bf.empty((nchan, ntime), dtype='i8', space='cuda_host')
-    np.copyto(np.asarray(pinned_in), x_host)
-    pinned_out = bf.empty((md, ntime), dtype='f32', space='cuda_host')
-    d_in = bf.empty((nchan, ntime), dtype='i8', space='cuda')
-    d_out = bf.empty((md, ntime), dtype='f32', space='cuda')
-    bf.copy_array(d_in, pinned_in)
-    bf.memset_array(d_out, 0)
-    log('buffers ready')
-    plan = Fdmt()
-    plan.init(nchan, md, w['f0'], w['df'])
-    ws_size = plan.get_workspace_size(d_in, d_out)
-    ws = bf.empty((ws_size,), dtype='u8', space='cuda')
-
-    def step_resident():
-        plan.execute_workspace(d_in, d_out, ws.ctypes.data, ws_size)
-
-    def step_e2e():
-        bf.copy_array(d_in, pinned_in)            # H2D of this gulp (pinned, async on the stream)
-        plan.execute_workspace(d_in, d_out, ws.ctypes.data, ws_size)
-        bf.copy_array(pinned_out, d_out)          # D2H of the dispersion bank (+ stream sync)
+    peaks, peak_kind = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     def timed(fn, nwarm, nstep, sampler=None):
         for _ in range(nwarm):
@@ -326,18 +453,53 @@ def main():
                 torch.cuda.synchronize()
             clocks = sampler.stop()
             clocks['window'] = 'timed steps + untimed post-roll of the same steps (nvidia-smi -lms 50)'
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], device='cuda')
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, clocks
+        return max_over_ranks(ev0.elapsed_time(ev1)), launches, clocks
 
-    log('workspace', ws_size)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, timed, barrier, max_over_ranks,
+                  sampler, peaks, peak_kind, numa)
+        dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ N = 1
+    w = workload(0)
+    nchan, ntime, md = w['nchan'], w['ntime'], w['max_delay']
+    x_host = make_input(w, 1234)
+    pinned_in = bf.empty((nchan, ntime), dtype='i8', space='cuda_host')
+    np.copyto(np.asarray(pinned_in), x_host)
+    pinned_out = bf.empty((md, ntime), dtype='f32', space='cuda_host')
+    d_in = bf.empty((nchan, ntime), dtype='i8', space='cuda')
+    d_out = bf.empty((md, ntime), dtype='f32', space='cuda')
+    bf.copy_array(d_in, pinned_in)
+    bf.memset_array(d_out, 0)
+    plan = Fdmt()
+    plan.init(nchan, md, w['f0'], w['df'])
+    ws_size = plan.get_workspace_size(d_in, d_out)
+    ws = bf.empty((ws_size,), dtype='u8', space='cuda')
+    log('workspace', ws_size)
+
+    def step_resident():
+        plan.execute_workspace(d_in, d_out, ws.ctypes.data, ws_size)
+
+    def step_e2e():
+        bf.copy_array(d_in, pinned_in)            # H2D of this gulp (pinned, async on the stream)
+        plan.execute_workspace(d_in, d_out, ws.ctypes.data, ws_size)
+        bf.copy_array(pinned_out, d_out)          # D2H of the dispersion bank (+ stream sync)
+
     ms_total, launches, clocks = timed(step_resident, args.warmup, args.steps, sampler)
     ms_step = ms_total / args.steps
+    launches_per_step = max(1, launches // args.steps)
     log('resident ms/step', ms_step)
+
+    # value check of exactly this gulp (untimed): five windows, both edges
+    got_dev = d_out
+
+    def got_fn(a, n):
+        return np.asarray(got_dev[:, a:a + n].copy('system'))
+    parity = oracle_window_check(x_host, got_fn, w, [(0, 4096), (40000, 4096), (65536 + 3, 4096), (100001, 4096),
+                                                       (ntime - 4096 - md, 4096 + md)])
+
     e2e_steps = max(4, min(args.steps, 10))
     ms_e2e_total, _, _ = timed(step_e2e, 2, e2e_steps)
     ms_e2e_serial = ms_e2e_total / e2e_steps
@@ -408,86 +570,62 @@ def main():
     try:
         run_pipeline(2)                                # warm-up
         ms_pipe = run_pipeline(e2e_steps) / e2e_steps
-    except Exception as e:                             # keep the serial figure; every rank still reduces
+    except Exception as e:                             # keep the serial figure
         log('pipelined e2e failed:', e)
         ms_pipe = float('inf')
-    if world > 1:
-        t = torch.tensor([ms_pipe], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_pipe = float(t.item())
     ms_e2e = min(ms_pipe, ms_e2e_serial)
     del d_in2, d_out2, ws2
-
     log('e2e ms/step', ms_e2e)
-    samples_per_step = nchan * NTIME_OUT * world            # pol not counted
+
+    samples_per_step = nchan * NTIME_OUT                    # pol not counted
     value = samples_per_step / (ms_step * 1e-3) / 1e6
     e2e_value = samples_per_step / (ms_e2e * 1e-3) / 1e6
 
     # Roofline of the op (all kernels of one bfFdmtExecute): compulsory bytes
-    # ntime*(nchan*1 + max_delay*4) per gulp, per GPU.
-    peaks, peak_kind = measured_peaks()
+    # ntime*(nchan*1 + max_delay*4) per gulp.
     alg_bytes = ntime * (nchan * 1 + md * 4)
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-    roofline = dict(bound='hbm', kernel='bfFdmtExecute = 3 x fdmt_tile_kernel (raw head 1..5, pass 6..9, final pass 10..12); '
-                           'bytes and time are those of the whole call',
-                    achieved=achieved, peak=peaks['hbm_gbs'], peak_source=peak_kind,
-                    unit='GB/s', frac=achieved / peaks['hbm_gbs'],
-                    algorithmic_bytes=alg_bytes, traffic=None)
-    prof = os.path.join(ROOT, 'profiles', 'fdmt_traffic.json')
-    if os.path.exists(prof):
-        try:
-            roofline['traffic'] = json.load(open(prof)).get('dram_bytes_per_call')
-        except Exception:
-            pass
+    traffic, traffic_how = (None, 'skipped')
+    if not args.no_traffic:
+        traffic, traffic_how = measure_traffic(launches_per_step)
+    roofline = dict(bound='hbm',
+                    kernel=f'bfFdmtExecute = {launches_per_step} launch(es) per gulp (fdmt_packed*: packed-integer '
+                           'schedule, see DESIGN.md 4.1); bytes and time are those of the whole call',
+                    achieved=achieved, peak=peaks['hbm_gbs'], peak_source=peak_kind, unit='GB/s',
+                    frac=achieved / peaks['hbm_gbs'], algorithmic_bytes=alg_bytes,
+                    traffic=traffic, traffic_source=traffic_how,
+                    traffic_over_algorithmic=(traffic / alg_bytes) if traffic else None)
 
-    # ---- second half of the metric: the fused GUPPI chain (config 3), per rank
+    # ---- the reference's own CUDA kernels on this box (the "kernel to beat")
+    gpu_reference = None
+    if not args.no_gpu_reference:
+        gpu_reference = time_gpu_reference(bf, torch, stream, d_in, d_out, w)
+
+    # ---- second half of the metric: the fused GUPPI chain (config 3)
     chain = None
     if not args.no_chain:
-        del ws, d_out
-        nframe, cchan, nfft, f_avg = 32, 4096, 4096, 4
-        nbyte = nframe * cchan * nfft * 4
-        raw = torch.randint(-127, 128, (nbyte,), dtype=torch.int8, device='cuda')
-        xg = bf.empty((nframe, cchan, nfft, 2), 'ci8', 'cuda')
-        from bifrost_b200.libbifrost import _bf, _check
-        _check(_bf.bfMemcpy(xg.ctypes.data, xg.as_BFarray().space, raw.data_ptr(),
-                            xg.as_BFarray().space, nbyte))
-        torch.cuda.synchronize()
-        del raw
-        og = bf.zeros((4, cchan * nfft // f_avg), 'f32', 'cuda')
-        ms_c, _, _ = timed(lambda: bf.spectrometer(xg, og, nfft, f_avg, 0.0), 3, 10)
-        ms_c /= 10
-        gbs = nbyte / (ms_c * 1e-3) / 1e9
-        chain = dict(workload='BASELINE config 3: GUPPI ci8 [32 frames, 4096 chan, 4096 fine_time, 2 pol] -> '
-                              'fft(fine_time, fftshift) -> stokes -> reduce(f_avg=4) -> accumulate(32 frames); '
-                              'bfSpectrometerFused, one kernel per gulp per GPU',
-                     ms_per_gulp=ms_c, value=nframe * cchan * nfft * world / (ms_c * 1e-3) / 1e6,
-                     unit='Msamples/s', hbm_GBps=gbs, hbm_frac=gbs / peaks['hbm_gbs'],
-                     note='fp32-issue bound (2 x 4096-pt FFT per 16 KB read); see DESIGN.md')
-        log('chain ms/gulp', ms_c)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        del ws
+        chain = time_chain(bf, torch, timed, peaks)
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         v, kind, cores, dt = cpu_fdmt_sample(w, CPU_SAMPLE_NTIME)
         cpu = dict(value=v, unit='Msamples/s', cores=cores, kind=kind,
                    sample=f"oracle CPU FDMT: {nchan} chan x {CPU_SAMPLE_NTIME} samples "
                           f"(1/{NTIME_OUT // CPU_SAMPLE_NTIME} of the gulp), {dt:.2f} s, "
                           f"{cores} thread(s) of {os.cpu_count()} host cores")
 
-    line = dict(metric=METRIC, value=value, unit='Msamples/s', n_gpus=world, steps=args.steps,
+    line = dict(metric=METRIC, value=value, unit='Msamples/s', n_gpus=1, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                scaling='weak', vs_baseline=None, dtype='u16/f32 (exact integers; bit-identical to the reference\'s f32)',
+                data='synthetic',
                 config=dict(workload='BASELINE config 2: bfFdmtExecute, max_dm=100 '
                                      f'(max_delay={md}) on {nchan}-chan x {NTIME_OUT}(+{md})-sample '
-                                     'int8 filterbank per GPU; f0=1000 MHz, bw=400 MHz, dt=256 us',
-                            sharding='one 4096-chan sub-band per GPU, no collective' if world > 1
-                                     else 'single GPU',
-                            l2='input 540 MB + output 419 MB per step exceed the 126 MB L2'),
-                roofline=roofline, cpu_baseline=cpu,
+                                     'int8 filterbank; f0=1000 MHz, bw=400 MHz, dt=256 us',
+                            sharding='single GPU',
+                            l2='input 540 MB + output 419 MB per step exceed the 126 MB L2',
+                            host_numa=numa),
+                roofline=roofline, cpu_baseline=cpu, gpu_reference=gpu_reference, parity=parity,
                 e2e=dict(value=e2e_value, unit='Msamples/s', ms_per_step=ms_e2e,
                          ms_per_step_serial=ms_e2e_serial, ms_per_step_pipelined=ms_pipe,
                          how='host buffers -> bf.copy_array(H2D) -> Fdmt.execute -> bf.copy_array(D2H) per gulp; '
@@ -496,8 +634,218 @@ def main():
                          h2d_bytes_per_step=int(nchan * ntime), d2h_bytes_per_step=int(md * ntime * 4)),
                 gpu_launches=int(launches), clocks=clocks, chain=chain)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def time_gpu_reference(bf, torch, stream, d_in, d_out, w):
+    """oracle/_ref/libbifrost_ref.so = the reference's own fdmt.cu compiled for
+    sm_100 (oracle/ref_build.sh): same device buffers, same stream."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    try:
+        import reflib
+        ref = reflib.load()
+    except Exception:
+        ref = None
+    if ref is None:
+        return dict(available=False, note='oracle/_ref/libbifrost_ref.so did not travel')
+    try:
+        from bifrost_b200.libbifrost import _check
+        h = ctypes.c_void_p(stream.cuda_stream)
+        ref.bfStreamSet(ctypes.byref(h))
+        plan = ctypes.c_void_p()
+        _check(ref.bfFdmtCreate(ctypes.byref(plan)))
+        _check(ref.bfFdmtInit(plan, w['nchan'], w['max_delay'], w['f0'], w['df'], -2.0, 2, None, None))
+        a_in, a_out = d_in.as_BFarray(), d_out.as_BFarray()
+        for _ in range(2):
+            _check(ref.bfFdmtExecute(plan, a_in, a_out, 0, None, None))
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _check(ref.bfFdmtExecute(plan, a_in, a_out, 0, None, None))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        _check(ref.bfFdmtDestroy(plan))
+        ms = float(np.median(times))
+        return dict(available=True, fdmt_ms_per_gulp=ms,
+                    fdmt_Msamples_s=w['nchan'] * NTIME_OUT / (ms * 1e-3) / 1e6,
+                    what="the reference's src/fdmt.cu kernels (13 launches) on the same gulp, same box")
+    except Exception as e:
+        return dict(available=False, note=f'reference library failed: {e}')
+
+
+def time_chain(bf, torch, timed, peaks):
+    nframe, cchan, nfft, f_avg = 32, 4096, 4096, 4
+    nbyte = nframe * cchan * nfft * 4
+    raw = torch.randint(-127, 128, (nbyte,), dtype=torch.int8, device='cuda')
+    xg = bf.empty((nframe, cchan, nfft, 2), 'ci8', 'cuda')
+    from bifrost_b200.libbifrost import _bf, _check
+    _check(_bf.bfMemcpy(xg.ctypes.data, xg.as_BFarray().space, raw.data_ptr(),
+                        xg.as_BFarray().space, nbyte))
+    torch.cuda.synchronize()
+    del raw
+    og = bf.zeros((4, cchan * nfft // f_avg), 'f32', 'cuda')
+    ms_c, _, _ = timed(lambda: bf.spectrometer(xg, og, nfft, f_avg, 0.0), 3, 10)
+    ms_c /= 10
+    gbs = nbyte / (ms_c * 1e-3) / 1e9
+    # useful fp32 work: 2 pols x 5 N log2 N per 4096-point FFT + detect/reduce (~16 flop/sample)
+    flops = nframe * cchan * (2 * 5 * nfft * 12 + 16 * nfft)
+    tflops = flops / (ms_c * 1e-3) / 1e12
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                 # SMs x lanes x FMA x GHz
+    return dict(workload='BASELINE config 3: GUPPI ci8 [32 frames, 4096 chan, 4096 fine_time, 2 pol] -> '
+                         'fft(fine_time, fftshift) -> stokes -> reduce(f_avg=4) -> accumulate(32 frames); '
+                         'bfSpectrometerFused, one kernel per gulp',
+                ms_per_gulp=ms_c, value=nframe * cchan * nfft / (ms_c * 1e-3) / 1e6, unit='Msamples/s',
+                roofline=dict(bound='fp32 issue (2 x 4096-pt FFT per 16 KB read; SURVEY 8d)',
+                              hbm_GBps=gbs, hbm_frac=gbs / peaks['hbm_gbs'], algorithmic_bytes=nbyte,
+                              fp32_tflops=tflops, fp32_peak_tflops=fp32_peak, fp32_frac=tflops / fp32_peak))
+
+
+def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, timed, barrier, max_over_ranks,
+              sampler, peaks, peak_kind, numa):
+    """Config 5: one gulp, N sub-bands, NCCL scatter + gather (strong scaling),
+    plus the replica (weak) figure."""
+    full = workload(0)
+    ntime = full['ntime']
+    subs = [subband(g, world) for g in range(world)]
+    sb = subs[rank]
+    nc, md = sb['nchan'], sb['max_delay']
+    offs = np.concatenate([[0], np.cumsum([s['max_delay'] for s in subs])]).astype(np.int64)
+    x_full = make_input(full, 1234)
+    x_sub = np.ascontiguousarray(x_full[sb['chan0']:sb['chan0'] + nc])
+    # device buffers as torch tensors (NCCL) viewed as bf arrays (C ABI)
+    t_in = torch.empty((nc, ntime), dtype=torch.int8, device='cuda')
+    t_full = torch.from_numpy(x_full).cuda() if rank == 0 else None
+    t_bank = torch.zeros((int(offs[-1]), ntime), dtype=torch.float32, device='cuda') if rank == 0 else None
+    t_out = t_bank[:md] if rank == 0 else torch.zeros((md, ntime), dtype=torch.float32, device='cuda')
+    a_in = bf.ndarray(base=(t_full[:nc] if rank == 0 else t_in))
+    a_out = bf.ndarray(base=t_out)
+    plan = Fdmt()
+    plan.init(nc, md, sb['f0'], sb['df'])
+    ws_size = plan.get_workspace_size(a_in, a_out)
+    ws = bf.empty((ws_size,), dtype='u8', space='cuda')
+    P2P = dist.P2POp
+
+    def scatter():
+        if rank == 0:
+            ops = [P2P(dist.isend, t_full[g * nc:(g + 1) * nc], g) for g in range(1, world)]
+        else:
+            ops = [P2P(dist.irecv, t_in, 0)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+    def gather():
+        if rank == 0:
+            ops = [P2P(dist.irecv, t_bank[int(offs[g]):int(offs[g + 1])], g) for g in range(1, world)]
+        else:
+            ops = [P2P(dist.isend, t_out, 0)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+    def compute():
+        plan.execute_workspace(a_in, a_out, ws.ctypes.data, ws_size)
+
+    def step_strong():
+        scatter()
+        compute()
+        gather()
+
+    ms_total, launches, clocks = timed(step_strong, args.warmup, args.steps, sampler)
+    ms_step = ms_total / args.steps
+    ms_scatter = timed(scatter, 2, 5)[0] / 5
+    ms_compute = timed(compute, 2, 5)[0] / 5
+    ms_gather = timed(gather, 2, 5)[0] / 5
+
+    # per-sub-band parity (untimed): this rank's bank against the oracle run with
+    # (nchan/N, f0_g, max_delay_g); rank 0 additionally checks a gathered bank
+    step_strong()
+    torch.cuda.synchronize()
+
+    def got_fn(a, n):
+        return t_out[:, a:a + n].cpu().numpy()
+    par = oracle_window_check(x_sub, got_fn, sb, [(0, 4096), (65536 + 3, 4096), (ntime - 4096 - md, 4096 + md)])
+    bad = torch.tensor([0 if par.get('ok') else 1], device='cuda')
+    dist.all_reduce(bad)
+    gathered_ok = None
+    if rank == 0:
+        g = world - 1
+        sg = subs[g]
+        xg = np.ascontiguousarray(x_full[sg['chan0']:sg['chan0'] + nc])
+        gathered_ok = oracle_window_check(xg, lambda a, n: t_bank[int(offs[g]):int(offs[g + 1]), a:a + n].cpu().numpy(),
+                                          sg, [(30000, 4096)]).get('ok')
+
+    # e2e: every rank H2D's its own sub-band from its own pinned buffer (NUMA-local),
+    # FDMT, gather to rank 0, rank 0 D2H of the whole bank
+    pinned_in = bf.empty((nc, ntime), dtype='i8', space='cuda_host')
+    np.copyto(np.asarray(pinned_in), x_sub)
+    a_in_e2e = bf.ndarray(base=t_in) if rank != 0 else a_in
+    pinned_bank = bf.empty((int(offs[-1]), ntime), dtype='f32', space='cuda_host') if rank == 0 else None
+    a_bank = bf.ndarray(base=t_bank) if rank == 0 else None
+
+    def step_e2e():
+        bf.copy_array(a_in_e2e, pinned_in)
+        plan.execute_workspace(a_in_e2e, a_out, ws.ctypes.data, ws_size)
+        gather()
+        if rank == 0:
+            bf.copy_array(pinned_bank, a_bank)
+
+    e2e_steps = max(4, min(args.steps, 10))
+    ms_e2e = timed(step_e2e, 2, e2e_steps)[0] / e2e_steps
+    del pinned_in, pinned_bank
+
+    # replicas (weak scaling, no collective): every rank its own full gulp
+    del ws
+    wr = workload(rank)
+    t_rin = torch.from_numpy(make_input(wr, 1234 + rank)).cuda() if rank != 0 else t_full
+    a_rin = bf.ndarray(base=t_rin)
+    a_rout = bf.empty((wr['max_delay'], wr['ntime']), dtype='f32', space='cuda')
+    rplan = Fdmt()
+    rplan.init(wr['nchan'], wr['max_delay'], wr['f0'], wr['df'])
+    ms_rep = timed(lambda: rplan.execute(a_rin, a_rout), 3, 10)[0] / 10
+
+    if rank != 0:
+        return
+    samples = NCHAN * NTIME_OUT
+    nvlink_scatter = (world - 1) * nc * ntime
+    nvlink_gather = int(offs[-1] - offs[1]) * ntime * 4
+    alg_bytes = ntime * (NCHAN + 4 * int(offs[-1]))
+    line = dict(metric=METRIC, value=samples / (ms_step * 1e-3) / 1e6, unit='Msamples/s', n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
+                scaling='strong', vs_baseline=None,
+                dtype='u16/f32 (exact integers; bit-identical to the reference\'s f32)', data='synthetic',
+                config=dict(workload=f'BASELINE config 5: the one {NCHAN}-chan x {NTIME_OUT}(+{full["max_delay"]})-sample int8 '
+                                     f'gulp of config 2 split into {world} sub-bands of {nc} channels',
+                            sharding=f'NCCL grouped send/recv scatter of the sub-bands from rank 0 -> per-GPU '
+                                     f'bfFdmtInit({nc}, max_delay_g, f0_g, df) + bfFdmtExecute -> NCCL grouped '
+                                     'send/recv gather of the [max_delay_g, ntime] f32 banks to rank 0',
+                            subband_max_delay=[s['max_delay'] for s in subs],
+                            subband_f0_mhz=[s['f0'] for s in subs], host_numa=numa,
+                            l2='per-GPU inputs and banks exceed L2 for N <= 4; the collectives stream through HBM'),
+                comm=dict(collective='ncclSend/ncclRecv groups (torch.distributed.batch_isend_irecv)',
+                          nvlink_bytes_per_step=int(nvlink_scatter + nvlink_gather),
+                          scatter_bytes=int(nvlink_scatter), gather_bytes=int(nvlink_gather),
+                          ms_scatter=ms_scatter, ms_compute_max_rank=ms_compute, ms_gather=ms_gather,
+                          limit='the gather: rank 0 receives (N-1)/N of the 420 MB bank over its NVLink ingress, '
+                                'which takes longer than one GPU needs to compute the whole bank'),
+                parity=dict(per_subband_ok=bool(int(bad.item()) == 0), gathered_bank_ok=gathered_ok,
+                            how='each rank: its bank vs oracle/fdmt_c.c with (nchan/N, f0_g, max_delay_g) on 3 windows, '
+                                'bit for bit; rank 0: one gathered bank after the collective'),
+                roofline=dict(bound='nvlink+hbm', achieved=alg_bytes / (ms_step * 1e-3) / 1e9, unit='GB/s',
+                              peak=peaks['hbm_gbs'], peak_source=peak_kind,
+                              frac=alg_bytes / (ms_step * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                              algorithmic_bytes=alg_bytes, traffic=None,
+                              note='single-GPU HBM peak as denominator; the step is NVLink-bound (comm.limit)'),
+                e2e=dict(value=samples / (ms_e2e * 1e-3) / 1e6, unit='Msamples/s', ms_per_step=ms_e2e,
+                         how='every rank: pinned host sub-band -> H2D -> Fdmt.execute -> NCCL gather; rank 0: D2H of '
+                             'the whole bank to pinned host memory; one stream per rank, max over ranks',
+                         h2d_bytes_per_step=int(NCHAN * ntime), d2h_bytes_per_step=int(offs[-1]) * ntime * 4),
+                replicas=dict(scaling='weak', what='every rank its own full 4096-chan gulp (sub-band above the '
+                                                   'previous rank\'s), no collective; max over ranks',
+                              ms_per_step=ms_rep, value=samples * world / (ms_rep * 1e-3) / 1e6, unit='Msamples/s'),
+                gpu_launches=int(launches), clocks=clocks)
+    print(json.dumps(line))
 
 
 if __name__ == '__main__':

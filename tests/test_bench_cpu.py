@@ -63,6 +63,21 @@ def _free_port():
     return port
 
 
+def test_config5_subbands_partition_the_gulp():
+    """Config 5: N sub-bands of 4096/N channels with their own headers; the
+    per-sub-band bank depths follow blocks/fdmt.py:79-81 and add up to (about)
+    the full band's."""
+    full = bench.workload(0)
+    for n in (2, 4, 8):
+        subs = [bench.subband(g, n) for g in range(n)]
+        assert [s['chan0'] for s in subs] == [g * 4096 // n for g in range(n)]
+        assert all(s['nchan'] == 4096 // n and s['ntime'] == full['ntime'] for s in subs)
+        for a, b in zip(subs[:-1], subs[1:]):
+            assert abs(a['f0'] + a['nchan'] * a['df'] - b['f0']) < 1e-9
+            assert a['max_delay'] > b['max_delay']          # nu^-2: the low sub-bands are the deep ones
+        assert full['max_delay'] <= sum(s['max_delay'] for s in subs) <= full['max_delay'] + n
+
+
 def test_dry_run_single():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--dry-run'],
                          capture_output=True, text=True, timeout=300, check=True)
@@ -79,10 +94,14 @@ def test_dry_run_world_size_2_gloo():
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
     assert len(lines) == 1                       # rank 0 alone prints
     line = json.loads(lines[0])
-    assert line['n_gpus'] == 2
+    assert line['n_gpus'] == 2 and line['scaling'] == 'strong'
     assert line['ms_per_step'] == 1.5            # max over ranks, not mean / rank 0
-    assert line['subband_f0_mhz'] == [1000.0, 1400.0]
-    assert abs(line['value'] - 2 * 4096 * 131072 / 1.5e-3 / 1e6) < 1e-3
+    assert line['subband_f0_mhz'] == [1000.0, 1200.0] and line['subband_nchan'] == [2048, 2048]
+    # one gulp whatever N is: the value is that gulp's samples over the slowest rank's time
+    assert abs(line['value'] - 4096 * 131072 / 1.5e-3 / 1e6) < 1e-3
+    # the banks of both ranks landed at their offsets in rank 0's bank, nothing left unwritten
+    assert line['gathered'] == [0.0, 1.0, 0.0]
+    assert line['bank_offsets'][1] == line['subband_max_delay'][0]
 
 
 def test_reference_arm_line(monkeypatch):
