@@ -736,6 +736,7 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 		cfg.nwarp   = std::max(1, std::min(8, pi < NWs.size() ? NWs[pi] : 8));
 		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : 74);
 		cfg.tcap    = pi < TCs.size() ? std::max(64, TCs[pi]) : (1 << 20);
+		cfg.fuse4   = env_int("BFB_FDMT_PACKED_FUSE", 1) != 0;
 		PackedPass cp;
 		bool ok = false;
 		// smaller delay blocks first (more programs, a little more redundancy),
@@ -898,20 +899,14 @@ static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int
 	int tmax = 0;
 	for( PackedPass const& cp : cps ) tmax = std::max(tmax, cp.T);
 	long C = std::max<long>(env_int("BFB_FDMT_PACKED_CHUNK", 2048), tmax);
-	struct Item { long key; int k, slot, prog; };
-	std::vector<Item> items;
-	for( size_t k=0; k<cps.size(); ++k ) {
-		int smax = (int)(C / cps[k].T) + 2;
-		if( smax > 31 || cps[k].nprog >= (1 << 24) ) return false;
-		for( int sl=0; sl<smax; ++sl )
-			for( int p=0; p<cps[k].nprog; ++p ) {
-				Item it = { (long)sl * cps[k].T * 16 + (long)(cps.size() - 1 - k), (int)k, sl, p };
-				items.push_back(it);
-			}
+	// Items of one round: every (pass, program).  The last pass (it streams the
+	// output to HBM) first, so that the DRAM-bound and the compute-bound passes
+	// interleave; inside a pass the heavy programs first (they are sorted so).
+	tmpl_->clear();
+	for( int k=(int)cps.size()-1; k>=0; --k ) {
+		if( cps[k].nprog >= (1 << 24) ) return false;
+		for( int p=0; p<cps[k].nprog; ++p ) tmpl_->push_back((k << 24) | p);
 	}
-	std::stable_sort(items.begin(), items.end(), [](Item const& a, Item const& b) { return a.key < b.key; });
-	tmpl_->resize(items.size());
-	for( size_t i=0; i<items.size(); ++i ) (*tmpl_)[i] = (items[i].k << 29) | (items[i].slot << 24) | items[i].prog;
 	*C_ = C;
 	*lag_ = 1 + (int)div_up<long>(tmax, C);
 	return true;
@@ -1109,7 +1104,7 @@ BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	PackedPass const& cp = cps[pass];
 	int h[16] = { cp.s0, cp.s1, cp.nlev, cp.esize, cp.src_kind, cp.dst_kind, cp.T, cp.nprog,
 	              cp.nwarp, cp.slots, cp.src_slots, cp.data_bytes, cp.lookback, cp.nrow_out,
-	              (int)cp.smem_bytes(), (int)std::min<long>(cp.nops, 1L << 30) };
+	              (int)cp.smem_bytes(), (int)std::min<long>(cp.nops, 1L << 30) | (cp.fused ? (1 << 30) : 0) };
 	memcpy(header, h, sizeof(h));
 	if( ops ) memcpy(ops, cp.ops.data(), cp.ops.size() * sizeof(int4));
 	if( src ) memcpy(src, cp.src.data(), cp.src.size() * sizeof(int4));

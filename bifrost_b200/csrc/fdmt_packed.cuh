@@ -49,6 +49,8 @@
 #include <vector>
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 namespace bfb {
 
@@ -57,6 +59,7 @@ enum {
 	PK_NO_B    = 1 << 1,     // absent high-frequency parent
 	PK_STORE_G = 1 << 2,     // row of the pass's top level: goes to the pass output
 	PK_BYTES   = 1 << 3,     // operands are rows of the 1-byte input
+	PK_GROUP4  = 1 << 4,     // two-slot op: rows 0/1 of a 4-channel band straight from the input (steps 1+2 fused)
 	PK_WO_SHIFT = 8,         // b's shift in 32-bit words (0..3)
 	PK_H_SHIFT  = 10,        // 16-bit passes: odd sample shift
 	PK_NVEC_SHIFT = 16,      // row window in 16-byte vectors
@@ -72,11 +75,13 @@ struct PackedCfg {
 	int nwarp = 8;
 	int smem_cap = 74 * 1024;
 	int tcap = 1 << 20;      // upper bound on T
+	bool fuse4 = true;       // fuse the first two steps of a byte pass where the plan allows
 };
 
 struct PackedPass {
 	int s0 = 0, s1 = 0, nlev = 0;
 	int esize = 2;           // 2: packed u16 accumulators, 4: fp32
+	bool fused = false;      // byte pass: op level 1 produces the rows of step s0+1 (PK_GROUP4)
 	int src_kind = PK_SRC_SAME, dst_kind = PK_DST_SAME;
 	int T = 0, nprog = 0, nwarp = 0, slots = 0, src_slots = 0;
 	int data_bytes = 0;      // shared-memory data region
@@ -149,12 +154,13 @@ inline int fdmt_last_u16_step(FdmtPlan const& P) {
 // to its row in the pass output (the compact workspace, or the delay itself
 // for the final pass), `src_index[r]` a row of step s0-1 to its row in the
 // source (workspace row, or input channel for the byte source).
+#define PK_FAIL(n_) do { if( getenv("BFB_FDMT_PACKED_DEBUG") ) fprintf(stderr, "build_packed_pass(%d..%d, D=%d, tcap=%d): fail %d\n", s0, s1, cfg.D, cfg.tcap, n_); return false; } while(0)
 inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> > const& used,
                               int s0, int s1, int esize, int src_kind, int dst_kind,
                               std::vector<int> const& src_index, std::vector<int> const& out_index,
                               PackedCfg const& cfg, PackedPass* cp) {
 	using namespace packed_detail;
-	if( s0 < 1 || s1 < s0 || s1 >= P.nstep() || s1 - s0 + 1 > PK_MAXLEV ) return false;
+	if( s0 < 1 || s1 < s0 || s1 >= P.nstep() || s1 - s0 + 1 > PK_MAXLEV ) PK_FAIL(1);
 	const int nlev = s1 - s0 + 1;
 	const int VS = 16 / esize, LS = PK_LV * VS, WLEN = 32 * LS;
 	const int nwarp = cfg.nwarp;
@@ -176,18 +182,35 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 			progs.push_back(pg);
 		}
 	}
-	if( progs.empty() ) return false;
+	if( progs.empty() ) PK_FAIL(2);
 	std::stable_sort(progs.begin(), progs.end(), [&](Prog const& a, Prog const& b) {
 		return P.bands[s1][a.band].ndelay * 64 + (int)a.rows.size() > P.bands[s1][b.band].ndelay * 64 + (int)b.rows.size();
 	});
+	// row -> band of step s0+1 (for the fused first two steps of a byte pass)
+	std::vector<int> band2_of_row;
+	if( bytes && nlev >= 2 ) {
+		band2_of_row.assign(P.nrow(s0 + 1), 0);
+		for( size_t b=0; b<P.bands[s0 + 1].size(); ++b )
+			for( int d=0; d<P.bands[s0 + 1][b].ndelay; ++d ) band2_of_row[P.bands[s0 + 1][b].row0 + d] = (int)b;
+	}
 	// per program: every needed row of every level with its window of shifts
 	std::vector<std::vector<std::map<int, Win> > > needs(progs.size());
 	int max_spread = 0, lookback = 0;
+	bool fuse = bytes && nlev >= 2 && cfg.fuse4;
 	for( size_t p=0; p<progs.size(); ++p ) {
 		std::vector<std::map<int, Win> >& need = needs[p];
 		need.assign(nlev + 1, std::map<int, Win>());
 		for( int r : progs[p].rows ) grow(need[nlev], r, 0, 0);
 		for( int li=nlev; li>=0; --li ) {
+			if( bytes && li == 2 && li < nlev ) {
+				// rows of one step-2 band share one window (they are produced together
+				// when the first two steps are fused)
+				std::map<int, Win> uni;
+				for( std::map<int, Win>::iterator it=need[li].begin(); it!=need[li].end(); ++it )
+					grow(uni, band2_of_row[it->first], it->second.lo, it->second.hi);
+				for( std::map<int, Win>::iterator it=need[li].begin(); it!=need[li].end(); ++it )
+					it->second = uni[band2_of_row[it->first]];
+			}
 			for( std::map<int, Win>::iterator it=need[li].begin(); it!=need[li].end(); ++it ) {
 				Win& w = it->second;
 				w.lo = floor_to(w.lo, VS); w.hi = ceil_to(w.hi, VS);
@@ -198,48 +221,80 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 				if( fr.src1 >= 0 ) grow(need[li-1], fr.src1, w.lo + fr.delay, w.hi + fr.delay);
 			}
 		}
+		// Fusion of steps 1 and 2 applies when every needed step-2 row is
+		//   row 0 = (x0 + x1) + (x2 + x3)        row 1 = (x0 + x1) + (x2 + x3)[t - 1]
+		// of four input channels x0..x3 (the usual case: the sub-band delays of
+		// the first steps are 0 or 1 sample), and it is its band's top row pair.
+		if( fuse && nlev == 2 ) fuse = false;              // (the fused rows go to shared memory)
+		if( fuse ) for( std::map<int, Win>::iterator it=need[2].begin(); fuse && it!=need[2].end(); ++it ) {
+			FdmtBand const& b2 = P.bands[s0 + 1][band2_of_row[it->first]];
+			int d = it->first - b2.row0;
+			if( d > 1 || b2.parent0 < 0 || b2.parent1 < 0 ) { fuse = false; break; }
+			FdmtBand const& q0 = P.bands[s0][b2.parent0];
+			FdmtBand const& q1 = P.bands[s0][b2.parent1];
+			FdmtRow const& fr = P.rows[s0 + 1][it->first];
+			if( fr.src0 != q0.row0 || fr.src1 != q1.row0 || fr.delay != d ) { fuse = false; break; }
+			FdmtRow const& r0 = P.rows[s0][q0.row0];
+			FdmtRow const& r1 = P.rows[s0][q1.row0];
+			if( r0.src0 < 0 || r0.src1 < 0 || r0.delay != 0 || r1.src0 < 0 || r1.src1 < 0 || r1.delay != 0 ) { fuse = false; break; }
+		}
 	}
 	int T = std::min(cfg.tcap, WLEN - max_spread) / 16 * 16;
-	if( T < 64 ) return false;
-	cp->s0 = s0; cp->s1 = s1; cp->nlev = nlev; cp->esize = esize;
+	if( T < 64 ) PK_FAIL(3);
+	// op levels: with fusion, op level 1 produces the step-(s0+1) rows from the
+	// input channels and step s0 has no rows of its own
+	const int nopl = fuse ? nlev - 1 : nlev;
+	auto step_level = [&](int ol) { return fuse ? ol + 1 : ol; };     // op level -> tree level
+	cp->s0 = s0; cp->s1 = s1; cp->nlev = nopl; cp->esize = esize; cp->fused = fuse;
 	cp->src_kind = src_kind; cp->dst_kind = dst_kind;
 	cp->T = T; cp->nprog = (int)progs.size(); cp->nwarp = nwarp; cp->lookback = lookback;
 	int slots = 1, src_slots = 1;
 	long nops = 0;
 	for( size_t p=0; p<progs.size(); ++p ) {
 		src_slots = std::max(src_slots, (int)needs[p][0].size() + 1);
-		for( int li=1; li<=nlev; ++li ) {
-			slots = std::max(slots, div_up<int>((int)needs[p][li].size(), nwarp) + 1);
-			nops += (long)needs[p][li].size();
+		for( int ol=1; ol<=nopl; ++ol ) {
+			int n = (int)needs[p][step_level(ol)].size();
+			if( fuse && ol == 1 ) {
+				// one two-slot op per band
+				std::map<int, int> bands;
+				for( std::map<int, Win>::iterator it=needs[p][2].begin(); it!=needs[p][2].end(); ++it ) bands[band2_of_row[it->first]] = 1;
+				n = 2 * div_up<int>((int)bands.size(), nwarp) * nwarp;
+			}
+			slots = std::max(slots, div_up<int>(n, nwarp) + 1);
+			nops += (long)needs[p][step_level(ol)].size();
 		}
 	}
-	if( bytes && src_slots > 4096 ) return false;
+	if( bytes && src_slots > 4096 ) PK_FAIL(4);
 	cp->slots = slots; cp->src_slots = src_slots; cp->nops = nops;
-	cp->ops.assign((size_t)cp->nprog * nlev * nwarp * slots, make_int4(0, 0, 0, 0));
+	cp->ops.assign((size_t)cp->nprog * nopl * nwarp * slots, make_int4(0, 0, 0, 0));
 	cp->src.assign((size_t)cp->nprog * src_slots, make_int4(0, 0, 0, 0));
 	cp->hdr.assign((size_t)cp->nprog, make_int4(0, 0, 0, 0));
 	int data_max = 0;
 	for( size_t p=0; p<progs.size(); ++p ) {
 		std::vector<std::map<int, Win> >& need = needs[p];
-		// shared-memory layout (bytes): even levels in region 0, odd levels in
-		// region 1 -- a level is read only by the next one
+		// shared-memory layout (bytes): stored levels alternate between two
+		// regions -- a level is read only by the next one.  Stored levels: the
+		// source (tree level 0) and the rows of op levels 1 .. nopl-1.
 		std::vector<std::map<int, int> > off(nlev), slot_of(1);
 		int region[2] = {0, 0};
-		for( int li=0; li<nlev; ++li ) {
+		for( int sl=0; sl<nopl; ++sl ) {                 // stored level sl holds tree level li
+			const int li = sl == 0 ? 0 : step_level(sl);
 			int o = 0, k = 0;
 			for( std::map<int, Win>::iterator it=need[li].begin(); it!=need[li].end(); ++it, ++k ) {
 				int len = T + it->second.hi - it->second.lo;
-				if( len > WLEN ) return false;
+				if( len > WLEN ) PK_FAIL(5);
 				off[li][it->first] = o;
 				if( li == 0 ) slot_of[0][it->first] = k;
 				// 1-byte rows: aligned superset of the window (up to 15 bytes in front)
 				// plus the look-ahead of the last lane; word rows: two vectors of slack
 				o += (li == 0 && bytes) ? round_up<int>(len + 16 + 16, 16) : (len + 2 * VS) * esize;
 			}
-			region[li & 1] = std::max(region[li & 1], o);
+			region[sl & 1] = std::max(region[sl & 1], o);
 		}
-		for( int li=1; li<nlev; li+=2 )
+		for( int sl=1; sl<nopl; sl+=2 ) {
+			const int li = step_level(sl);
 			for( std::map<int, int>::iterator it=off[li].begin(); it!=off[li].end(); ++it ) it->second += region[0];
+		}
 		data_max = std::max(data_max, region[0] + region[1]);
 		// source table
 		long staged = 0;
@@ -247,13 +302,44 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 			int k = 0;
 			for( std::map<int, Win>::iterator it=need[0].begin(); it!=need[0].end(); ++it, ++k ) {
 				int len = T + it->second.hi - it->second.lo;
-				if( it->first >= (int)src_index.size() || src_index[it->first] < 0 ) return false;
+				if( it->first >= (int)src_index.size() || src_index[it->first] < 0 ) PK_FAIL(6);
 				cp->src[p * src_slots + k] = make_int4(src_index[it->first], -it->second.hi, off[0][it->first], len);
 				staged += (long)len * esize;
 			}
 		}
 		cp->hdr[p] = make_int4(P.bands[s1][progs[p].band].nchan, (int)need[0].size(), bytes ? 0 : (int)staged, 0);
-		for( int li=1; li<=nlev; ++li ) {
+		for( int ol=1; ol<=nopl; ++ol ) {
+			const int li = step_level(ol);
+			int4* base = &cp->ops[((size_t)p * nopl + (ol - 1)) * nwarp * slots];
+			if( fuse && ol == 1 ) {
+				// fused steps s0, s0+1: one op (two slots) per step-(s0+1) band
+				std::map<int, std::vector<int> > by_band;
+				for( std::map<int, Win>::iterator it=need[2].begin(); it!=need[2].end(); ++it )
+					by_band[band2_of_row[it->first]].push_back(it->first);
+				int k = 0;
+				for( std::map<int, std::vector<int> >::iterator bt=by_band.begin(); bt!=by_band.end(); ++bt, ++k ) {
+					FdmtBand const& b2 = P.bands[s0 + 1][bt->first];
+					Win const& w = need[2][bt->second[0]];
+					const int len = T + w.hi - w.lo;
+					int chan_row[4] = { P.rows[s0][P.bands[s0][b2.parent0].row0].src0, P.rows[s0][P.bands[s0][b2.parent0].row0].src1,
+					                    P.rows[s0][P.bands[s0][b2.parent1].row0].src0, P.rows[s0][P.bands[s0][b2.parent1].row0].src1 };
+					int mask = 0, dst[2] = {0, 0};
+					for( int r : bt->second ) { int d = r - b2.row0; mask |= 1 << d; dst[d] = off[2][r]; }
+					int field[4];
+					for( int c=0; c<4; ++c ) {
+						Win const& cw = need[0][chan_row[c]];
+						int ea = cw.hi - w.hi;                   // first sample of the window inside the staged row
+						// row 1 reads the channels of the upper pair one sample earlier
+						if( ea < ((c >= 2 && (mask & 2)) ? 1 : 0) || ea + len > T + cw.hi - cw.lo ) PK_FAIL(7);
+						field[c] = slot_of[0][chan_row[c]] | (ea << 12);
+					}
+					int4 a = make_int4(dst[0], field[0], field[1], PK_GROUP4 | (mask << PK_WO_SHIFT) | ((len / VS) << PK_NVEC_SHIFT));
+					int4 b = make_int4(dst[1], field[2], field[3], PK_GROUP4 | ((len / VS) << PK_NVEC_SHIFT));
+					int4* slot = base + (size_t)(k % nwarp) * slots + 2 * (k / nwarp);
+					slot[0] = a; slot[1] = b;
+				}
+				continue;
+			}
 			int k = 0;
 			for( std::map<int, Win>::iterator it=need[li].begin(); it!=need[li].end(); ++it, ++k ) {
 				Win const& w = it->second;
@@ -267,15 +353,15 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 				else {
 					Win const& aw = need[li-1][fr.src0];
 					int ea = aw.hi - w.hi;                       // samples from the row's first to the window's first
-					if( ea < 0 || ea + len > T + aw.hi - aw.lo ) return false;
+					if( ea < 0 || ea + len > T + aw.hi - aw.lo ) PK_FAIL(8);
 					if( byte_op ) op.y = slot_of[0][fr.src0] | (ea << 12);
-					else { if( ea % VS ) return false; op.y = off[li-1][fr.src0] + ea * esize; }
+					else { if( ea % VS ) PK_FAIL(9); op.y = off[li-1][fr.src0] + ea * esize; }
 				}
 				if( fr.src1 < 0 ) ctl |= PK_NO_B;
 				else {
 					Win const& bw = need[li-1][fr.src1];
 					int eb = bw.hi - w.hi - fr.delay;
-					if( eb < 0 || eb + len > T + bw.hi - bw.lo ) return false;
+					if( eb < 0 || eb + len > T + bw.hi - bw.lo ) PK_FAIL(10);
 					if( byte_op ) op.z = slot_of[0][fr.src1] | (eb << 12);
 					else {
 						int sub = eb % VS;
@@ -285,19 +371,20 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 				}
 				if( li == nlev ) {
 					ctl |= PK_STORE_G;
-					if( it->first >= (int)out_index.size() || out_index[it->first] < 0 ) return false;
+					if( it->first >= (int)out_index.size() || out_index[it->first] < 0 ) PK_FAIL(11);
 					op.x = out_index[it->first];
 				} else op.x = off[li][it->first];
 				op.w = ctl | ((len / VS) << PK_NVEC_SHIFT);
-				cp->ops[(((size_t)p * nlev + (li - 1)) * nwarp + (k % nwarp)) * slots + (k / nwarp)] = op;
+				base[(size_t)(k % nwarp) * slots + (k / nwarp)] = op;
 			}
 		}
 	}
 	cp->data_bytes = data_max + (32 * PK_LV + 4) * 16;     // slack: lanes past a row's end still load
-	if( cp->smem_bytes() > (size_t)cfg.smem_cap ) return false;
+	if( cp->smem_bytes() > (size_t)cfg.smem_cap ) PK_FAIL(12);
 	return true;
 }
 
+#undef PK_FAIL
 // ---------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------
@@ -548,6 +635,73 @@ __device__ __forceinline__ void pk_bytes_widen(const unsigned char* dbase, uint3
 	for( int k=0; k<6; ++k ) { o[2*k] = __byte_perm(x[k], 0, 0x4140); o[2*k+1] = __byte_perm(x[k], 0, 0x4342); }
 }
 
+// The same with one word (two samples) of history in front: o[0] holds samples
+// -2,-1 and o[1..12] samples 0..23.
+__device__ __forceinline__ void pk_bytes_widen_halo(const unsigned char* dbase, uint32_t addr, uint32_t flip, uint32_t (&o)[13]) {
+	const uint32_t a0 = addr - 2u;
+	const uint32_t m = a0 & 7u;
+	const uint2* p = (const uint2*)(dbase + (a0 - m));
+	uint32_t w[10];
+#pragma unroll
+	for( int j=0; j<5; ++j ) { uint2 v = p[j]; w[2*j] = v.x; w[2*j+1] = v.y; }
+	const uint32_t sh = (m & 3u) * 8u;
+	uint32_t x[7];
+	if( m & 4u ) {
+#pragma unroll
+		for( int k=0; k<7; ++k ) x[k] = __funnelshift_r(w[k+1], w[k+2], sh) ^ flip;
+	} else {
+#pragma unroll
+		for( int k=0; k<7; ++k ) x[k] = __funnelshift_r(w[k], w[k+1], sh) ^ flip;
+	}
+#pragma unroll
+	for( int k=0; k<6; ++k ) { o[2*k] = __byte_perm(x[k], 0, 0x4140); o[2*k+1] = __byte_perm(x[k], 0, 0x4342); }
+	o[12] = __byte_perm(x[6], 0, 0x4140);
+}
+
+// Steps 1 and 2 fused: rows 0 / 1 of a 4-channel band straight from the staged
+// input channels x0..x3:
+//   row0 = (x0 + x1) + (x2 + x3)      row1 = (x0 + x1) + (x2 + x3)[t - 1]
+// (two op slots: A = {dst0, x0, x1, ctl}, B = {dst1, x2, x3, -}).
+__device__ __forceinline__ void pk_group4_op(const int4& A, const int4& B, const PackedSmem& S,
+                                             const PackedTile& tl, int lane) {
+	unsigned char* dbase = S.dbase;
+	const int nvec = A.w >> PK_NVEC_SHIFT;
+	const int mask = (A.w >> PK_WO_SHIFT) & 3;
+	auto addr = [&](int f) { const int k = f & 0xFFF; return (uint32_t)S.ssrc[k].z + S.smis[k] + ((uint32_t)f >> 12) + 24u * lane; };
+	uint32_t s0[12], s1[13];
+	{
+		uint32_t x1[12];
+		pk_bytes_widen(dbase, addr(A.y), tl.flip, s0);
+		pk_bytes_widen(dbase, addr(A.z), tl.flip, x1);
+#pragma unroll
+		for( int k=0; k<12; ++k ) s0[k] += x1[k];
+	}
+	{
+		uint32_t x3[13];
+		pk_bytes_widen_halo(dbase, addr(B.y), tl.flip, s1);
+		pk_bytes_widen_halo(dbase, addr(B.z), tl.flip, x3);
+#pragma unroll
+		for( int k=0; k<13; ++k ) s1[k] += x3[k];
+	}
+	if( mask & 1 ) {
+		uint4* d = (uint4*)(dbase + A.x) + PK_LV * lane;
+#pragma unroll
+		for( int j=0; j<PK_LV; ++j )
+			if( PK_LV * lane + j < nvec )
+				d[j] = make_uint4(s0[4*j] + s1[4*j+1], s0[4*j+1] + s1[4*j+2], s0[4*j+2] + s1[4*j+3], s0[4*j+3] + s1[4*j+4]);
+	}
+	if( mask & 2 ) {
+		uint4* d = (uint4*)(dbase + B.x) + PK_LV * lane;
+#pragma unroll
+		for( int j=0; j<PK_LV; ++j )
+			if( PK_LV * lane + j < nvec )
+				d[j] = make_uint4(s0[4*j]   + __funnelshift_r(s1[4*j],   s1[4*j+1], 16),
+				                  s0[4*j+1] + __funnelshift_r(s1[4*j+1], s1[4*j+2], 16),
+				                  s0[4*j+2] + __funnelshift_r(s1[4*j+2], s1[4*j+3], 16),
+				                  s0[4*j+3] + __funnelshift_r(s1[4*j+3], s1[4*j+4], 16));
+	}
+}
+
 // One op: row = a + shift(b), operands in shared memory, result to shared
 // memory or to the pass output.
 template<int ESZ, int SRCK, int DSTK>
@@ -647,6 +801,12 @@ __device__ __forceinline__ void pk_levels(const PackedSmem& S, const PackedParam
 			const int4 op = nxt;
 			if( op.w == 0 ) break;
 			nxt = list[m + 1];                     // the last slot of a list is always a terminator
+			if( (SRCK == PK_SRC_BYTES) && (op.w & PK_GROUP4) ) {
+				pk_group4_op(op, nxt, S, tl, lane);    // two slots
+				++m;
+				nxt = list[m + 1];
+				continue;
+			}
 			pk_row_op<ESZ, SRCK, DSTK>(op, S, P, tl, lane, warp);
 		}
 		__syncthreads();
@@ -690,15 +850,16 @@ fdmt_packed_kernel(const __grid_constant__ PackedParams P) {
 // ---------------------------------------------------------------------------
 // One persistent kernel for the whole transform.
 //
-// Time is cut into chunks of C samples.  An item is one (pass, program, tile);
-// items are claimed from a global counter in rounds -- round r holds the tiles
-// of chunk r - lag*k of pass k -- so pass k+1 follows pass k by `lag` chunks
-// and the workspaces between passes are short RINGS in time that stay in L2.
-// A tile waits (acquire on a per-(pass, chunk) counter) for the producer chunks
-// its source window touches and, before it overwrites ring columns, for the
-// consumer chunks that still read the old contents.  Every item an item waits
-// for has a lower claim index (lag and the ring length are chosen for that on
-// the host), so the claimed prefix always makes progress.
+// Time is cut into chunks of C samples.  An item is one (pass, program, chunk):
+// the tiles of that program whose first sample lies in the chunk.  Items are
+// claimed from a global counter in rounds -- round r holds chunk r - lag*k of
+// pass k -- so pass k+1 follows pass k by `lag` chunks and the workspaces
+// between passes are short RINGS in time that stay in L2.  An item waits
+// (acquire on a per-(pass, chunk) counter) for the producer chunks its source
+// windows touch and, before it overwrites ring columns, for the consumer chunks
+// that still read the old contents.  Every item an item waits for has a lower
+// claim index (lag and the ring length are chosen for that on the host), so
+// the claimed prefix always makes progress.
 // ---------------------------------------------------------------------------
 struct MegaPass {
 	PackedParams p;
@@ -711,9 +872,10 @@ struct MegaParams {
 	MegaPass pass[PK_MAXPASS];
 	int  npass, lag, nchunk, ipr;
 	long t_ref, C, total;
-	const int* tmpl;  // [ipr]: pass << 29 | tile slot in chunk << 24 | program
-	int* counters;    // [0] next item, [1] CTAs gone, [2 + k*nchunk + j] finished tiles
+	const int* tmpl;  // [ipr]: pass << 24 | program
+	int* counters;    // [0] next item, [1] CTAs gone, [2 + k*nchunk + j] finished items
 };
+struct MegaItem { int k, prog, valid; long j, i0, i1; };
 
 namespace packed_dev {
 __device__ __forceinline__ long mega_ifirst(const MegaParams& M, int k, long j) {
@@ -725,22 +887,22 @@ __device__ __forceinline__ long mega_ifirst(const MegaParams& M, int k, long j) 
 __device__ __forceinline__ long mega_chunk_of_tile(const MegaParams& M, int k, long i) {
 	return (M.pass[k].p.t_begin + i * M.pass[k].p.T - M.t_ref) / M.C;
 }
-// Spins until every tile of chunks [jlo, jhi] of pass k has finished.
+// Spins until every item of chunks [jlo, jhi] of pass k has finished.
 __device__ __forceinline__ void mega_wait(const MegaParams& M, int k, long jlo, long jhi) {
 	for( long j=jlo; j<=jhi; ++j ) {
 		if( j < 0 || j >= M.nchunk ) continue;
-		const int target = (int)(mega_ifirst(M, k, j + 1) - mega_ifirst(M, k, j)) * M.pass[k].nprog;
 		const int* c = M.counters + 2 + (long)k * M.nchunk + j;
-		while( ld_acquire(c) < target ) __nanosleep(100);
+		while( ld_acquire(c) < M.pass[k].nprog ) __nanosleep(64);
 	}
 }
 template<int ESZ, int SRCK, int DSTK>
-__device__ __forceinline__ void mega_item(const PackedParams& P, int prog, long t0, unsigned char* smem,
+__device__ __forceinline__ void mega_item(const PackedParams& P, const MegaItem& it, unsigned char* smem,
                                           uint32_t& parity, int lane, int warp, int nwarp) {
 	const PackedSmem S = pk_carve<ESZ, DSTK>(smem, P, nwarp);
-	pk_load_tables(S, P, prog, nwarp);
+	pk_load_tables(S, P, it.prog, nwarp);
 	__syncthreads();
-	pk_tile<ESZ, SRCK, DSTK>(S, P, t0, 0, 0, 0, parity, lane, warp, nwarp);
+	for( long i=it.i0; i<it.i1; ++i )
+		pk_tile<ESZ, SRCK, DSTK>(S, P, P.t_begin + i * P.T, 0, 0, 0, parity, lane, warp, nwarp);
 }
 } // namespace packed_dev
 
@@ -748,7 +910,7 @@ __global__ void __launch_bounds__(256, 3)
 fdmt_packed_mega_kernel(const __grid_constant__ MegaParams M) {
 	using namespace packed_dev;
 	extern __shared__ __align__(16) unsigned char pk_smem[];
-	__shared__ long s_item;
+	__shared__ MegaItem s_item;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
 	if( threadIdx.x == 0 ) {
 		mbar_init((uint64_t*)pk_smem, 1);
@@ -757,55 +919,70 @@ fdmt_packed_mega_kernel(const __grid_constant__ MegaParams M) {
 	uint32_t parity = 0;
 	for(;;) {
 		__syncthreads();                                  // everyone is done with the previous item
-		if( threadIdx.x == 0 ) s_item = atomicAdd(M.counters, 1);
-		__syncthreads();
-		const long idx = s_item;
-		if( idx >= M.total ) break;
-		const long round = idx / M.ipr;
-		const int  e = __ldg(M.tmpl + (idx - round * M.ipr));
-		const int  k = (e >> 29) & 7, slot = (e >> 24) & 31, prog = e & 0xFFFFFF;
-		const long j = round - (long)M.lag * k;
-		if( j < 0 || j >= M.nchunk ) continue;
-		const MegaPass& mp = M.pass[k];
-		const long i = mega_ifirst(M, k, j) + slot;
-		if( i >= mega_ifirst(M, k, j + 1) ) continue;
-		const long t0 = mp.p.t_begin + i * mp.p.T;
 		if( threadIdx.x == 0 ) {
-			if( k > 0 ) {
-				// producer tiles under [t0 - lookback, t0 + T)
-				const MegaPass& pp = M.pass[k-1];
-				long lo = t0 - mp.lookback - pp.p.t_begin, hi = t0 + mp.p.T - 1 - pp.p.t_begin;
-				long ilo = lo <= 0 ? 0 : lo / pp.p.T, ihi = hi / pp.p.T;
-				if( ihi >= pp.nt ) ihi = pp.nt - 1;
-				mega_wait(M, k - 1, mega_chunk_of_tile(M, k - 1, ilo), mega_chunk_of_tile(M, k - 1, ihi));
-			}
-			if( k + 1 < M.npass ) {
-				// consumer tiles that read what this tile's columns held one ring turn ago
-				const MegaPass& cp = M.pass[k+1];
-				long lo = t0 - mp.p.dst_rl - cp.p.t_begin, hi = t0 + mp.p.T - 1 - mp.p.dst_rl + cp.lookback - cp.p.t_begin;
-				if( hi >= 0 ) {
-					long ilo = lo <= 0 ? 0 : lo / cp.p.T, ihi = hi / cp.p.T;
-					if( ihi >= cp.nt ) ihi = cp.nt - 1;
-					if( ilo <= ihi ) mega_wait(M, k + 1, mega_chunk_of_tile(M, k + 1, ilo), mega_chunk_of_tile(M, k + 1, ihi));
+			// claim, decode and wait: one thread does the arithmetic for the CTA
+			MegaItem it;
+			it.valid = 0; it.k = -1; it.prog = 0; it.j = 0; it.i0 = it.i1 = 0;
+			const long idx = atomicAdd(M.counters, 1);
+			if( idx < M.total ) {
+				const long round = idx / M.ipr;
+				const int  e = __ldg(M.tmpl + (idx - round * M.ipr));
+				it.k = e >> 24; it.prog = e & 0xFFFFFF;
+				it.j = round - (long)M.lag * it.k;
+				if( it.j >= 0 && it.j < M.nchunk ) {
+					const int k = it.k;
+					const MegaPass& mp = M.pass[k];
+					it.valid = 1;
+					it.i0 = mega_ifirst(M, k, it.j); it.i1 = mega_ifirst(M, k, it.j + 1);
+					if( it.i0 < it.i1 ) {
+						const long t_lo = mp.p.t_begin + it.i0 * mp.p.T;          // first output sample
+						const long t_hi = mp.p.t_begin + it.i1 * mp.p.T;          // one past the last
+						if( k > 0 ) {
+							// producer tiles under [t_lo - lookback, t_hi)
+							const MegaPass& pp = M.pass[k-1];
+							long lo = t_lo - mp.lookback - pp.p.t_begin, hi = t_hi - 1 - pp.p.t_begin;
+							long ilo = lo <= 0 ? 0 : lo / pp.p.T, ihi = hi / pp.p.T;
+							if( ihi >= pp.nt ) ihi = pp.nt - 1;
+							mega_wait(M, k - 1, mega_chunk_of_tile(M, k - 1, ilo), mega_chunk_of_tile(M, k - 1, ihi));
+						}
+						if( k + 1 < M.npass ) {
+							// consumer tiles that read what these columns held one ring turn ago
+							const MegaPass& cp = M.pass[k+1];
+							long lo = t_lo - mp.p.dst_rl - cp.p.t_begin;
+							long hi = t_hi - 1 - mp.p.dst_rl + cp.lookback - cp.p.t_begin;
+							if( hi >= 0 ) {
+								long ilo = lo <= 0 ? 0 : lo / cp.p.T, ihi = hi / cp.p.T;
+								if( ihi >= cp.nt ) ihi = cp.nt - 1;
+								if( ilo <= ihi ) mega_wait(M, k + 1, mega_chunk_of_tile(M, k + 1, ilo), mega_chunk_of_tile(M, k + 1, ihi));
+							}
+						}
+					}
 				}
 			}
 			__threadfence();
+			s_item = it;
 		}
 		__syncthreads();
-		switch( mp.kind ) {
-		case 0:  mega_item<2, PK_SRC_BYTES, PK_DST_SAME >(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
-		case 1:  mega_item<2, PK_SRC_BYTES, PK_DST_CVT  >(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
-		case 2:  mega_item<2, PK_SRC_BYTES, PK_DST_FINAL>(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
-		case 3:  mega_item<2, PK_SRC_SAME,  PK_DST_SAME >(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
-		case 4:  mega_item<2, PK_SRC_SAME,  PK_DST_CVT  >(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
-		case 5:  mega_item<2, PK_SRC_SAME,  PK_DST_FINAL>(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
-		case 6:  mega_item<4, PK_SRC_SAME,  PK_DST_SAME >(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
-		default: mega_item<4, PK_SRC_SAME,  PK_DST_FINAL>(mp.p, prog, t0, pk_smem, parity, lane, warp, nwarp); break;
+		const MegaItem it = s_item;
+		if( it.k < 0 ) break;                              // no items left
+		if( !it.valid ) continue;                          // chunk outside the gulp for this pass
+		if( it.i0 < it.i1 ) {
+			const MegaPass& mp = M.pass[it.k];
+			switch( mp.kind ) {
+			case 0:  mega_item<2, PK_SRC_BYTES, PK_DST_SAME >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			case 1:  mega_item<2, PK_SRC_BYTES, PK_DST_CVT  >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			case 2:  mega_item<2, PK_SRC_BYTES, PK_DST_FINAL>(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			case 3:  mega_item<2, PK_SRC_SAME,  PK_DST_SAME >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			case 4:  mega_item<2, PK_SRC_SAME,  PK_DST_CVT  >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			case 5:  mega_item<2, PK_SRC_SAME,  PK_DST_FINAL>(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			case 6:  mega_item<4, PK_SRC_SAME,  PK_DST_SAME >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			default: mega_item<4, PK_SRC_SAME,  PK_DST_FINAL>(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			}
+			// (pk_levels ends with a barrier: every store of the item has been issued)
 		}
-		// (pk_levels ends with a barrier: every store of the item has been issued)
 		if( threadIdx.x == 0 ) {
 			__threadfence();
-			atomicAdd(M.counters + 2 + (long)k * M.nchunk + j, 1);
+			atomicAdd(M.counters + 2 + (long)it.k * M.nchunk + it.j, 1);
 		}
 	}
 	if( threadIdx.x == 0 ) {

@@ -344,7 +344,8 @@ BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
  * header[0] = 0 when it does not apply, else header = {1, npass, lag, ipr,
  * nchunk, C, t_ref, then per pass: tb, nt, ring length of its output workspace
  * (0 for the last pass)} (7 + 3*npass longs; pass 32); tmpl (may be NULL)
- * receives ipr ints: pass << 29 | tile slot in chunk << 24 | program. */
+ * receives ipr ints: pass << 24 | program (one item per pass, program
+ * and chunk: the tiles of the program that start in the chunk). */
 BFstatus bfFdmtPackedMegaQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                               double exponent, long ntime, long* header, int* tmpl);
 

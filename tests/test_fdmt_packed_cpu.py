@@ -15,7 +15,7 @@ import pytest
 from bifrost_b200.libbifrost import _bf
 from oracle import fdmt as ofdmt
 
-NO_A, NO_B, STORE_G, BYTES = 1, 2, 4, 8
+NO_A, NO_B, STORE_G, BYTES, GROUP4 = 1, 2, 4, 8, 16
 WO_SHIFT, H_SHIFT, NVEC_SHIFT = 8, 10, 16
 POISON = -(1 << 40)
 
@@ -34,6 +34,8 @@ def query(nchan, md, f0, df):
         keys = ('s0 s1 nlev esize src_kind dst_kind T nprog nwarp slots src_slots data_bytes '
                 'lookback nrow_out smem_bytes nops').split()
         p = dict(zip(keys, (int(v) for v in h)))
+        p['fused'] = bool(p['nops'] >> 30)
+        p['nops'] &= (1 << 30) - 1
         ops = np.zeros((p['nprog'], p['nlev'], p['nwarp'], p['slots'], 4), np.int32)
         src = np.zeros((p['nprog'], p['src_slots'], 4), np.int32)
         ph = np.zeros((p['nprog'], 4), np.int32)
@@ -102,12 +104,37 @@ class Machine(object):
             assert srcs[nsrc][3] == 0
         for lev in range(1, p['nlev'] + 1):
             for warp in range(p['nwarp']):
-                for op in p['ops'][prog, lev - 1, warp]:
+                oplist = p['ops'][prog, lev - 1, warp]
+                skip = False
+                for m, op in enumerate(oplist):
+                    if skip:
+                        skip = False
+                        continue
                     dst, ay, bz, ctl = (int(v) for v in op)
                     if ctl == 0:
                         break
                     n = (ctl >> NVEC_SHIFT) * VS
                     assert n <= 32 * 3 * VS
+                    if ctl & GROUP4:
+                        # steps 1+2 fused: two slots, four input channels
+                        assert p['src_kind'] == 0 and lev == 1 and p['fused']
+                        dst1, f2, f3, ctl2 = (int(v) for v in oplist[m + 1])
+                        assert ctl2 & GROUP4
+                        skip = True
+
+                        def chan(field, back):
+                            k, e = field & 0xFFF, (field & 0xFFFFFFFF) >> 12
+                            assert k < nsrc and e - back >= 0 and e + n <= int(srcs[k][3])
+                            base = int(srcs[k][2])
+                            return data[base + e - back: base + e - back + n]
+                        s0 = chan(ay, 0) + chan(bz, 0)
+                        mask = (ctl >> WO_SHIFT) & 3
+                        for d, where in ((0, dst), (1, dst1)):
+                            if mask & (1 << d):
+                                r = s0 + chan(f2, d) + chan(f3, d)
+                                assert (r >= 0).all() and (r < 65536).all() and where % 16 == 0
+                                data[where: where + n * esz: esz] = r
+                        continue
                     if ctl & BYTES:
                         assert p['src_kind'] == 0 and lev == 1
                         def rd(field):
@@ -301,59 +328,58 @@ def run_persistent(x, passes, mg, out):
             r.append((int(e[:, 1].min()), int((e[:, 1] + e[:, 3]).max())))
         reach.append(r)
     done = np.zeros((n, nchunk), np.int64)
-    finished = [set() for _ in range(n)]           # (prog, tile) finished, per pass
-    target = [[(ifirst(k, j + 1) - ifirst(k, j)) * passes[k]['nprog'] for j in range(nchunk)] for k in range(n)]
     nround = nchunk + lag * (n - 1)
     executed = 0
+    amin = [min(r[0] for r in reach[k]) for k in range(n)]
     for rnd in range(nround):
         for e in mg['tmpl']:
-            e = int(e) & 0xFFFFFFFF
-            k, slot, prog = (e >> 29) & 7, (e >> 24) & 31, e & 0xFFFFFF
+            e = int(e)
+            k, prog = e >> 24, e & 0xFFFFFF
             j = rnd - lag * k
             if j < 0 or j >= nchunk:
                 continue
-            i = ifirst(k, j) + slot
-            if i >= ifirst(k, j + 1):
-                continue
-            t0 = tb[k] + i * T[k]
+            i0, i1 = ifirst(k, j), ifirst(k, j + 1)
             waited = {}
-            if k > 0:
-                lo, hi = t0 - passes[k]['lookback'] - tb[k - 1], t0 + T[k] - 1 - tb[k - 1]
-                ilo, ihi = (0 if lo <= 0 else lo // T[k - 1]), min(hi // T[k - 1], nt[k - 1] - 1)
-                waited[k - 1] = (chunk_of(k - 1, ilo), chunk_of(k - 1, ihi))
-                # true producers of this program's staged columns
-                a, b = reach[k][prog]
-                for ip in range(max(0, (t0 + a - tb[k - 1]) // T[k - 1]), (t0 + b - 1 - tb[k - 1]) // T[k - 1] + 1):
-                    assert waited[k - 1][0] <= chunk_of(k - 1, ip) <= waited[k - 1][1]
-            if k + 1 < n:
-                ring = mg['per'][k]['ring']
-                lo = t0 - ring - tb[k + 1]
-                hi = t0 + T[k] - 1 - ring + passes[k + 1]['lookback'] - tb[k + 1]
-                if hi >= 0:
-                    ilo, ihi = (0 if lo <= 0 else lo // T[k + 1]), min(hi // T[k + 1], nt[k + 1] - 1)
-                    if ilo <= ihi:
-                        waited[k + 1] = (chunk_of(k + 1, ilo), chunk_of(k + 1, ihi))
-                # true readers of the overwritten columns: consumer tiles whose staged
-                # times intersect [t0 - ring, t0 + T - ring)
-                old_lo, old_hi = t0 - ring, t0 + T[k] - ring
-                for ic in range(nt[k + 1]):
-                    tc = tb[k + 1] + ic * T[k + 1]
-                    a = min(r[0] for r in reach[k + 1])
-                    if tc + a >= old_hi:
-                        break
-                    if tc + T[k + 1] <= old_lo:
-                        continue
-                    w = waited.get(k + 1)
-                    assert w is not None and w[0] <= chunk_of(k + 1, ic) <= w[1]
+            if i0 < i1:
+                t_lo, t_hi = tb[k] + i0 * T[k], tb[k] + i1 * T[k]
+                if k > 0:
+                    lo, hi = t_lo - passes[k]['lookback'] - tb[k - 1], t_hi - 1 - tb[k - 1]
+                    ilo, ihi = (0 if lo <= 0 else lo // T[k - 1]), min(hi // T[k - 1], nt[k - 1] - 1)
+                    waited[k - 1] = (chunk_of(k - 1, ilo), chunk_of(k - 1, ihi))
+                    # true producers of this program's staged columns
+                    a, b = reach[k][prog]
+                    for ip in range(max(0, (t_lo + a - tb[k - 1]) // T[k - 1]),
+                                    (t_hi - T[k] + b - 1 - tb[k - 1]) // T[k - 1] + 1):
+                        assert waited[k - 1][0] <= chunk_of(k - 1, ip) <= waited[k - 1][1]
+                if k + 1 < n:
+                    ring = mg['per'][k]['ring']
+                    lo = t_lo - ring - tb[k + 1]
+                    hi = t_hi - 1 - ring + passes[k + 1]['lookback'] - tb[k + 1]
+                    if hi >= 0:
+                        ilo, ihi = (0 if lo <= 0 else lo // T[k + 1]), min(hi // T[k + 1], nt[k + 1] - 1)
+                        if ilo <= ihi:
+                            waited[k + 1] = (chunk_of(k + 1, ilo), chunk_of(k + 1, ihi))
+                    # true readers of the overwritten columns: consumer tiles whose staged
+                    # times intersect [t_lo - ring, t_hi - ring)
+                    old_lo, old_hi = t_lo - ring, t_hi - ring
+                    for ic in range(nt[k + 1]):
+                        tc = tb[k + 1] + ic * T[k + 1]
+                        if tc + amin[k + 1] >= old_hi:
+                            break
+                        if tc + T[k + 1] <= old_lo:
+                            continue
+                        w = waited.get(k + 1)
+                        assert w is not None and w[0] <= chunk_of(k + 1, ic) <= w[1]
             for kk, (jlo, jhi) in waited.items():
                 for jj in range(jlo, jhi + 1):
                     if 0 <= jj < nchunk:
-                        assert done[kk, jj] == target[kk][jj], "item claimed before what it waits for"
-            machines[k].run(prog, i)
+                        assert done[kk, jj] == passes[kk]['nprog'], "item claimed before what it waits for"
+            for i in range(i0, i1):
+                machines[k].run(prog, i)
+                executed += 1
             done[k, j] += 1
-            executed += 1
     assert executed == sum(nt[k] * passes[k]['nprog'] for k in range(n))
-    assert (done == np.array(target)).all()
+    assert all((done[k] == passes[k]['nprog']).all() for k in range(n))
 
 
 @pytest.mark.parametrize("nchan,md,f0,df,ntime,knobs", [

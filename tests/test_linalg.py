@@ -235,3 +235,56 @@ def test_invalid_forms_return_status():
     assert _bf.bfLinAlgMatMul(h.obj, 1.0, a.as_BFarray(), b.as_BFarray(), 0.0, c.as_BFarray()) == \
         _bf.BF_STATUS_INVALID_SHAPE
     assert _bf.bfLinAlgMatMul(h.obj, 1.0, None, None, 0.0, c.as_BFarray()) == _bf.BF_STATUS_INVALID_ARGUMENT
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ntime", [512, 2048, 8192])
+def test_baseline_config4_full_size_against_the_oracle(ntime):
+    """BASELINE config 4 at its real size: x ci8 [ntime, 512 chan, 256 stand x 2 pol],
+    C cf32 [512, 512, 512] (the shape bench / tools/bench_ops.py time), value-checked
+    on a channel subset -- integer-exact -- against oracle/linalg.py.  |C| stays
+    below 2^24 only for ntime <= 512 with full-range int8, so the longer
+    integrations draw from [-31, 31] (sums < 2^24: fp32-exact on both sides)."""
+    import torch
+    nchan, n = 512, 512
+    amp = 127 if ntime <= 512 else 31
+    g = torch.Generator(device='cuda').manual_seed(ntime)
+    raw = torch.randint(-amp, amp + 1, (ntime, nchan, n, 2), dtype=torch.int8, device='cuda', generator=g)
+    d_x = bf.ndarray(space='cuda', shape=(ntime, nchan, n), dtype='ci8', buffer=raw.data_ptr())   # zero-copy view
+    d_c = bf.zeros((nchan, n, n), 'cf32', 'cuda')
+    LinAlg().matmul(1, None, d_x.transpose((1, 0, 2)), 0, d_c)
+    chans = [0, 1, 255, 256, 300, 511]
+    got = np.stack([np.asarray(d_c[c:c + 1].copy('system'))[0] for c in chans])
+    sub = raw[:, chans].cpu().numpy()                                      # [ntime, 6, n, 2]
+    x = np.empty((len(chans), ntime, n), dtype=CI8)
+    x['re'] = np.transpose(sub[..., 0], (1, 0, 2))
+    x['im'] = np.transpose(sub[..., 1], (1, 0, 2))
+    want = olinalg.correlate(x)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_correlator_matches_the_reference_library():
+    """Same BFarray structs through the reference's own bfLinAlgMatMul
+    (oracle/_ref, src/linalg.cu:242-357 + linalg_kernels.cu) and ours."""
+    import ctypes
+    import reflib
+    ref = reflib.load()
+    if ref is None or not hasattr(ref, 'bfLinAlgMatMul'):
+        pytest.skip("oracle/_ref/libbifrost_ref.so not present")
+    from bifrost_b200.libbifrost import _check
+    rng = np.random.default_rng(77)
+    for (ntime, nchan, n) in [(64, 3, 32), (512, 4, 512), (200, 2, 130)]:
+        x = rand_ci8(rng, (ntime, nchan, n))
+        ours = run_bhb(x)
+        d_x = bf.asarray(x, space='cuda')
+        xv = d_x.transpose((1, 0, 2))
+        d_c = bf.zeros((nchan, n, n), 'cf32', 'cuda')
+        h = ctypes.c_void_p()
+        _check(ref.bfLinAlgCreate(ctypes.byref(h)))
+        _check(ref.bfLinAlgMatMul(h, 1.0, None, xv.as_BFarray(), 0.0, d_c.as_BFarray()))
+        _check(ref.bfStreamSynchronize())
+        theirs = np.asarray(d_c.copy('system'))
+        _check(ref.bfLinAlgDestroy(h))
+        il = np.tril_indices(n)
+        np.testing.assert_array_equal(ours[:, il[0], il[1]], theirs[:, il[0], il[1]])
