@@ -1,9 +1,10 @@
-"""correlate block (mirrors python/bifrost/blocks/correlate.py:37-138 ->
-bfLinAlgMatMul(a=NULL, b=x))."""
-from copy import deepcopy
-
+"""correlate block (same contract as python/bifrost/blocks/correlate.py:37-138;
+the data path is bfLinAlgMatMul(a=NULL, b=x): the int8 tensor-core correlator)."""
 from bifrost_b200.pipeline import TransformBlock
 from bifrost_b200.linalg import LinAlg
+from bifrost_b200.blocks import _header as H
+
+_IN_AXES = ['time', 'freq', 'station', 'pol']
 
 
 class CorrelateBlock(TransformBlock):
@@ -21,23 +22,28 @@ class CorrelateBlock(TransformBlock):
     def on_sequence(self, iseq):
         self.nframe_integrated = 0
         ihdr = iseq.header
-        itensor = ihdr['_tensor']
-        if itensor['labels'] != ['time', 'freq', 'station', 'pol']:
-            raise ValueError("Expected axes ['time', 'freq', 'station', 'pol'], got %s" % itensor['labels'])
-        ohdr = deepcopy(ihdr)
-        ot = ohdr['_tensor']
-        ot['dtype'] = 'cf32'
-        for key in ('shape', 'labels', 'scales', 'units'):
-            if key in ot:
-                time_, freq, stand, pol = itensor[key]
-                ot[key] = [time_, freq, stand, pol, deepcopy(stand), deepcopy(pol)]
-        ot['labels'] = ['time', 'freq', 'station_i', 'pol_i', 'station_j', 'pol_j']
-        if 'scales' in ot:
-            s = ot['scales'][0]
-            ot['scales'][0] = [s[0], s[1] * self.nframe_per_integration]
+        if ihdr['_tensor']['labels'] != _IN_AXES:
+            raise ValueError("Expected axes %s, got %s" % (_IN_AXES, ihdr['_tensor']['labels']))
+        ohdr, otensor = H.derive(ihdr)
+        otensor['dtype'] = 'cf32'
+        # [time, freq, station, pol] -> [time, freq, station_i, pol_i, station_j, pol_j]
+        H.remap_axes(ihdr['_tensor'], otensor, [0, 1, 2, 3, 2, 3])
+        otensor['labels'] = ['time', 'freq', 'station_i', 'pol_i', 'station_j', 'pol_j']
+        H.scale_step(otensor, 0, self.nframe_per_integration)
         ohdr['matrix_fill_mode'] = 'lower'
-        ohdr['gulp_nframe'] = 1
+        # an integration is made of whole input gulps: the gulp the block reads
+        # (its own setting, else the upstream one, capped at one integration) has
+        # to divide nframe_per_integration (blocks/correlate.py:67-74)
+        ohdr['gulp_nframe'] = min(ihdr.get('gulp_nframe') or 1, self.nframe_per_integration)
+        gulp = self.gulp_nframe or ohdr['gulp_nframe']
+        if self.nframe_per_integration % gulp:
+            raise ValueError("gulp_nframe (%i) does not divide nframe_per_integration (%i)"
+                             % (gulp, self.nframe_per_integration))
         return ohdr
+
+    def _gulp(self):
+        # the input is read in gulps that tile an integration
+        return self.gulp_nframe or min(self._iseq.header.get('gulp_nframe') or 1, self.nframe_per_integration)
 
     def on_data(self, ispan, ospan):
         idata, odata = ispan.data, ospan.data
@@ -45,10 +51,11 @@ class CorrelateBlock(TransformBlock):
         # [time, freq, stand*pol] -> [freq, time, stand*pol] view; out [freq, n, n]
         x = idata.reshape(ntime, nchan, nstand * npol).transpose(1, 0, 2)
         c = odata.reshape(nchan, nstand * npol, nstand * npol)
-        beta = 0. if self.nframe_integrated == 0 else 1.
-        self.linalg.matmul(1., None, x, beta, c)
+        self.linalg.matmul(1., None, x, 1. if self.nframe_integrated else 0., c)
         self.nframe_integrated += ispan.nframe
-        if self.nframe_integrated >= self.nframe_per_integration:
+        if self.nframe_integrated > self.nframe_per_integration:
+            raise RuntimeError("integration overran: gulp does not tile nframe_per_integration")
+        if self.nframe_integrated == self.nframe_per_integration:
             self.nframe_integrated = 0
             return 1
         return 0

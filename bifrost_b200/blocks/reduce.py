@@ -1,9 +1,10 @@
-"""reduce block (mirrors python/bifrost/blocks/reduce.py:38-118 -> bfReduce)."""
-from copy import deepcopy
-
+"""reduce block (same contract as python/bifrost/blocks/reduce.py:38-118; the
+data path is bfReduce)."""
 from bifrost_b200.pipeline import TransformBlock
-from bifrost_b200.DataType import DataType
 from bifrost_b200.reduce import reduce as bf_reduce
+from bifrost_b200.blocks import _header as H
+
+_COMPLEX_IN = ('cf32', 'ci8', 'ci16')
 
 
 class ReduceBlock(TransformBlock):
@@ -21,31 +22,26 @@ class ReduceBlock(TransformBlock):
 
     def on_sequence(self, iseq):
         ihdr = iseq.header
-        itensor = ihdr['_tensor']
-        ohdr = deepcopy(ihdr)
-        otensor = ohdr['_tensor']
-        otensor['dtype'] = 'f32'
-        if itensor['dtype'] in ['cf32', 'ci8', 'ci16'] and not self.op.startswith('pwr'):
-            otensor['dtype'] = 'cf32'
-        self.axis = (itensor['labels'].index(self.specified_axis)
-                     if isinstance(self.specified_axis, str) else self.specified_axis)
-        frame_axis = itensor['shape'].index(-1)
-        self.frame_factor = 1
-        self.factor = self.specified_factor
-        if self.axis == frame_axis:
+        ohdr, otensor = H.derive(ihdr)
+        # power ops give real output; plain ops keep complex input complex
+        keeps_complex = ihdr['_tensor']['dtype'] in _COMPLEX_IN and not self.op.startswith('pwr')
+        otensor['dtype'] = 'cf32' if keeps_complex else 'f32'
+        self.axis = H.axis_index(otensor, self.specified_axis)
+        self.factor, self.frame_factor = self.specified_factor, 1
+        if self.axis == H.frame_axis(otensor):
+            # along time: fewer frames come out, the shape entry stays -1
             if self.factor is None:
                 raise ValueError("Cannot reduce all of the frame axis")
             self.frame_factor = self.factor
             ohdr['gulp_nframe'] = max((ihdr.get('gulp_nframe') or self.factor) // self.factor, 1)
         else:
+            length = otensor['shape'][self.axis]
             if self.factor is None:
-                self.factor = otensor['shape'][self.axis]
-            if otensor['shape'][self.axis] % self.factor:
+                self.factor = length
+            if length % self.factor:
                 raise ValueError("Reduce factor does not divide axis length")
-            otensor['shape'][self.axis] //= self.factor
-        if 'scales' in otensor:
-            s = otensor['scales'][self.axis]
-            otensor['scales'][self.axis] = [s[0], s[1] * self.factor]
+            otensor['shape'][self.axis] = length // self.factor
+        H.scale_step(otensor, self.axis, self.factor)
         return ohdr
 
     def on_data(self, ispan, ospan):

@@ -1,8 +1,8 @@
-"""transpose block (mirrors python/bifrost/blocks/transpose.py:38-92 -> bfTranspose)."""
-from copy import deepcopy
-
+"""transpose block (same contract as python/bifrost/blocks/transpose.py:38-92;
+the data path is bfTranspose)."""
 from bifrost_b200.pipeline import TransformBlock
 from bifrost_b200.transpose import transpose as bf_transpose
+from bifrost_b200.blocks import _header as H
 
 
 class TransposeBlock(TransformBlock):
@@ -14,15 +14,10 @@ class TransposeBlock(TransformBlock):
         return ('cuda',)          # the reference's numpy fallback for 'system' is not part of the hot path
 
     def on_sequence(self, iseq):
-        ihdr = iseq.header
-        itensor = ihdr['_tensor']
-        self.axes = [itensor['labels'].index(ax) if isinstance(ax, str) else ax
-                     for ax in self.specified_axes]
-        ohdr = deepcopy(ihdr)
-        otensor = ohdr['_tensor']
-        for item in ('shape', 'labels', 'scales', 'units'):
-            if item in itensor:
-                otensor[item] = [itensor[item][ax] for ax in self.axes]
+        ohdr, otensor = H.derive(iseq.header)
+        itensor = iseq.header['_tensor']
+        self.axes = [H.axis_index(itensor, ax) for ax in self.specified_axes]
+        H.remap_axes(itensor, otensor, self.axes)
         return ohdr
 
     def on_data(self, ispan, ospan):

@@ -203,3 +203,37 @@ def test_block_scope_and_space_validation():
             assert 'space' in str(e)
         else:
             raise AssertionError("system-space input to a cuda-only block must be rejected")
+
+
+def test_correlate_block_header_and_gulp_contract():
+    """blocks/correlate.py:51-74 of the reference: six-axis output tensor, time
+    step scaled by the integration length, gulp capped at one integration and
+    required to divide it."""
+    import pytest
+    from bifrost_b200 import blocks
+
+    class Seq(object):
+        def __init__(self, gulp):
+            self.header = {'_tensor': {'dtype': 'ci8', 'shape': [-1, 4, 16, 2],
+                                       'labels': ['time', 'freq', 'station', 'pol'],
+                                       'scales': [[0, 1e-3], [100.0, 0.1], None, None],
+                                       'units': ['s', 'MHz', None, None]},
+                           'name': 'corr', 'gulp_nframe': gulp}
+
+    with Pipeline():
+        src = array_source(np.zeros((4, 4, 16, 2), dtype=bf.DataType('ci8').as_numpy_dtype()), Seq(32).header, gulp_nframe=32)
+        blk = blocks.correlate(src, nframe_per_integration=96)
+    ohdr = blk.on_sequence(Seq(32))
+    t = ohdr['_tensor']
+    assert t['dtype'] == 'cf32' and t['shape'] == [-1, 4, 16, 2, 16, 2]
+    assert t['labels'] == ['time', 'freq', 'station_i', 'pol_i', 'station_j', 'pol_j']
+    assert t['scales'][0] == [0, 1e-3 * 96] and t['units'] == ['s', 'MHz', None, None, None, None]
+    assert ohdr['matrix_fill_mode'] == 'lower' and ohdr['gulp_nframe'] == 32
+    assert blk.on_sequence(Seq(200))['gulp_nframe'] == 96        # capped at one integration
+    with pytest.raises(ValueError):
+        blk.on_sequence(Seq(40))                                  # 40 does not divide 96
+    blk.gulp_nframe = 48                                          # the user's own gulp wins
+    assert blk.on_sequence(Seq(40))['gulp_nframe'] == 40
+    blk.gulp_nframe = 36
+    with pytest.raises(ValueError):
+        blk.on_sequence(Seq(32))
