@@ -45,8 +45,12 @@ def _scope_stack():
 class block_scope(object):
     """Attribute scope inherited by blocks created inside it (gulp_nframe,
     buffer_nframe, buffer_factor, core, gpu, share_temp_storage, fuse) --
-    pipeline.py:84-134.  ``fuse=True`` lets chains that have a fused kernel
-    (see blocks.spectrometer) collapse into one launch."""
+    pipeline.py:84-134.  ``gpu`` selects the device of the blocks' thread;
+    ``fuse=True`` collapses chains that have a fused kernel into one launch
+    (Pipeline._fuse_chains); ``core``, ``buffer_factor`` and
+    ``share_temp_storage`` configure the reference's thread-per-block ring
+    scheduler, which this synchronous executor does not have: they are accepted
+    and have no effect here."""
 
     def __init__(self, **kwargs):
         self.kwargs = kwargs
@@ -77,9 +81,65 @@ class Pipeline(object):
         _tls.pipeline_stack.pop()
 
     def run(self):
+        self._fuse_chains()
         sources = [b for b in self.blocks if isinstance(b, SourceBlock)]
         for src in sources:
             src._run()
+
+    def _fuse_chains(self):
+        """Honours ``block_scope(fuse=True)`` (pipeline.py:84-134 of the reference,
+        where the flag only removes the ring between blocks): a chain
+            transpose(['time','pol','freq','fine_time']) -> fft('fine_time', apply_fftshift=True)
+            -> detect('stokes') -> [merge_axes('freq', ...)] -> reduce('freq', f) -> accumulate(n)
+        whose blocks were all created under fuse=True, each feeding only the next,
+        is replaced by one SpectrometerBlock (one kernel launch per gulp,
+        bfSpectrometerFused) between the chain's input and output rings."""
+        from bifrost_b200.blocks.transpose import TransposeBlock
+        from bifrost_b200.blocks.fft import FftBlock
+        from bifrost_b200.blocks.detect import DetectBlock
+        from bifrost_b200.blocks.reduce import ReduceBlock
+        from bifrost_b200.blocks.accumulate import AccumulateBlock
+        from bifrost_b200.blocks.spectrometer import SpectrometerBlock
+
+        def only_consumer(ring, through_views=False):
+            """The single block reading `ring` (optionally through one header view)."""
+            if len(ring.consumers) == 1 and not ring.views:
+                return ring.consumers[0]
+            if through_views and not ring.consumers and len(ring.views) == 1:
+                return only_consumer(ring.views[0])
+            return None
+
+        for t in [b for b in self.blocks if isinstance(b, TransposeBlock) and b.fuse]:
+            if list(t.specified_axes) != ['time', 'pol', 'freq', 'fine_time']:
+                continue
+            f = only_consumer(t.orings[0])
+            if not (isinstance(f, FftBlock) and f.fuse and f.specified_axes == ['fine_time'] and f.apply_fftshift
+                    and not f.inverse and not f.real_output):
+                continue
+            d = only_consumer(f.orings[0])
+            if not (isinstance(d, DetectBlock) and d.fuse and d.mode == 'stokes' and d.specified_axis in (None, 'pol')):
+                continue
+            r = only_consumer(d.orings[0], through_views=True)
+            if not (isinstance(r, ReduceBlock) and r.fuse and r.specified_axis == 'freq' and r.op == 'sum'
+                    and r.specified_factor in (1, 2, 4, 8, 16, 32)):
+                continue
+            a = only_consumer(r.orings[0])
+            if not (isinstance(a, AccumulateBlock) and a.fuse and a.dtype in (None, 'f32')):
+                continue
+            iring, oring = t.irings[0], a.orings[0]
+            if not hasattr(_tls, 'pipeline_stack'):
+                _tls.pipeline_stack = [Pipeline()]
+            _tls.pipeline_stack.append(self)
+            try:
+                spec = SpectrometerBlock(iring, f_avg=r.specified_factor, n_int=a.nframe,
+                                         gulp_nframe=t.gulp_nframe, gpu=t.gpu, core=t.core)
+            finally:
+                _tls.pipeline_stack.pop()
+            iring.consumers.remove(t)
+            spec.orings = [oring]
+            oring.owner = spec
+            for b in (t, f, d, r, a):
+                self.blocks.remove(b)
 
     def shutdown(self):
         pass

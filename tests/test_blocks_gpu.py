@@ -65,11 +65,41 @@ def test_guppi_chain_unfused_vs_fused_vs_oracle():
     assert a.shape == (nframe // n_int, 4, nchan * nfft // f_avg) == b_.shape
     want = np.stack([oracle_chain(x[i * n_int:(i + 1) * n_int], f_avg) for i in range(nframe // n_int)])
     scale = np.sqrt(np.mean(want[:, 0] ** 2))
-    assert np.abs(a - want).max() <= 2e-5 * scale
-    assert np.abs(b_ - want).max() <= 2e-5 * scale
+    assert np.abs(a - want).max() <= 1e-5 * scale
+    assert np.abs(b_ - want).max() <= 1e-5 * scale
     t = unfused.headers[0]['_tensor']
     assert t['labels'] == ['time', 'pol', 'freq'] and t['shape'] == [-1, 4, nchan * nfft // f_avg]
     assert fused.headers[0]['_tensor']['shape'] == t['shape']
+
+
+def test_fuse_scope_runs_the_chain_as_one_kernel():
+    """The same chain written block by block under block_scope(fuse=True): the
+    executor swaps in the fused kernel (one launch per gulp) and the result is
+    the oracle's."""
+    nframe, nchan, nfft, f_avg, n_int = 8, 4, 4096, 4, 4
+    x = make_voltages(nframe, nchan, nfft, 43)
+    out = Collect()
+    with Pipeline() as p:
+        src = blocks.array_source(x, guppi_header(nchan, nfft), gulp_nframe=2)
+        b = blocks.copy(src, space='cuda')
+        with bf.block_scope(fuse=True):
+            c = blocks.transpose(b, ['time', 'pol', 'freq', 'fine_time'])
+            c = blocks.fft(c, axes='fine_time', axis_labels='fine_freq', apply_fftshift=True)
+            c = blocks.detect(c, mode='stokes')
+            c = views.merge_axes(c, 'freq', 'fine_freq')
+            c = blocks.reduce(c, 'freq', f_avg)
+            c = blocks.accumulate(c, n_int)
+        c = blocks.copy(c, space='cuda_host')
+        blocks.callback_sink(c, out.seq, out.data)
+        before = bf.launch_count()
+        p.run()
+        launches = bf.launch_count() - before
+    assert 'SpectrometerBlock' in [type(b).__name__ for b in p.blocks]
+    assert launches <= nframe // 2 + 2                 # one fused launch per 2-frame gulp (copies launch nothing)
+    got = np.concatenate(out.chunks, 0)
+    want = np.stack([oracle_chain(x[i * n_int:(i + 1) * n_int], f_avg) for i in range(nframe // n_int)])
+    assert np.abs(got - want).max() <= 1e-5 * np.sqrt(np.mean(want[:, 0] ** 2))
+    assert out.headers[0]['_tensor']['labels'] == ['time', 'pol', 'freq']
 
 
 def test_fdmt_block_with_overlap_equals_one_big_transform():

@@ -237,3 +237,46 @@ def test_correlate_block_header_and_gulp_contract():
     blk.gulp_nframe = 36
     with pytest.raises(ValueError):
         blk.on_sequence(Seq(32))
+
+
+def test_fuse_scope_collapses_the_guppi_chain():
+    """block_scope(fuse=True): transpose -> fft -> detect -> merge_axes -> reduce ->
+    accumulate becomes one SpectrometerBlock between the same rings; a chain that
+    is not all inside the scope is left alone (structure only: nothing runs)."""
+    from bifrost_b200 import blocks, views
+    from bifrost_b200.blocks.spectrometer import SpectrometerBlock
+    hdr = {'_tensor': {'dtype': 'ci8', 'shape': [-1, 4, 4096, 2], 'labels': ['time', 'freq', 'fine_time', 'pol'],
+                       'scales': [[0, 1.], [1200.0, 100.0], [0, 1e-8], None], 'units': ['s', 'MHz', 's', None]},
+           'name': 'guppi', 'gulp_nframe': 1}
+    x = np.zeros((2, 4, 4096, 2), dtype=bf.DataType('ci8').as_numpy_dtype())
+
+    def build(fuse_all):
+        seen = []
+        p = Pipeline()
+        with p:
+            src = array_source(x, hdr, gulp_nframe=1)
+            with bf.block_scope(fuse=True):
+                c = blocks.transpose(src, ['time', 'pol', 'freq', 'fine_time'])
+                c = blocks.fft(c, axes='fine_time', axis_labels='fine_freq', apply_fftshift=True)
+                c = blocks.detect(c, mode='stokes')
+                c = views.merge_axes(c, 'freq', 'fine_freq')
+                c = blocks.reduce(c, 'freq', 4)
+                if fuse_all:
+                    c = blocks.accumulate(c, 8)
+            if not fuse_all:
+                c = blocks.accumulate(c, 8)
+            sink = callback_sink(c, None, lambda s: seen.append(s))
+        return p, src, sink
+
+    p, src, sink = build(True)
+    p._fuse_chains()
+    kinds = [type(b).__name__ for b in p.blocks]
+    assert kinds.count('SpectrometerBlock') == 1
+    assert not {'TransposeBlock', 'FftBlock', 'DetectBlock', 'ReduceBlock', 'AccumulateBlock'} & set(kinds)
+    spec = [b for b in p.blocks if isinstance(b, SpectrometerBlock)][0]
+    assert spec.f_avg == 4 and spec.n_int == 8
+    assert src.orings[0].consumers == [spec] and spec.orings[0].consumers == [sink]
+    p, src, sink = build(False)
+    p._fuse_chains()
+    kinds = [type(b).__name__ for b in p.blocks]
+    assert 'SpectrometerBlock' not in kinds and 'FftBlock' in kinds
