@@ -908,7 +908,10 @@ static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int
 		for( int p=0; p<cps[k].nprog; ++p ) tmpl_->push_back((k << 24) | p);
 	}
 	*C_ = C;
-	*lag_ = 1 + (int)div_up<long>(tmax, C);
+	// pass k+1 follows pass k by `lag` chunks: one more than the reach of a tile
+	// is enough for the claim order to be valid; a longer lag keeps the consumers
+	// away from producers that are still running (about 1.5 rounds are in flight)
+	*lag_ = std::max(1 + (int)div_up<long>(tmax, C), env_int("BFB_FDMT_PACKED_LAG", 1 + (int)div_up<long>(tmax, C)));
 	return true;
 }
 static bool build_mega_template(BFfdmt_impl* plan) {
