@@ -711,6 +711,8 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 	std::vector<int> NWs  = env_int_list("BFB_FDMT_PACKED_WARPS");
 	std::vector<int> SMs  = env_int_list("BFB_FDMT_PACKED_SMEM_KB");
 	std::vector<int> TCs  = env_int_list("BFB_FDMT_PACKED_TCAP");
+	std::vector<int> PFs  = env_int_list("BFB_FDMT_PACKED_PREFETCH");
+	std::vector<int> LVs  = env_int_list("BFB_FDMT_PACKED_LV");
 	// step-0 row -> input channel
 	std::vector<int> src_index(P.nrow(0), -1);
 	for( size_t c=0; c<P.bands[0].size(); ++c )
@@ -737,6 +739,8 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : 74);
 		cfg.tcap    = pi < TCs.size() ? std::max(64, TCs[pi]) : (1 << 20);
 		cfg.fuse4   = env_int("BFB_FDMT_PACKED_FUSE", 1) != 0;
+		cfg.own_src = pi < PFs.size() ? PFs[pi] != 0 : (s0 == 1);    // default: the first pass (it reads HBM)
+		cfg.lv      = (pi < LVs.size() && LVs[pi] == 5) ? 5 : 3;
 		PackedPass cp;
 		bool ok = false;
 		// smaller delay blocks first (more programs, a little more redundancy),
@@ -834,16 +838,16 @@ static size_t packed_geometry(std::vector<PackedPass> const& passes, long ntime,
 	return std::max<size_t>(off, 512);
 }
 
-template<int ESZ, int SRCK, int DSTK>
+template<int ESZ, int SRCK, int DSTK, int LV>
 static cudaError_t launch_packed_kernel(PackedParams const& q, dim3 grid, int threads, size_t smem, cudaStream_t st) {
 	static size_t attr_smem = 0;
 	if( smem > attr_smem ) {
-		cudaError_t e = cudaFuncSetAttribute(fdmt_packed_kernel<ESZ, SRCK, DSTK>,
+		cudaError_t e = cudaFuncSetAttribute(fdmt_packed_kernel<ESZ, SRCK, DSTK, LV>,
 		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if( e != cudaSuccess ) return e;
 		attr_smem = smem;
 	}
-	fdmt_packed_kernel<ESZ, SRCK, DSTK><<<grid, threads, smem, st>>>(q);
+	fdmt_packed_kernel<ESZ, SRCK, DSTK, LV><<<grid, threads, smem, st>>>(q);
 	return cudaGetLastError();
 }
 
@@ -865,7 +869,9 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 	const int threads = cp.nwarp * 32;
 	const size_t smem = cp.smem_bytes();
 	cudaError_t e = cudaErrorInvalidValue;
-#define BFB_CH_LAUNCH(E_, S_, D_) e = launch_packed_kernel<E_, S_, D_>(q, grid, threads, smem, st)
+#define BFB_CH_LAUNCH(E_, S_, D_) \
+	e = (cp.lv == 5 && S_ != PK_SRC_BYTES) ? launch_packed_kernel<E_, (S_ == PK_SRC_BYTES ? PK_SRC_SAME : S_), D_, 5>(q, grid, threads, smem, st) \
+	                                        : launch_packed_kernel<E_, S_, D_, 3>(q, grid, threads, smem, st)
 	if( cp.esize == 2 ) {
 		if( cp.src_kind == PK_SRC_BYTES ) {
 			if(      cp.dst_kind == PK_DST_SAME ) BFB_CH_LAUNCH(2, PK_SRC_BYTES, PK_DST_SAME);
@@ -889,7 +895,8 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 
 // ---- persistent single-launch form -------------------------------------------
 static int mega_kind(PackedPass const& cp) {
-	return cp.esize == 2 ? cp.src_kind * 3 + cp.dst_kind : (cp.dst_kind == PK_DST_FINAL ? 7 : 6);
+	int kind = cp.esize == 2 ? cp.src_kind * 3 + cp.dst_kind : (cp.dst_kind == PK_DST_FINAL ? 7 : 6);
+	return kind + (cp.lv == 5 ? 8 : 0);
 }
 // Items of one round: every (pass, program, tile slot of a chunk), ordered by
 // the slot's time offset so the passes advance together (the final pass, which
@@ -1105,9 +1112,10 @@ BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	if( pass < 0 ) { header[0] = ok ? (int)cps.size() : 0; return BF_STATUS_SUCCESS; }
 	BFB_ASSERT(ok && pass < (int)cps.size(), BF_STATUS_INVALID_ARGUMENT);
 	PackedPass const& cp = cps[pass];
-	int h[16] = { cp.s0, cp.s1, cp.nlev, cp.esize, cp.src_kind, cp.dst_kind, cp.T, cp.nprog,
+	int h[24] = { cp.s0, cp.s1, cp.nlev, cp.esize, cp.src_kind, cp.dst_kind, cp.T, cp.nprog,
 	              cp.nwarp, cp.slots, cp.src_slots, cp.data_bytes, cp.lookback, cp.nrow_out,
-	              (int)cp.smem_bytes(), (int)std::min<long>(cp.nops, 1L << 30) | (cp.fused ? (1 << 30) : 0) };
+	              (int)cp.smem_bytes(), (int)std::min<long>(cp.nops, 1L << 30), cp.lv, cp.fused ? 1 : 0,
+	              cp.prefetch ? 1 : 0, 0, 0, 0, 0, 0 };
 	memcpy(header, h, sizeof(h));
 	if( ops ) memcpy(ops, cp.ops.data(), cp.ops.size() * sizeof(int4));
 	if( src ) memcpy(src, cp.src.data(), cp.src.size() * sizeof(int4));
@@ -1400,6 +1408,7 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 				q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
 				q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
 				q.is_signed = (in->dtype == BF_DTYPE_I8);
+				q.prefetch = cp.prefetch ? 1 : 0;
 				mp.kind = mega_kind(cp); mp.nprog = cp.nprog; mp.lookback = cp.lookback; mp.nt = geom[k].nt;
 			}
 			long grid = std::min<long>(M.total, (long)mega_blocks_per_sm * mega_sms);
@@ -1431,6 +1440,7 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 			q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
 			q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
 			q.is_signed = (in->dtype == BF_DTYPE_I8);
+			q.prefetch = cp.prefetch ? 1 : 0;
 			q.src_rl = k > 0 ? geom[k-1].stride : 1;           // linear workspaces: the rings never wrap
 			q.dst_rl = k == npass - 1 ? (1L << 62) : geom[k].stride;
 			BFstatus ls = launch_packed_pass(cp, q, nbatch, cst);

@@ -28,7 +28,8 @@
 // constant offsets (no delay logic in the kernel): a warp per row, lane l owns
 // three 16-byte vectors (24 u16 / 12 fp32 samples; the 48-byte lane stride
 // keeps 128-bit accesses conflict-free), a is vector-aligned, b's sub-vector
-// shift is a funnel shift.  Levels ping-pong between two shared regions.
+// shift is a funnel shift.  Merged levels ping-pong between two shared regions;
+// the staged source has a third, so the next tile's rows are fetched meanwhile.
 //
 // SOURCES.  All global->shared staging is TMA (cp.async.bulk + mbarrier):
 // workspace rows are 16-byte aligned by construction; rows of the 1-byte input
@@ -64,7 +65,7 @@ enum {
 	PK_H_SHIFT  = 10,        // 16-bit passes: odd sample shift
 	PK_NVEC_SHIFT = 16,      // row window in 16-byte vectors
 	PK_MAXLEV  = 6,
-	PK_LV      = 3,          // 16-byte vectors per lane per row
+	PK_LV_BYTES = 3,         // 16-byte vectors per lane per row in the pass that reads the 1-byte input
 	PK_MAXPASS = 6,
 };
 enum { PK_SRC_BYTES = 0, PK_SRC_SAME = 1 };
@@ -76,12 +77,16 @@ struct PackedCfg {
 	int smem_cap = 74 * 1024;
 	int tcap = 1 << 20;      // upper bound on T
 	bool fuse4 = true;       // fuse the first two steps of a byte pass where the plan allows
+	bool own_src = true;     // the staged source gets a shared-memory region of its own (next-tile prefetch)
+	int lv = 3;              // 16-byte vectors per lane per row (odd: conflict-free lane stride); 3 or 5
 };
 
 struct PackedPass {
 	int s0 = 0, s1 = 0, nlev = 0;
 	int esize = 2;           // 2: packed u16 accumulators, 4: fp32
 	bool fused = false;      // byte pass: op level 1 produces the rows of step s0+1 (PK_GROUP4)
+	bool prefetch = false;   // the source has its own region: the next tile's rows are requested early
+	int lv = 3;              // 16-byte vectors per lane per row
 	int src_kind = PK_SRC_SAME, dst_kind = PK_DST_SAME;
 	int T = 0, nprog = 0, nwarp = 0, slots = 0, src_slots = 0;
 	int data_bytes = 0;      // shared-memory data region
@@ -98,7 +103,7 @@ struct PackedPass {
 	}
 	size_t smem_bytes() const {
 		size_t b = table_bytes();
-		if( dst_kind == PK_DST_FINAL ) b += (size_t)nwarp * 32 * PK_LV * vs() * sizeof(float);
+		if( dst_kind == PK_DST_FINAL ) b += (size_t)nwarp * 32 * lv * vs() * sizeof(float);
 		return b + (size_t)data_bytes;
 	}
 };
@@ -162,7 +167,9 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 	using namespace packed_detail;
 	if( s0 < 1 || s1 < s0 || s1 >= P.nstep() || s1 - s0 + 1 > PK_MAXLEV ) PK_FAIL(1);
 	const int nlev = s1 - s0 + 1;
-	const int VS = 16 / esize, LS = PK_LV * VS, WLEN = 32 * LS;
+	const int LV = (src_kind == PK_SRC_BYTES) ? (int)PK_LV_BYTES : cfg.lv;
+	if( LV != 3 && LV != 5 ) PK_FAIL(13);
+	const int VS = 16 / esize, LS = LV * VS, WLEN = 32 * LS;
 	const int nwarp = cfg.nwarp;
 	const bool bytes = (src_kind == PK_SRC_BYTES);
 	// programs: blocks of used rows of each step-s1 band, heavy ones first (their
@@ -245,7 +252,7 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 	// input channels and step s0 has no rows of its own
 	const int nopl = fuse ? nlev - 1 : nlev;
 	auto step_level = [&](int ol) { return fuse ? ol + 1 : ol; };     // op level -> tree level
-	cp->s0 = s0; cp->s1 = s1; cp->nlev = nopl; cp->esize = esize; cp->fused = fuse;
+	cp->s0 = s0; cp->s1 = s1; cp->nlev = nopl; cp->esize = esize; cp->fused = fuse; cp->prefetch = cfg.own_src; cp->lv = LV;
 	cp->src_kind = src_kind; cp->dst_kind = dst_kind;
 	cp->T = T; cp->nprog = (int)progs.size(); cp->nwarp = nwarp; cp->lookback = lookback;
 	int slots = 1, src_slots = 1;
@@ -272,11 +279,13 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 	int data_max = 0;
 	for( size_t p=0; p<progs.size(); ++p ) {
 		std::vector<std::map<int, Win> >& need = needs[p];
-		// shared-memory layout (bytes): stored levels alternate between two
-		// regions -- a level is read only by the next one.  Stored levels: the
-		// source (tree level 0) and the rows of op levels 1 .. nopl-1.
+		// shared-memory layout (bytes).  Stored levels: the source (tree level 0)
+		// and the rows of op levels 1 .. nopl-1.  The source has a region of its
+		// own (the next tile's rows are requested while this tile is merged); the
+		// merged levels alternate between two regions -- a level is read only by
+		// the next one.
 		std::vector<std::map<int, int> > off(nlev), slot_of(1);
-		int region[2] = {0, 0};
+		int region[3] = {0, 0, 0};                       // [0], [1]: merged rows, alternating; [2]: the source
 		for( int sl=0; sl<nopl; ++sl ) {                 // stored level sl holds tree level li
 			const int li = sl == 0 ? 0 : step_level(sl);
 			int o = 0, k = 0;
@@ -289,13 +298,16 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 				// plus the look-ahead of the last lane; word rows: two vectors of slack
 				o += (li == 0 && bytes) ? round_up<int>(len + 16 + 16, 16) : (len + 2 * VS) * esize;
 			}
-			region[sl & 1] = std::max(region[sl & 1], o);
+			const int rg = (sl == 0 && cfg.own_src) ? 2 : (sl & 1);
+			region[rg] = std::max(region[rg], o);
 		}
-		for( int sl=1; sl<nopl; sl+=2 ) {
-			const int li = step_level(sl);
-			for( std::map<int, int>::iterator it=off[li].begin(); it!=off[li].end(); ++it ) it->second += region[0];
+		// layout: [source (if it has its own region)][even stored levels][odd stored levels]
+		for( int sl=(cfg.own_src ? 1 : 0); sl<nopl; ++sl ) {
+			const int li = sl == 0 ? 0 : step_level(sl);
+			const int base = region[2] + ((sl & 1) ? region[0] : 0);
+			if( base ) for( std::map<int, int>::iterator it=off[li].begin(); it!=off[li].end(); ++it ) it->second += base;
 		}
-		data_max = std::max(data_max, region[0] + region[1]);
+		data_max = std::max(data_max, region[0] + region[1] + region[2]);
 		// source table
 		long staged = 0;
 		{
@@ -379,7 +391,7 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 			}
 		}
 	}
-	cp->data_bytes = data_max + (32 * PK_LV + 4) * 16;     // slack: lanes past a row's end still load
+	cp->data_bytes = data_max + (32 * LV + 4) * 16;        // slack: lanes past a row's end still load
 	if( cp->smem_bytes() > (size_t)cfg.smem_cap ) PK_FAIL(12);
 	return true;
 }
@@ -398,6 +410,7 @@ struct PackedParams {
 	long ntile;
 	int  T, nlev, slots, src_slots;
 	int  is_signed;
+	int  prefetch;                                   // the source region is not reused by merged rows
 	long src_rl, dst_rl;                             // ring lengths (columns) of the workspaces; >= width: linear
 };
 
@@ -443,9 +456,9 @@ template<int ESZ> __device__ __forceinline__ uint32_t pk_add(uint32_t a, uint32_
 	return __float_as_uint(__fadd_rn(__uint_as_float(a), __uint_as_float(b)));
 }
 
-template<int ESZ, int DSTK>
+template<int ESZ, int DSTK, int LV>
 __device__ __forceinline__ PackedSmem pk_carve(unsigned char* smem, const PackedParams& P, int nwarp) {
-	constexpr int LS = PK_LV * (16 / ESZ);
+	constexpr int LS = LV * (16 / ESZ);
 	PackedSmem S;
 	S.mbar = (uint64_t*)smem;                       // fixed place: it outlives the items of the persistent kernel
 	S.sops = (int4*)(smem + 16);
@@ -466,64 +479,70 @@ __device__ __forceinline__ void pk_load_tables(const PackedSmem& S, const Packed
 	if( threadIdx.x == 0 ) S.shdr[0] = __ldg(P.hdr + prog);
 }
 
-// Stages the source rows of one tile with TMA bulk copies issued by warp 0;
-// every warp's lane 0 then waits on the mbarrier.  Workspace rows: the window
-// itself, split where it wraps around the ring.  1-byte input rows: the
-// 16-byte-aligned superset of the window, the misalignment kept per row for
-// the level-1 ops; rows that touch the ends of the gulp (t < 0, t >= ntime)
-// are written by hand with zeros outside.
+// Staging of the source rows of one tile, in two halves so that the copies of
+// the NEXT tile fly while the current one is being merged (the source has a
+// shared-memory region of its own, free again once level 1 has run).
+//   pk_stage_issue  (warp 0): TMA bulk copies (cp.async.bulk + mbarrier).
+//     Workspace rows: the window itself, split where it wraps around the ring.
+//     1-byte input rows: the 16-byte-aligned superset of the window, the
+//     misalignment kept per row (smis) for the level-1 ops; rows that touch the
+//     ends of the gulp (t < 0, t >= ntime) are only marked.
+//   pk_stage_finish (all warps): the marked rows are written by hand with zeros
+//     outside the gulp, then every warp's lane 0 waits on the mbarrier.
 template<int ESZ, int SRCK>
-__device__ __forceinline__ void pk_stage(const PackedSmem& S, const PackedParams& P, long t0, long soff, long roff,
-                                         uint32_t& parity, int lane, int warp, int nwarp) {
+__device__ __forceinline__ void pk_stage_issue(const PackedSmem& S, const PackedParams& P, long t0, long soff, long roff,
+                                               int lane) {
 	const int4 hdr = S.shdr[0];
-	if( warp == 0 ) {
-		// (the rows may have been written by other SMs through the generic proxy
-		// moments ago -- persistent kernel -- and shared memory was last read by
-		// this CTA's own generic loads)
-		fence_proxy_async_all();
-		if( SRCK == PK_SRC_BYTES ) {
-			const unsigned char* rin = (const unsigned char*)P.raw + roff;
-			uint32_t mine = 0;
-			for( int k=lane; k<hdr.y; k+=32 ) {
-				const int4 e = S.ssrc[k];
-				const long ts = t0 + e.y;
-				const unsigned char* g = rin + (long)e.x * P.rstride + ts;
-				const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
-				const uint32_t nb = (mis + e.w + 15) & ~15u;
-				const bool interior = ts >= 16 && ts + e.w + 16 <= P.ntime;
-				S.smis[k] = interior ? (unsigned char)mis : (unsigned char)0xFF;
-				if( interior ) mine += nb;
-			}
+	// (the rows may have been written by other SMs through the generic proxy
+	// moments ago -- persistent kernel -- and shared memory was last read by
+	// this CTA's own generic loads)
+	fence_proxy_async_all();
+	if( SRCK == PK_SRC_BYTES ) {
+		const unsigned char* rin = (const unsigned char*)P.raw + roff;
+		uint32_t mine = 0;
+		for( int k=lane; k<hdr.y; k+=32 ) {
+			const int4 e = S.ssrc[k];
+			const long ts = t0 + e.y;
+			const unsigned char* g = rin + (long)e.x * P.rstride + ts;
+			const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
+			const uint32_t nb = (mis + e.w + 15) & ~15u;
+			const bool interior = ts >= 16 && ts + e.w + 16 <= P.ntime;
+			S.smis[k] = interior ? (unsigned char)mis : (unsigned char)0xFF;
+			if( interior ) mine += nb;
+		}
 #pragma unroll
-			for( int o=16; o>0; o>>=1 ) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-			if( lane == 0 ) mbar_expect_tx(S.mbar, mine);
-			__syncwarp();
-			for( int k=lane; k<hdr.y; k+=32 ) {
-				const int4 e = S.ssrc[k];
-				const long ts = t0 + e.y;
-				const unsigned char* g = rin + (long)e.x * P.rstride + ts;
-				const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
-				if( ts >= 16 && ts + e.w + 16 <= P.ntime )
-					bulk_g2s(S.dbase + e.z, g - mis, (mis + e.w + 15) & ~15u, S.mbar);
-			}
-		} else {
-			if( lane == 0 ) mbar_expect_tx(S.mbar, (uint32_t)hdr.z);
-			__syncwarp();
-			const unsigned char* src = (const unsigned char*)P.src + soff * ESZ;
-			for( int k=lane; k<hdr.y; k+=32 ) {
-				const int4 e = S.ssrc[k];
-				const long c0 = (t0 + e.y - P.src_tb) % P.src_rl;
-				const unsigned char* g = src + (long)e.x * P.sstride * ESZ;
-				unsigned char* d = S.dbase + e.z;
-				const long n1 = min((long)e.w, P.src_rl - c0);
-				bulk_g2s(d, g + c0 * ESZ, (uint32_t)n1 * ESZ, S.mbar);
-				if( n1 < e.w ) bulk_g2s(d + n1 * ESZ, g, (uint32_t)(e.w - n1) * ESZ, S.mbar);
-			}
+		for( int o=16; o>0; o>>=1 ) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+		if( lane == 0 ) mbar_expect_tx(S.mbar, mine);
+		__syncwarp();
+		for( int k=lane; k<hdr.y; k+=32 ) {
+			const int4 e = S.ssrc[k];
+			const long ts = t0 + e.y;
+			const unsigned char* g = rin + (long)e.x * P.rstride + ts;
+			const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
+			if( ts >= 16 && ts + e.w + 16 <= P.ntime )
+				bulk_g2s(S.dbase + e.z, g - mis, (mis + e.w + 15) & ~15u, S.mbar);
+		}
+	} else {
+		if( lane == 0 ) mbar_expect_tx(S.mbar, (uint32_t)hdr.z);
+		__syncwarp();
+		const unsigned char* src = (const unsigned char*)P.src + soff * ESZ;
+		for( int k=lane; k<hdr.y; k+=32 ) {
+			const int4 e = S.ssrc[k];
+			const long c0 = (t0 + e.y - P.src_tb) % P.src_rl;
+			const unsigned char* g = src + (long)e.x * P.sstride * ESZ;
+			unsigned char* d = S.dbase + e.z;
+			const long n1 = min((long)e.w, P.src_rl - c0);
+			bulk_g2s(d, g + c0 * ESZ, (uint32_t)n1 * ESZ, S.mbar);
+			if( n1 < e.w ) bulk_g2s(d + n1 * ESZ, g, (uint32_t)(e.w - n1) * ESZ, S.mbar);
 		}
 	}
+}
+template<int ESZ, int SRCK>
+__device__ __forceinline__ void pk_stage_finish(const PackedSmem& S, const PackedParams& P, long t0, long roff,
+                                                uint32_t& parity, int lane, int warp, int nwarp) {
 	if( SRCK == PK_SRC_BYTES ) {
 		// rows at the ends of the gulp: every warp writes its share by hand
-		__syncthreads();                             // smis is written by warp 0
+		const int4 hdr = S.shdr[0];
 		const unsigned char* rin = (const unsigned char*)P.raw + roff;
 		for( int k=warp; k<hdr.y; k+=nwarp ) {
 			if( S.smis[k] != 0xFF ) continue;
@@ -545,15 +564,15 @@ __device__ __forceinline__ void pk_stage(const PackedSmem& S, const PackedParams
 // A finished row of the pass's top level -> pass output (same element type),
 // or, for an fp32 pass that ends the plan, the diagonal store of fdmt.cu:141-147.
 // Workspaces are rings in time: column = (t - tb) mod ring length.
-template<int ESZ, int DSTK>
-__device__ __forceinline__ void pk_store_out(const uint32_t (&o)[12], const int4& op, int nvec,
+template<int ESZ, int DSTK, int LV>
+__device__ __forceinline__ void pk_store_out(const uint32_t (&o)[4*LV], const int4& op, int nvec,
                                              const PackedParams& P, const PackedTile& tl, float* scratch, int lane, int warp) {
-	constexpr int VS = 16 / ESZ, LS = PK_LV * VS;
+	constexpr int VS = 16 / ESZ, LS = LV * VS;
 	if( DSTK == PK_DST_FINAL ) {
 		float* sc = scratch + (size_t)warp * 32 * LS;
 		__syncwarp();
 #pragma unroll
-		for( int j=0; j<PK_LV; ++j )
+		for( int j=0; j<LV; ++j )
 			*(uint4*)(sc + LS * lane + 4 * j) = make_uint4(o[4*j], o[4*j+1], o[4*j+2], o[4*j+3]);
 		__syncwarp();
 		const long d = op.x;
@@ -566,9 +585,9 @@ __device__ __forceinline__ void pk_store_out(const uint32_t (&o)[12], const int4
 	} else {
 		unsigned char* g = (unsigned char*)P.dst + (tl.doff + (long)op.x * P.dstride) * ESZ;
 #pragma unroll
-		for( int j=0; j<PK_LV; ++j )
-			if( PK_LV * lane + j < nvec ) {
-				long c = tl.dcol + (long)(PK_LV * lane + j) * VS;
+		for( int j=0; j<LV; ++j )
+			if( LV * lane + j < nvec ) {
+				long c = tl.dcol + (long)(LV * lane + j) * VS;
 				if( c >= P.dst_rl ) c -= P.dst_rl;
 				*(uint4*)(g + c * ESZ) = make_uint4(o[4*j], o[4*j+1], o[4*j+2], o[4*j+3]);
 			}
@@ -576,14 +595,14 @@ __device__ __forceinline__ void pk_store_out(const uint32_t (&o)[12], const int4
 }
 // Top level of a 16-bit pass with fp32 output: halves added in 32 bits, bias
 // removed, converted (exact), stored to the fp32 workspace or diagonally.
-template<int DSTK>
-__device__ __forceinline__ void pk_store_wide(const uint32_t (&av)[12], const uint32_t (&bt)[12], const int4& op,
+template<int DSTK, int LV>
+__device__ __forceinline__ void pk_store_wide(const uint32_t (&av)[4*LV], const uint32_t (&bt)[4*LV], const int4& op,
                                               int nvec, const PackedParams& P, const PackedTile& tl,
                                               float* scratch, int lane, int warp) {
-	constexpr int LS = PK_LV * 8;
-	float f[2 * 12];
+	constexpr int LS = LV * 8;
+	float f[8*LV];
 #pragma unroll
-	for( int k=0; k<12; ++k ) {
+	for( int k=0; k<4*LV; ++k ) {
 		int lo = (int)(av[k] & 0xFFFFu) + (int)(bt[k] & 0xFFFFu) - tl.bias;
 		int hi = (int)(av[k] >> 16)     + (int)(bt[k] >> 16)     - tl.bias;
 		f[2*k] = (float)lo; f[2*k+1] = (float)hi;
@@ -591,8 +610,8 @@ __device__ __forceinline__ void pk_store_wide(const uint32_t (&av)[12], const ui
 	if( DSTK == PK_DST_CVT ) {
 		float* g = (float*)P.dst + tl.doff + (long)op.x * P.dstride;
 #pragma unroll
-		for( int j=0; j<2*PK_LV; ++j )
-			if( 2 * (PK_LV * lane) + j < 2 * nvec ) {
+		for( int j=0; j<2*LV; ++j )
+			if( 2 * (LV * lane) + j < 2 * nvec ) {
 				long c = tl.dcol + LS * lane + 4 * j;
 				if( c >= P.dst_rl ) c -= P.dst_rl;
 				*(float4*)(g + c) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
@@ -601,7 +620,7 @@ __device__ __forceinline__ void pk_store_wide(const uint32_t (&av)[12], const ui
 		float* sc = scratch + (size_t)warp * 32 * LS;
 		__syncwarp();
 #pragma unroll
-		for( int j=0; j<2*PK_LV; ++j ) *(float4*)(sc + LS * lane + 4 * j) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
+		for( int j=0; j<2*LV; ++j ) *(float4*)(sc + LS * lane + 4 * j) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
 		__syncwarp();
 		const long d = op.x;
 		float* g = (float*)P.dst + tl.doff + d * P.dstride - d + tl.t0;
@@ -684,17 +703,17 @@ __device__ __forceinline__ void pk_group4_op(const int4& A, const int4& B, const
 		for( int k=0; k<13; ++k ) s1[k] += x3[k];
 	}
 	if( mask & 1 ) {
-		uint4* d = (uint4*)(dbase + A.x) + PK_LV * lane;
+		uint4* d = (uint4*)(dbase + A.x) + PK_LV_BYTES * lane;
 #pragma unroll
-		for( int j=0; j<PK_LV; ++j )
-			if( PK_LV * lane + j < nvec )
+		for( int j=0; j<PK_LV_BYTES; ++j )
+			if( PK_LV_BYTES * lane + j < nvec )
 				d[j] = make_uint4(s0[4*j] + s1[4*j+1], s0[4*j+1] + s1[4*j+2], s0[4*j+2] + s1[4*j+3], s0[4*j+3] + s1[4*j+4]);
 	}
 	if( mask & 2 ) {
-		uint4* d = (uint4*)(dbase + B.x) + PK_LV * lane;
+		uint4* d = (uint4*)(dbase + B.x) + PK_LV_BYTES * lane;
 #pragma unroll
-		for( int j=0; j<PK_LV; ++j )
-			if( PK_LV * lane + j < nvec )
+		for( int j=0; j<PK_LV_BYTES; ++j )
+			if( PK_LV_BYTES * lane + j < nvec )
 				d[j] = make_uint4(s0[4*j]   + __funnelshift_r(s1[4*j],   s1[4*j+1], 16),
 				                  s0[4*j+1] + __funnelshift_r(s1[4*j+1], s1[4*j+2], 16),
 				                  s0[4*j+2] + __funnelshift_r(s1[4*j+2], s1[4*j+3], 16),
@@ -704,16 +723,17 @@ __device__ __forceinline__ void pk_group4_op(const int4& A, const int4& B, const
 
 // One op: row = a + shift(b), operands in shared memory, result to shared
 // memory or to the pass output.
-template<int ESZ, int SRCK, int DSTK>
+template<int ESZ, int SRCK, int DSTK, int LV>
 __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, const PackedParams& P,
                                           const PackedTile& tl, int lane, int warp) {
 	unsigned char* dbase = S.dbase;
 	const int nvec = op.w >> PK_NVEC_SHIFT;
 	const int wo = (op.w >> PK_WO_SHIFT) & 3;
 	const int hbits = ((op.w >> PK_H_SHIFT) & 1) * 16;
-	uint32_t av[12];
+	uint32_t av[4*LV];
+	bool done = false;
 	const bool wide = (ESZ == 2) && (DSTK != PK_DST_SAME) && (op.w & PK_STORE_G);
-	if( (SRCK == PK_SRC_BYTES) && (op.w & PK_BYTES) ) {
+	if constexpr( SRCK == PK_SRC_BYTES && LV == PK_LV_BYTES ) if( op.w & PK_BYTES ) {
 		// level 1 of the first pass: both operands are channels of the 1-byte input
 		uint32_t bt[12];
 		if( op.w & PK_NO_A ) {
@@ -730,111 +750,127 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 			const int kb = op.z & 0xFFF;
 			pk_bytes_widen(dbase, (uint32_t)S.ssrc[kb].z + S.smis[kb] + ((uint32_t)op.z >> 12) + 24u * lane, tl.flip, bt);
 		}
-		if( wide ) { pk_store_wide<DSTK>(av, bt, op, nvec, P, tl, S.scratch, lane, warp); return; }
+		if( wide ) { pk_store_wide<DSTK, LV>(av, bt, op, nvec, P, tl, S.scratch, lane, warp); return; }
 #pragma unroll
 		for( int k=0; k<12; ++k ) av[k] += bt[k];
-	} else {
-		uint32_t bw[16];
+		done = true;
+	}
+	if( !done ) {
+		uint32_t bw[4*LV+4];
 		if( op.w & (PK_NO_A | PK_NO_B) ) {
 			// absent parent (odd band counts): zeros stand in
 			if( op.w & PK_NO_A ) {
 #pragma unroll
-				for( int k=0; k<12; ++k ) av[k] = 0u;
+				for( int k=0; k<4*LV; ++k ) av[k] = 0u;
 			} else {
-				const uint4* a = (const uint4*)(dbase + op.y) + PK_LV * lane;
+				const uint4* a = (const uint4*)(dbase + op.y) + LV * lane;
 #pragma unroll
-				for( int j=0; j<PK_LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
+				for( int j=0; j<LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
 			}
 			if( op.w & PK_NO_B ) {
 #pragma unroll
-				for( int k=0; k<16; ++k ) bw[k] = 0u;
+				for( int k=0; k<4*LV+4; ++k ) bw[k] = 0u;
 			} else {
-				const uint4* b = (const uint4*)(dbase + op.z) + PK_LV * lane;
+				const uint4* b = (const uint4*)(dbase + op.z) + LV * lane;
 #pragma unroll
-				for( int j=0; j<PK_LV+1; ++j ) { uint4 v = b[j]; bw[4*j] = v.x; bw[4*j+1] = v.y; bw[4*j+2] = v.z; bw[4*j+3] = v.w; }
+				for( int j=0; j<LV+1; ++j ) { uint4 v = b[j]; bw[4*j] = v.x; bw[4*j+1] = v.y; bw[4*j+2] = v.z; bw[4*j+3] = v.w; }
 			}
 		} else {
-			const uint4* a = (const uint4*)(dbase + op.y) + PK_LV * lane;
-			const uint4* b = (const uint4*)(dbase + op.z) + PK_LV * lane;
+			const uint4* a = (const uint4*)(dbase + op.y) + LV * lane;
+			const uint4* b = (const uint4*)(dbase + op.z) + LV * lane;
 #pragma unroll
-			for( int j=0; j<PK_LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
+			for( int j=0; j<LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
 #pragma unroll
-			for( int j=0; j<PK_LV+1; ++j ) { uint4 v = b[j]; bw[4*j] = v.x; bw[4*j+1] = v.y; bw[4*j+2] = v.z; bw[4*j+3] = v.w; }
+			for( int j=0; j<LV+1; ++j ) { uint4 v = b[j]; bw[4*j] = v.x; bw[4*j+1] = v.y; bw[4*j+2] = v.z; bw[4*j+3] = v.w; }
 		}
 #define BFB_PK_SHIFTED(W_, k_) ((ESZ == 2) ? __funnelshift_r(bw[(k_) + W_], bw[(k_) + W_ + 1], hbits) : bw[(k_) + W_])
 		if( wide ) {
-			uint32_t bt[12];
+			uint32_t bt[4*LV];
 			switch( wo ) {
-			case 0:  _Pragma("unroll") for( int k=0; k<12; ++k ) bt[k] = BFB_PK_SHIFTED(0, k); break;
-			case 1:  _Pragma("unroll") for( int k=0; k<12; ++k ) bt[k] = BFB_PK_SHIFTED(1, k); break;
-			case 2:  _Pragma("unroll") for( int k=0; k<12; ++k ) bt[k] = BFB_PK_SHIFTED(2, k); break;
-			default: _Pragma("unroll") for( int k=0; k<12; ++k ) bt[k] = BFB_PK_SHIFTED(3, k); break;
+			case 0:  _Pragma("unroll") for( int k=0; k<4*LV; ++k ) bt[k] = BFB_PK_SHIFTED(0, k); break;
+			case 1:  _Pragma("unroll") for( int k=0; k<4*LV; ++k ) bt[k] = BFB_PK_SHIFTED(1, k); break;
+			case 2:  _Pragma("unroll") for( int k=0; k<4*LV; ++k ) bt[k] = BFB_PK_SHIFTED(2, k); break;
+			default: _Pragma("unroll") for( int k=0; k<4*LV; ++k ) bt[k] = BFB_PK_SHIFTED(3, k); break;
 			}
-			pk_store_wide<DSTK>(av, bt, op, nvec, P, tl, S.scratch, lane, warp);
+			pk_store_wide<DSTK, LV>(av, bt, op, nvec, P, tl, S.scratch, lane, warp);
 			return;
 		}
 		switch( wo ) {
-		case 0:  _Pragma("unroll") for( int k=0; k<12; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(0, k)); break;
-		case 1:  _Pragma("unroll") for( int k=0; k<12; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(1, k)); break;
-		case 2:  _Pragma("unroll") for( int k=0; k<12; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(2, k)); break;
-		default: _Pragma("unroll") for( int k=0; k<12; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(3, k)); break;
+		case 0:  _Pragma("unroll") for( int k=0; k<4*LV; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(0, k)); break;
+		case 1:  _Pragma("unroll") for( int k=0; k<4*LV; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(1, k)); break;
+		case 2:  _Pragma("unroll") for( int k=0; k<4*LV; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(2, k)); break;
+		default: _Pragma("unroll") for( int k=0; k<4*LV; ++k ) av[k] = pk_add<ESZ>(av[k], BFB_PK_SHIFTED(3, k)); break;
 		}
 #undef BFB_PK_SHIFTED
 	}
 	if( op.w & PK_STORE_G ) {
-		pk_store_out<ESZ, DSTK>(av, op, nvec, P, tl, S.scratch, lane, warp);
+		pk_store_out<ESZ, DSTK, LV>(av, op, nvec, P, tl, S.scratch, lane, warp);
 	} else {
-		uint4* d = (uint4*)(dbase + op.x) + PK_LV * lane;
+		uint4* d = (uint4*)(dbase + op.x) + LV * lane;
 #pragma unroll
-		for( int j=0; j<PK_LV; ++j )
-			if( PK_LV * lane + j < nvec ) d[j] = make_uint4(av[4*j], av[4*j+1], av[4*j+2], av[4*j+3]);
+		for( int j=0; j<LV; ++j )
+			if( LV * lane + j < nvec ) d[j] = make_uint4(av[4*j], av[4*j+1], av[4*j+2], av[4*j+3]);
 	}
 }
 
-template<int ESZ, int SRCK, int DSTK>
+template<int ESZ, int SRCK, int DSTK, int LV>
 __device__ __forceinline__ void pk_levels(const PackedSmem& S, const PackedParams& P, const PackedTile& tl,
-                                          int lane, int warp, int nwarp) {
-	for( int lev=1; lev<=P.nlev; ++lev ) {
+                                          int lev0, int lev1, int lane, int warp, int nwarp) {
+	for( int lev=lev0; lev<=lev1; ++lev ) {
 		const int4* list = S.sops + ((size_t)(lev - 1) * nwarp + warp) * P.slots;
 		int4 nxt = list[0];
 		for( int m=0; m<P.slots; ++m ) {
 			const int4 op = nxt;
 			if( op.w == 0 ) break;
 			nxt = list[m + 1];                     // the last slot of a list is always a terminator
-			if( (SRCK == PK_SRC_BYTES) && (op.w & PK_GROUP4) ) {
+			if constexpr( SRCK == PK_SRC_BYTES && LV == PK_LV_BYTES ) if( op.w & PK_GROUP4 ) {
 				pk_group4_op(op, nxt, S, tl, lane);    // two slots
 				++m;
 				nxt = list[m + 1];
 				continue;
 			}
-			pk_row_op<ESZ, SRCK, DSTK>(op, S, P, tl, lane, warp);
+			pk_row_op<ESZ, SRCK, DSTK, LV>(op, S, P, tl, lane, warp);
 		}
 		__syncthreads();
 	}
 }
 
-// One (program, tile): tables already in shared memory.
-template<int ESZ, int SRCK, int DSTK>
-__device__ __forceinline__ void pk_tile(const PackedSmem& S, const PackedParams& P, long t0, long soff, long roff,
-                                        long doff, uint32_t& parity, int lane, int warp, int nwarp) {
-	pk_stage<ESZ, SRCK>(S, P, t0, soff, roff, parity, lane, warp, nwarp);
-	__syncthreads();
-	PackedTile tl;
-	tl.t0 = t0; tl.dcol = (t0 - P.dst_tb) % P.dst_rl; tl.doff = doff;
-	tl.bias = P.is_signed ? 128 * S.shdr[0].x : 0;
-	tl.flip = P.is_signed ? 0x80808080u : 0u;
-	pk_levels<ESZ, SRCK, DSTK>(S, P, tl, lane, warp, nwarp);
+// The tiles first, first + stride, ... (count of them) of one program, tables
+// already in shared memory.  The source rows of tile i+1 are requested as soon
+// as level 1 of tile i has consumed tile i's.
+template<int ESZ, int SRCK, int DSTK, int LV>
+__device__ __forceinline__ void pk_tiles(const PackedSmem& S, const PackedParams& P, long first, long stride, long count,
+                                         long soff, long roff, long doff, uint32_t& parity, int lane, int warp, int nwarp) {
+	if( count <= 0 ) return;
+	if( warp == 0 ) pk_stage_issue<ESZ, SRCK>(S, P, P.t_begin + first * P.T, soff, roff, lane);
+	for( long n=0; n<count; ++n ) {
+		const long t0 = P.t_begin + (first + n * stride) * P.T;
+		__syncthreads();                               // smis / staged rows of this tile were requested by warp 0
+		pk_stage_finish<ESZ, SRCK>(S, P, t0, roff, parity, lane, warp, nwarp);
+		__syncthreads();
+		PackedTile tl;
+		tl.t0 = t0; tl.dcol = (t0 - P.dst_tb) % P.dst_rl; tl.doff = doff;
+		tl.bias = P.is_signed ? 128 * S.shdr[0].x : 0;
+		tl.flip = P.is_signed ? 0x80808080u : 0u;
+		pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, 1, 1, lane, warp, nwarp);
+		const bool more = n + 1 < count && warp == 0;
+		if( more && P.prefetch )
+			pk_stage_issue<ESZ, SRCK>(S, P, P.t_begin + (first + (n + 1) * stride) * P.T, soff, roff, lane);
+		pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, 2, P.nlev, lane, warp, nwarp);
+		if( more && !P.prefetch )
+			pk_stage_issue<ESZ, SRCK>(S, P, P.t_begin + (first + (n + 1) * stride) * P.T, soff, roff, lane);
+	}
 }
 } // namespace packed_dev
 
 // One pass per launch: grid (tile stride, program, batch).
-template<int ESZ, int SRCK, int DSTK>
-__global__ void __launch_bounds__(256, 3)
+template<int ESZ, int SRCK, int DSTK, int LV>
+__global__ void __launch_bounds__(256, LV == 3 ? 3 : 2)
 fdmt_packed_kernel(const __grid_constant__ PackedParams P) {
 	using namespace packed_dev;
 	extern __shared__ __align__(16) unsigned char pk_smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-	const PackedSmem S = pk_carve<ESZ, DSTK>(pk_smem, P, nwarp);
+	const PackedSmem S = pk_carve<ESZ, DSTK, LV>(pk_smem, P, nwarp);
 	pk_load_tables(S, P, blockIdx.y, nwarp);
 	if( threadIdx.x == 0 ) {
 		mbar_init(S.mbar, 1);
@@ -842,9 +878,9 @@ fdmt_packed_kernel(const __grid_constant__ PackedParams P) {
 	}
 	__syncthreads();
 	uint32_t parity = 0;
-	for( long tile=blockIdx.x; tile<P.ntile; tile+=gridDim.x )
-		pk_tile<ESZ, SRCK, DSTK>(S, P, P.t_begin + tile * P.T, (long)blockIdx.z * P.sbatch,
-		                         (long)blockIdx.z * P.rbatch, (long)blockIdx.z * P.dbatch, parity, lane, warp, nwarp);
+	const long count = blockIdx.x < P.ntile ? (P.ntile - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+	pk_tiles<ESZ, SRCK, DSTK, LV>(S, P, blockIdx.x, gridDim.x, count, (long)blockIdx.z * P.sbatch,
+	                          (long)blockIdx.z * P.rbatch, (long)blockIdx.z * P.dbatch, parity, lane, warp, nwarp);
 }
 
 // ---------------------------------------------------------------------------
@@ -863,7 +899,7 @@ fdmt_packed_kernel(const __grid_constant__ PackedParams P) {
 // ---------------------------------------------------------------------------
 struct MegaPass {
 	PackedParams p;
-	int  kind;        // 0..5: 16-bit (src_kind*3 + dst_kind), 6: fp32 -> fp32, 7: fp32 -> final
+	int  kind;        // 0..5: 16-bit (src_kind*3 + dst_kind), 6: fp32 -> fp32, 7: fp32 -> final; +8: five vectors per lane
 	int  nprog;
 	int  lookback;
 	long nt;          // tiles
@@ -895,18 +931,17 @@ __device__ __forceinline__ void mega_wait(const MegaParams& M, int k, long jlo, 
 		while( ld_acquire(c) < M.pass[k].nprog ) __nanosleep(64);
 	}
 }
-template<int ESZ, int SRCK, int DSTK>
+template<int ESZ, int SRCK, int DSTK, int LV>
 __device__ __forceinline__ void mega_item(const PackedParams& P, const MegaItem& it, unsigned char* smem,
                                           uint32_t& parity, int lane, int warp, int nwarp) {
-	const PackedSmem S = pk_carve<ESZ, DSTK>(smem, P, nwarp);
+	const PackedSmem S = pk_carve<ESZ, DSTK, LV>(smem, P, nwarp);
 	pk_load_tables(S, P, it.prog, nwarp);
 	__syncthreads();
-	for( long i=it.i0; i<it.i1; ++i )
-		pk_tile<ESZ, SRCK, DSTK>(S, P, P.t_begin + i * P.T, 0, 0, 0, parity, lane, warp, nwarp);
+	pk_tiles<ESZ, SRCK, DSTK, LV>(S, P, it.i0, 1, it.i1 - it.i0, 0, 0, 0, parity, lane, warp, nwarp);
 }
 } // namespace packed_dev
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 fdmt_packed_mega_kernel(const __grid_constant__ MegaParams M) {
 	using namespace packed_dev;
 	extern __shared__ __align__(16) unsigned char pk_smem[];
@@ -969,14 +1004,17 @@ fdmt_packed_mega_kernel(const __grid_constant__ MegaParams M) {
 		if( it.i0 < it.i1 ) {
 			const MegaPass& mp = M.pass[it.k];
 			switch( mp.kind ) {
-			case 0:  mega_item<2, PK_SRC_BYTES, PK_DST_SAME >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
-			case 1:  mega_item<2, PK_SRC_BYTES, PK_DST_CVT  >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
-			case 2:  mega_item<2, PK_SRC_BYTES, PK_DST_FINAL>(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
-			case 3:  mega_item<2, PK_SRC_SAME,  PK_DST_SAME >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
-			case 4:  mega_item<2, PK_SRC_SAME,  PK_DST_CVT  >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
-			case 5:  mega_item<2, PK_SRC_SAME,  PK_DST_FINAL>(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
-			case 6:  mega_item<4, PK_SRC_SAME,  PK_DST_SAME >(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
-			default: mega_item<4, PK_SRC_SAME,  PK_DST_FINAL>(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+#define BFB_MEGA_CASE(K_, E_, S_, D_, L_) case K_: mega_item<E_, S_, D_, L_>(mp.p, it, pk_smem, parity, lane, warp, nwarp); break;
+			BFB_MEGA_CASE(0,  2, PK_SRC_BYTES, PK_DST_SAME,  3) BFB_MEGA_CASE(1,  2, PK_SRC_BYTES, PK_DST_CVT,   3)
+			BFB_MEGA_CASE(2,  2, PK_SRC_BYTES, PK_DST_FINAL, 3)
+			BFB_MEGA_CASE(3,  2, PK_SRC_SAME,  PK_DST_SAME,  3) BFB_MEGA_CASE(4,  2, PK_SRC_SAME,  PK_DST_CVT,   3)
+			BFB_MEGA_CASE(5,  2, PK_SRC_SAME,  PK_DST_FINAL, 3)
+			BFB_MEGA_CASE(6,  4, PK_SRC_SAME,  PK_DST_SAME,  3) BFB_MEGA_CASE(7,  4, PK_SRC_SAME,  PK_DST_FINAL, 3)
+			BFB_MEGA_CASE(11, 2, PK_SRC_SAME,  PK_DST_SAME,  5) BFB_MEGA_CASE(12, 2, PK_SRC_SAME,  PK_DST_CVT,   5)
+			BFB_MEGA_CASE(13, 2, PK_SRC_SAME,  PK_DST_FINAL, 5)
+			BFB_MEGA_CASE(14, 4, PK_SRC_SAME,  PK_DST_SAME,  5) BFB_MEGA_CASE(15, 4, PK_SRC_SAME,  PK_DST_FINAL, 5)
+#undef BFB_MEGA_CASE
+			default: break;
 			}
 			// (pk_levels ends with a barrier: every store of the item has been issued)
 		}

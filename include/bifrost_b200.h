@@ -331,8 +331,9 @@ BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
  * packed-integer FDMT schedule that bfFdmtExecute runs for 1-byte inputs --
  * see csrc/fdmt_packed.cuh for the op layout.  pass < 0: header[0] = number of
  * passes (0: the schedule does not apply to this plan).  Otherwise
- * header[16] = {s0, s1, nlev, esize, src_kind, dst_kind, T, nprog, nwarp,
- * slots, src_slots, data_bytes, lookback, nrow_out, smem_bytes, nops};
+ * header[24] = {s0, s1, nlev, esize, src_kind, dst_kind, T, nprog, nwarp,
+ * slots, src_slots, data_bytes, lookback, nrow_out, smem_bytes, nops, lv,
+ * fused, prefetch, 0...};
  * ops receives 4*nprog*nlev*nwarp*slots ints, src 4*nprog*src_slots ints,
  * hdr 4*nprog ints (each may be NULL). */
 BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,

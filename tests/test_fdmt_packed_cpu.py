@@ -25,17 +25,16 @@ def _ip(a):
 
 
 def query(nchan, md, f0, df):
-    hdr = np.zeros(16, np.int32)
+    hdr = np.zeros(24, np.int32)
     assert _bf.bfFdmtPackedQuery(nchan, md, f0, df, -2.0, -1, _ip(hdr), None, None, None) == 0
     passes = []
     for k in range(int(hdr[0])):
-        h = np.zeros(16, np.int32)
+        h = np.zeros(24, np.int32)
         assert _bf.bfFdmtPackedQuery(nchan, md, f0, df, -2.0, k, _ip(h), None, None, None) == 0
         keys = ('s0 s1 nlev esize src_kind dst_kind T nprog nwarp slots src_slots data_bytes '
-                'lookback nrow_out smem_bytes nops').split()
+                'lookback nrow_out smem_bytes nops lv fused prefetch').split()
         p = dict(zip(keys, (int(v) for v in h)))
-        p['fused'] = bool(p['nops'] >> 30)
-        p['nops'] &= (1 << 30) - 1
+        p['fused'] = bool(p['fused'])
         ops = np.zeros((p['nprog'], p['nlev'], p['nwarp'], p['slots'], 4), np.int32)
         src = np.zeros((p['nprog'], p['src_slots'], 4), np.int32)
         ph = np.zeros((p['nprog'], 4), np.int32)
@@ -114,7 +113,7 @@ class Machine(object):
                     if ctl == 0:
                         break
                     n = (ctl >> NVEC_SHIFT) * VS
-                    assert n <= 32 * 3 * VS
+                    assert n <= 32 * p['lv'] * VS
                     if ctl & GROUP4:
                         # steps 1+2 fused: two slots, four input channels
                         assert p['src_kind'] == 0 and lev == 1 and p['fused']
