@@ -1,4 +1,9 @@
-"""The fused spectrometer kernel against (1) the oracle chain
+"""Tolerance (north_star: 1e-5 relative): every output within 1e-5 of its own
+magnitude, with the rms of Stokes I as the floor for the near-empty bins --
+``close()`` below.  (The inputs carry a strong tone per channel, so the largest
+absolute errors sit on bins that are ~20x the rms.)
+
+The fused spectrometer kernel against (1) the oracle chain
 fft(x/128, fftshift) -> stokes -> sum of f_avg bins -> sum over frames in fp64
 and (2) the unfused C-ABI ops run one after the other on the GPU."""
 import numpy as np
@@ -25,6 +30,13 @@ def make(nframe, nchan, nfft, seed):
     return x
 
 
+def close(got, want, tol=1e-5):
+    scale = np.sqrt(np.mean(np.asarray(want)[0] ** 2))
+    err = np.abs(got - want)
+    lim = tol * np.maximum(np.abs(want), scale)
+    assert (err <= lim).all(), (float((err / lim).max()), float(err.max()), float(scale))
+
+
 def oracle_chain(x, f_avg):
     v = (x['re'].astype(np.float64) + 1j * x['im'].astype(np.float64)) / 128.0
     spec = np.fft.fftshift(np.fft.fft(v, axis=2), axes=2)        # [frame, chan, fine, pol]
@@ -45,8 +57,7 @@ def test_fused_matches_oracle(f_avg):
     bf.spectrometer(d_x, d_o, nfft, f_avg, beta=0.0)
     got = np.asarray(d_o.copy('system'))
     want = oracle_chain(x, f_avg)
-    scale = np.sqrt(np.mean(want[0] ** 2))
-    assert np.abs(got - want).max() <= 1e-5 * scale
+    close(got, want)
     # the tone lands in the right (shifted) bin of channel 0
     k = (11 + nfft // 2) % nfft
     assert np.argmax(got[0, :nfft // f_avg]) == k // f_avg
@@ -60,7 +71,7 @@ def test_beta_accumulates_across_calls():
     bf.spectrometer(bf.asarray(x2, space='cuda'), d_o, nfft, f_avg, beta=1.0)
     got = np.asarray(d_o.copy('system'))
     want = oracle_chain(x1, f_avg) + oracle_chain(x2, f_avg)
-    assert np.abs(got - want).max() <= 1e-5 * np.sqrt(np.mean(want[0] ** 2))
+    close(got, want)
 
 
 def test_fused_matches_unfused_ops():
@@ -85,8 +96,7 @@ def test_fused_matches_unfused_ops():
     d_o = bf.empty((4, nchan * nfft // f_avg), 'f32', 'cuda')
     bf.spectrometer(d_x, d_o, nfft, f_avg)
     fused = np.asarray(d_o.copy('system'))
-    scale = np.sqrt(np.mean(unfused[0] ** 2))
-    assert np.abs(fused - unfused).max() <= 1e-5 * scale
+    close(fused, unfused)
 
 
 def test_unsupported_shapes_are_reported():
@@ -115,6 +125,4 @@ def test_baseline_config3_full_size_against_fp64():
     x = np.zeros(sub.shape[:4], dtype=bf.DataType('ci8').as_numpy_dtype())
     x['re'], x['im'] = sub[..., 0], sub[..., 1]
     want = oracle_chain(x, f_avg).reshape(4, len(chans), nfft // f_avg)
-    scale = np.sqrt(np.mean(want[0] ** 2))
-    err = np.abs(got[:, chans] - want).max()
-    assert err <= 1e-5 * scale, (err, scale)
+    close(got[:, chans], want)

@@ -1,5 +1,9 @@
 #!/bin/bash
 # round-2 GPU check G: FDMT parity with the new knobs, then prefetch / vectors-per-lane sweep
+echo "== correlator vs reference library"
+timeout -s KILL 300 python -m pytest tests/test_linalg.py -x -q -m gpu -k reference_library 2>&1 | tail -30
+echo "== spectrometer"
+timeout -s KILL 600 python -m pytest tests/test_spectrometer.py tests/test_blocks_gpu.py -q -m gpu 2>&1 | tail -5
 echo "== FDMT parity"
 timeout -s KILL 1500 python -m pytest tests/test_fdmt.py -x -q -m gpu 2>&1 | tail -6
 echo "== timing"
