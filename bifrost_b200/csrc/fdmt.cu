@@ -906,11 +906,13 @@ static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int
 	int tmax = 0;
 	for( PackedPass const& cp : cps ) tmax = std::max(tmax, cp.T);
 	long C = std::max<long>(env_int("BFB_FDMT_PACKED_CHUNK", 2048), tmax);
-	// Items of one round: every (pass, program).  The last pass (it streams the
-	// output to HBM) first, so that the DRAM-bound and the compute-bound passes
-	// interleave; inside a pass the heavy programs first (they are sorted so).
+	// Items of one round: every (pass, program), producers first: about 1.5
+	// rounds of items are in flight, and an item should find what it waits for
+	// finished, not merely claimed -- with the first pass at the head of its
+	// round the distance (in claimed items) from a producer chunk to its
+	// consumers is the largest.  Inside a pass the heavy programs come first.
 	tmpl_->clear();
-	for( int k=(int)cps.size()-1; k>=0; --k ) {
+	for( int k=0; k<(int)cps.size(); ++k ) {
 		if( cps[k].nprog >= (1 << 24) ) return false;
 		for( int p=0; p<cps[k].nprog; ++p ) tmpl_->push_back((k << 24) | p);
 	}

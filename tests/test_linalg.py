@@ -287,4 +287,12 @@ def test_correlator_matches_the_reference_library():
         theirs = np.asarray(d_c.copy('system'))
         _check(ref.bfLinAlgDestroy(h))
         il = np.tril_indices(n)
-        np.testing.assert_array_equal(ours[:, il[0], il[1]], theirs[:, il[0], il[1]])
+        a, b = ours[:, il[0], il[1]], theirs[:, il[0], il[1]]
+        # The reference accumulates (x/127)(y/127) in fp32 and rounds x127^2 at the end
+        # (linalg_kernels.cu:94-112): exact only while the rounding errors stay below
+        # one half -- short integrations.  Ours is integer-exact (checked against the
+        # oracle above); the long case agrees to the reference's own fp32 accuracy.
+        if ntime <= 64:
+            np.testing.assert_array_equal(a, b)
+        else:
+            np.testing.assert_allclose(a, b, rtol=2e-5, atol=2.0)

@@ -41,6 +41,18 @@ def timeit(fn, nrep=10, nwarm=3, stream=None):
     return float(np.median(times))
 
 
+def cufft_ms(nbatch, nfft, stream, shift=False):
+    """cuFFT (through torch.fft: bench tooling only, never on the product path)
+    on the same number of transforms: cf32 -> cf32 c2c, the kernel the reference
+    calls for this op (src/fft.cu:224-239).  The reference additionally converts
+    ci8 -> cf32 in a load callback, so cuFFT's own traffic is 16 B/sample."""
+    x = torch.randn(nbatch, nfft, dtype=torch.complex64, device='cuda')
+    fn = (lambda: torch.fft.fftshift(torch.fft.fft(x, dim=1), dim=1)) if shift else (lambda: torch.fft.fft(x, dim=1))
+    ms = timeit(fn, nrep=5, stream=stream)
+    del x
+    return ms
+
+
 def report(name, ms, nbytes, ref_ms=None, **extra):
     line = dict(op=name, ms=round(ms, 4), alg_GBps=round(nbytes / ms / 1e6, 1))
     if ref_ms is not None:
@@ -140,8 +152,11 @@ def main():
         plan = bf.fft.Fft()
         plan.init(d_t, d_f, axes=[3], apply_fftshift=True)
         ms = timeit(lambda: plan.execute(d_t, d_f), nrep=5, stream=stream)
-        report('chain.fft ci8->cf32 n=4096 fftshift', ms, 5 * I, Msamples_per_s=round(nframe * nchan * nfft / ms / 1e3, 1))
         del d_t
+        cu = cufft_ms(nframe * npol * nchan, nfft, stream)
+        report('chain.fft ci8->cf32 n=4096 fftshift', ms, 5 * I, Msamples_per_s=round(nframe * nchan * nfft / ms / 1e3, 1),
+               cufft_c2c_cf32_ms=round(cu, 4), cufft_GBps=round(16 * nframe * npol * nchan * nfft / cu / 1e6, 1),
+               speedup_vs_cufft=round(cu / ms, 2))
         d_d = bf.empty((nframe, 4, nchan, nfft), 'f32', 'cuda')
         ms = timeit(lambda: bf.detect(d_f, d_d, 'stokes', 1), nrep=5, stream=stream)
         report('chain.detect stokes', ms, 8 * I, Msamples_per_s=round(nframe * nchan * nfft / ms / 1e3, 1))
@@ -169,9 +184,12 @@ def main():
             plan = bf.fft.Fft()
             plan.init(d_i, d_o, axes=[1], apply_fftshift=False)
             ms = timeit(lambda: plan.execute(d_i, d_o), nrep=5, stream=stream)
-            report('fft ci8->cf32 n=%d batch=%d' % (nfft_, nbatch), ms, 10 * nbatch * nfft_,
-                   Msamples_per_s=round(nbatch * nfft_ / ms / 1e3, 1))
             del d_i, d_o, plan
+            cu = cufft_ms(nbatch, nfft_, stream)
+            report('fft ci8->cf32 n=%d batch=%d' % (nfft_, nbatch), ms, 10 * nbatch * nfft_,
+                   Msamples_per_s=round(nbatch * nfft_ / ms / 1e3, 1),
+                   cufft_c2c_cf32_ms=round(cu, 4), cufft_GBps=round(16 * nbatch * nfft_ / cu / 1e6, 1),
+                   speedup_vs_cufft=round(cu / ms, 2))
 
     if 'correlate' in ops:
         nchan_c, nstand, npol_c = 512, 256, 2
