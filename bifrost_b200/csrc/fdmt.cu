@@ -736,7 +736,9 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 		const size_t pi = passes.size();
 		cfg.D       = pi < Ds.size()  ? Ds[pi]  : (s0 == 1 ? 64 : 24);
 		cfg.nwarp   = std::max(1, std::min(8, pi < NWs.size() ? NWs[pi] : 8));
-		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : 74);
+		// three CTAs per SM for the pass that waits on HBM, two (larger delay blocks,
+		// fewer redundant rows) for the others -- measured optimum for config 2
+		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : (s0 == 1 ? 74 : 110));
 		cfg.tcap    = pi < TCs.size() ? std::max(64, TCs[pi]) : (1 << 20);
 		cfg.fuse4   = env_int("BFB_FDMT_PACKED_FUSE", 1) != 0;
 		cfg.own_src = pi < PFs.size() ? PFs[pi] != 0 : (s0 == 1);    // default: the first pass (it reads HBM)
@@ -861,7 +863,7 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 		cudaGetDevice(&dev);
 		if( cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0 ) sm_count = 148;
 	}
-	const long waves = std::max(1, env_int("BFB_FDMT_PACKED_WAVES", 4));
+	const long waves = std::max(1, env_int("BFB_FDMT_PACKED_WAVES", 8));
 	long gx = div_up<long>(2L * sm_count * waves, (long)cp.nprog * nbatch);
 	gx = std::max<long>(1, std::min<long>(gx, q.ntile));
 	gx = div_up<long>(q.ntile, div_up<long>(q.ntile, gx));      // equal shares
@@ -906,13 +908,11 @@ static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int
 	int tmax = 0;
 	for( PackedPass const& cp : cps ) tmax = std::max(tmax, cp.T);
 	long C = std::max<long>(env_int("BFB_FDMT_PACKED_CHUNK", 2048), tmax);
-	// Items of one round: every (pass, program), producers first: about 1.5
-	// rounds of items are in flight, and an item should find what it waits for
-	// finished, not merely claimed -- with the first pass at the head of its
-	// round the distance (in claimed items) from a producer chunk to its
-	// consumers is the largest.  Inside a pass the heavy programs come first.
+	// Items of one round: every (pass, program); the last pass first (measured:
+	// with the producers first the consumers of the next round find them still
+	// running more often).  Inside a pass the heavy programs come first.
 	tmpl_->clear();
-	for( int k=0; k<(int)cps.size(); ++k ) {
+	for( int k=(int)cps.size()-1; k>=0; --k ) {
 		if( cps[k].nprog >= (1 << 24) ) return false;
 		for( int p=0; p<cps[k].nprog; ++p ) tmpl_->push_back((k << 24) | p);
 	}
@@ -920,7 +920,7 @@ static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int
 	// pass k+1 follows pass k by `lag` chunks: one more than the reach of a tile
 	// is enough for the claim order to be valid; a longer lag keeps the consumers
 	// away from producers that are still running (about 1.5 rounds are in flight)
-	*lag_ = std::max(1 + (int)div_up<long>(tmax, C), env_int("BFB_FDMT_PACKED_LAG", 1 + (int)div_up<long>(tmax, C)));
+	*lag_ = std::max(1 + (int)div_up<long>(tmax, C), env_int("BFB_FDMT_PACKED_LAG", 2 + (int)div_up<long>(tmax, C)));
 	return true;
 }
 static bool build_mega_template(BFfdmt_impl* plan) {
@@ -943,7 +943,7 @@ static size_t mega_geometry(std::vector<PackedPass> const& cps, long C, int lag,
 	int tmax = 0, lbmax = 0;
 	for( PackedPass const& cp : cps ) { tmax = std::max(tmax, cp.T); lbmax = std::max(lbmax, cp.lookback); }
 	// a writer must find its readers claimed in an earlier round (fdmt_packed.cuh)
-	const long want = C * (lag + div_up<long>(tmax + lbmax, C) + 1 + std::max(0, env_int("BFB_FDMT_PACKED_RING_EXTRA", 0)));
+	const long want = C * (lag + div_up<long>(tmax + lbmax, C) + 1 + std::max(0, env_int("BFB_FDMT_PACKED_RING_EXTRA", 2)));
 	long te = 0;
 	for( int k=0; k<n; ++k ) te = std::max(te, geom[k].te);
 	mg->nchunk = (int)div_up<long>(te - geom[0].tb, C);

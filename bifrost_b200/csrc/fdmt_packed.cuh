@@ -296,7 +296,9 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 				if( li == 0 ) slot_of[0][it->first] = k;
 				// 1-byte rows: aligned superset of the window (up to 15 bytes in front)
 				// plus the look-ahead of the last lane; word rows: two vectors of slack
-				o += (li == 0 && bytes) ? round_up<int>(len + 16 + 16, 16) : (len + 2 * VS) * esize;
+				// word rows get the full window capacity (+1 vector: b's look-ahead), so
+				// that shared-memory stores need no per-vector predicate
+				o += (li == 0 && bytes) ? round_up<int>(len + 16 + 16, 16) : (WLEN + VS) * esize;
 			}
 			const int rg = (sl == 0 && cfg.own_src) ? 2 : (sl & 1);
 			region[rg] = std::max(region[rg], o);
@@ -684,7 +686,6 @@ __device__ __forceinline__ void pk_bytes_widen_halo(const unsigned char* dbase, 
 __device__ __forceinline__ void pk_group4_op(const int4& A, const int4& B, const PackedSmem& S,
                                              const PackedTile& tl, int lane) {
 	unsigned char* dbase = S.dbase;
-	const int nvec = A.w >> PK_NVEC_SHIFT;
 	const int mask = (A.w >> PK_WO_SHIFT) & 3;
 	auto addr = [&](int f) { const int k = f & 0xFFF; return (uint32_t)S.ssrc[k].z + S.smis[k] + ((uint32_t)f >> 12) + 24u * lane; };
 	uint32_t s0[12], s1[13];
@@ -706,14 +707,12 @@ __device__ __forceinline__ void pk_group4_op(const int4& A, const int4& B, const
 		uint4* d = (uint4*)(dbase + A.x) + PK_LV_BYTES * lane;
 #pragma unroll
 		for( int j=0; j<PK_LV_BYTES; ++j )
-			if( PK_LV_BYTES * lane + j < nvec )
-				d[j] = make_uint4(s0[4*j] + s1[4*j+1], s0[4*j+1] + s1[4*j+2], s0[4*j+2] + s1[4*j+3], s0[4*j+3] + s1[4*j+4]);
+			d[j] = make_uint4(s0[4*j] + s1[4*j+1], s0[4*j+1] + s1[4*j+2], s0[4*j+2] + s1[4*j+3], s0[4*j+3] + s1[4*j+4]);
 	}
 	if( mask & 2 ) {
 		uint4* d = (uint4*)(dbase + B.x) + PK_LV_BYTES * lane;
 #pragma unroll
 		for( int j=0; j<PK_LV_BYTES; ++j )
-			if( PK_LV_BYTES * lane + j < nvec )
 				d[j] = make_uint4(s0[4*j]   + __funnelshift_r(s1[4*j],   s1[4*j+1], 16),
 				                  s0[4*j+1] + __funnelshift_r(s1[4*j+1], s1[4*j+2], 16),
 				                  s0[4*j+2] + __funnelshift_r(s1[4*j+2], s1[4*j+3], 16),
@@ -806,20 +805,22 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 	if( op.w & PK_STORE_G ) {
 		pk_store_out<ESZ, DSTK, LV>(av, op, nvec, P, tl, S.scratch, lane, warp);
 	} else {
+		// (rows have room for all 32 * LV vectors: lanes past the window write junk
+		// nobody reads)
 		uint4* d = (uint4*)(dbase + op.x) + LV * lane;
 #pragma unroll
-		for( int j=0; j<LV; ++j )
-			if( LV * lane + j < nvec ) d[j] = make_uint4(av[4*j], av[4*j+1], av[4*j+2], av[4*j+3]);
+		for( int j=0; j<LV; ++j ) d[j] = make_uint4(av[4*j], av[4*j+1], av[4*j+2], av[4*j+3]);
 	}
 }
 
 template<int ESZ, int SRCK, int DSTK, int LV>
 __device__ __forceinline__ void pk_levels(const PackedSmem& S, const PackedParams& P, const PackedTile& tl,
                                           int lev0, int lev1, int lane, int warp, int nwarp) {
-	for( int lev=lev0; lev<=lev1; ++lev ) {
-		const int4* list = S.sops + ((size_t)(lev - 1) * nwarp + warp) * P.slots;
+	const int slots = P.slots;
+	const int4* list = S.sops + ((lev0 - 1) * nwarp + warp) * slots;
+	for( int lev=lev0; lev<=lev1; ++lev, list += nwarp * slots ) {
 		int4 nxt = list[0];
-		for( int m=0; m<P.slots; ++m ) {
+		for( int m=0; m<slots; ++m ) {
 			const int4 op = nxt;
 			if( op.w == 0 ) break;
 			nxt = list[m + 1];                     // the last slot of a list is always a terminator

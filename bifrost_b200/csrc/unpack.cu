@@ -1,4 +1,5 @@
-// unpack.cu -- bfUnpack for sm_100a (device arrays).
+// unpack.cu -- bfUnpack for sm_100a (device arrays; system-space arrays are
+// unpacked by a host loop with the reference's CPU convention, as its ABI does).
 //
 // Replaces: src/unpack.cpp:242-535 (entry + dtype dispatch) with the device
 // kernels of src/gunpack.cu:41-294.  Bit-exact integer work.
@@ -13,15 +14,19 @@
 // align_msb).  `conjugated` mismatch between in and out negates the odd slots.
 // Outputs: i8/ci8 (signed in), u8 (unsigned in), or f32/cf32/f64/cf64
 // promoted from the signed 8-bit result.
+// System-space arrays (src/unpack.cpp:48-197): the same field extraction on the
+// host, except that signed 1-bit follows the reference's CPU convention there
+// (bit 1 -> -1, bit 0 -> 0; -128 / 0 when align_msb) -- the two conventions of
+// the reference differ and each space keeps its own.
 #include "core.hpp"
 
 #include <algorithm>
 
 namespace bfb {
 
-template<int NBIT, bool SIGNED>
-__device__ __forceinline__ void unpack_byte(unsigned ival, bool rev, bool msb, bool conj,
-                                            signed char (&o)[8 / NBIT]) {
+template<int NBIT, bool SIGNED, bool CPU1BIT = false>
+__host__ __device__ __forceinline__ void unpack_byte(unsigned ival, bool rev, bool msb, bool conj,
+                                                     signed char (&o)[8 / NBIT]) {
 	constexpr int K = 8 / NBIT;
 	constexpr unsigned MASK = (1u << NBIT) - 1;
 #pragma unroll
@@ -32,7 +37,8 @@ __device__ __forceinline__ void unpack_byte(unsigned ival, bool rev, bool msb, b
 		if( SIGNED ) {
 			signed char placed;
 			int down;
-			if( NBIT == 1 ) { placed = (signed char)((((~field) & 1u) << 7) | 0x40u); down = 6; }
+			if( NBIT == 1 && CPU1BIT ) { placed = (signed char)(field << 7); down = 7; }
+			else if( NBIT == 1 ) { placed = (signed char)((((~field) & 1u) << 7) | 0x40u); down = 6; }
 			else            { placed = (signed char)(field << (8 - NBIT));           down = 8 - NBIT; }
 			v = msb ? (int)placed : ((int)placed >> down);
 			if( conj && (j & 1) ) v = -v;
@@ -126,9 +132,43 @@ static BFstatus launch_unpack(const void* in, void* out, long nbyte, bool rev, b
 	return BF_STATUS_SUCCESS;
 }
 
+// System-space arrays: the same arithmetic in a host loop.
+template<int NBIT, bool SIGNED, typename Out>
+static BFstatus host_unpack(const void* in_, void* out_, long nbyte, bool rev, bool msb, bool conj) {
+	constexpr int K = 8 / NBIT;
+	const unsigned char* in = (const unsigned char*)in_;
+	Out* out = (Out*)out_;
+	for( long i=0; i<nbyte; ++i ) {
+		signed char o[K];
+		unpack_byte<NBIT, SIGNED, true>(in[i], rev, msb, conj, o);
+		for( int j=0; j<K; ++j ) {
+			if( sizeof(Out) == 1 ) ((signed char*)out)[i * K + j] = o[j];
+			else out[i * K + j] = (Out)o[j];
+		}
+	}
+	return BF_STATUS_SUCCESS;
+}
+
 template<int NBIT, bool SIGNED>
 static BFstatus unpack_out(BFdtype otype, const void* in, void* out, long nbyte, bool rev,
-                           bool msb, bool conj, cudaStream_t s) {
+                           bool msb, bool conj, cudaStream_t s, bool on_host = false) {
+	if( on_host ) {
+		switch( otype ) {
+		case BF_DTYPE_I8: case BF_DTYPE_CI8:
+			if( !SIGNED ) BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
+			return host_unpack<NBIT,SIGNED,signed char>(in, out, nbyte, rev, msb, conj);
+		case BF_DTYPE_U8:
+			if( SIGNED ) BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
+			return host_unpack<NBIT,SIGNED,signed char>(in, out, nbyte, rev, msb, conj);
+		case BF_DTYPE_F32: case BF_DTYPE_CF32:
+			if( !SIGNED ) BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
+			return host_unpack<NBIT,SIGNED,float>(in, out, nbyte, rev, msb, conj);
+		case BF_DTYPE_F64: case BF_DTYPE_CF64:
+			if( !SIGNED ) BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
+			return host_unpack<NBIT,SIGNED,double>(in, out, nbyte, rev, msb, conj);
+		default: BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
+		}
+	}
 	switch( otype ) {
 	case BF_DTYPE_I8: case BF_DTYPE_CI8:
 		if( !SIGNED ) BFB_FAIL(BF_STATUS_UNSUPPORTED_DTYPE);
@@ -158,9 +198,10 @@ BFstatus bfUnpack(BFarray const* in, BFarray const* out, BFbool align_msb) {
 	for( int d=0; d<in->ndim; ++d ) BFB_ASSERT(in->shape[d] == out->shape[d], BF_STATUS_INVALID_SHAPE);
 	BFB_ASSERT(dtype_is_complex(in->dtype) == dtype_is_complex(out->dtype), BF_STATUS_INVALID_DTYPE);
 	BFB_ASSERT(dtype_is_complex(in->dtype) || !in->conjugated, BF_STATUS_INVALID_DTYPE);
-	// The reference also unpacks host arrays on the CPU; this library is the
-	// device path only.
-	BFB_ASSERT(space_on_device(in->space) && space_on_device(out->space), BF_STATUS_UNSUPPORTED_SPACE);
+	// Both arrays on the device, or both in plain system memory (host loop, as
+	// src/unpack.cpp does for host arrays); a mix is not bridged here.
+	const bool on_host = in->space == BF_SPACE_SYSTEM && out->space == BF_SPACE_SYSTEM;
+	BFB_ASSERT(on_host || (space_on_device(in->space) && space_on_device(out->space)), BF_STATUS_UNSUPPORTED_SPACE);
 	int nbit = dtype_nbit_real(in->dtype);
 	BFB_ASSERT(nbit == 1 || nbit == 2 || nbit == 4, BF_STATUS_UNSUPPORTED_DTYPE);
 	int kind = dtype_kind(in->dtype);
@@ -187,18 +228,18 @@ BFstatus bfUnpack(BFarray const* in, BFarray const* out, BFbool align_msb) {
 	bool rev = in->big_endian != 0;           // host is little-endian
 	bool conj = (in->conjugated != 0) != (out->conjugated != 0);
 	bool msb = align_msb != 0;
-	cudaStream_t s = thread_stream();
+	cudaStream_t s = on_host ? nullptr : thread_stream();
 	BFB_TRY(
 		if( is_signed ) {
 			switch( nbit ) {
-			case 1:  return unpack_out<1,true >(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s);
-			case 2:  return unpack_out<2,true >(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s);
-			default: return unpack_out<4,true >(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s);
+			case 1:  return unpack_out<1,true >(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s, on_host);
+			case 2:  return unpack_out<2,true >(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s, on_host);
+			default: return unpack_out<4,true >(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s, on_host);
 			}
 		} else {
 			switch( nbit ) {
-			case 2:  return unpack_out<2,false>(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s);
-			default: return unpack_out<4,false>(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s);
+			case 2:  return unpack_out<2,false>(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s, on_host);
+			default: return unpack_out<4,false>(out->dtype, in->data, out->data, nbyte, rev, msb, conj, s, on_host);
 			}
 		}
 	);

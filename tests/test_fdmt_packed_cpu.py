@@ -241,7 +241,7 @@ def test_packed_schedule_of_the_baseline_plan():
     assert [(p['s0'], p['s1'], p['esize']) for p in passes] == [(1, 5, 2), (6, 9, 2), (10, 12, 4)]
     assert passes[0]['src_kind'] == 0 and passes[1]['dst_kind'] == 1 and passes[2]['dst_kind'] == 2
     for p in passes:
-        assert p['smem_bytes'] <= 75 * 1024 and p['T'] >= 256      # three CTAs per SM
+        assert p['smem_bytes'] <= 111 * 1024 and p['T'] >= 256     # two or three CTAs per SM
     ntime = 1200
     rng = np.random.default_rng(5)
     x = rng.integers(-128, 128, size=(nchan, ntime)).astype(np.int8)

@@ -88,3 +88,50 @@ def test_status_codes():
     d = bf.empty((4, 8), 'ci8', 'cuda')
     e = bf.empty((4, 8), 'ci16', 'cuda')
     assert _bf.bfUnpack(d.as_BFarray(), e.as_BFarray(), 0) == _bf.BF_STATUS_UNSUPPORTED_DTYPE
+
+
+# ---- system-space arrays: the host path of the ABI (src/unpack.cpp:48-197) ----
+@pytest.mark.parametrize("vec,big_endian,conj", KNOWN)
+@pytest.mark.parametrize("odtype", ['ci8', 'cf32'])
+def test_host_known_answers(vec, big_endian, conj, odtype):
+    """The reference's own known-answer vectors (test/test_unpack.py:33-97) through
+    bfUnpack on system-space arrays -- runs without a GPU."""
+    iarray = bf.ndarray(np.array(vec, np.uint8).reshape(3, 2).view(bf.DataType('ci4').as_numpy_dtype()),
+                        dtype='ci4')
+    if big_endian:
+        iarray = iarray.byteswap()
+    if conj:
+        iarray = iarray.conj()
+    out = bf.empty((3, 2), dtype=odtype, space='system')
+    bf.unpack(iarray, out)
+    out = np.asarray(out)
+    got = np.stack([out['re'], out['im']], -1) if odtype == 'ci8' else np.stack([out.real, out.imag], -1)
+    np.testing.assert_array_equal(got, ANSWER)
+
+
+def test_host_matches_oracle_all_modes():
+    """Every dtype / endianness / align_msb / conjugate combination on the host,
+    against the oracle's CPU convention (signed 1-bit: bit 1 -> -1, bit 0 -> 0)."""
+    rng = np.random.default_rng(2)
+    raw = rng.integers(0, 256, size=(5, 23), dtype=np.uint8)
+    for (idt, nbit, signed, cplx) in [('i4', 4, True, False), ('ci4', 4, True, True), ('i2', 2, True, False),
+                                      ('ci2', 2, True, True), ('i1', 1, True, False), ('ci1', 1, True, True),
+                                      ('u4', 4, False, False), ('u2', 2, False, False)]:
+        per = 8 // nbit // (2 if cplx else 1)
+        shape = (5, 23 * per)
+        odts = (['ci8', 'cf32'] if cplx else ['i8', 'f64']) if signed else ['u8']
+        for odt, big, msb, conj in itertools.product(odts, [False, True], [False, True],
+                                                     [False, True] if cplx else [False]):
+            a = bf.ndarray(space='system', shape=shape, dtype=idt, buffer=raw.ctypes.data)
+            a.bf.native = not big
+            a.bf.conjugated = conj
+            out = bf.empty(shape, dtype=odt, space='system')
+            bf.unpack(a, out, align_msb=msb)
+            o = np.asarray(out)
+            if cplx:
+                got = (np.stack([o['re'], o['im']], -1) if odt == 'ci8' else np.stack([o.real, o.imag], -1))
+            else:
+                got = o
+            want = ounpack.unpack(raw, nbit, signed, byte_reverse=big, align_msb=msb, conjugate=conj, gpu=False)
+            np.testing.assert_array_equal(got.reshape(want.shape).astype(np.float64), want.astype(np.float64),
+                                          err_msg=str((idt, odt, big, msb, conj)))
