@@ -920,7 +920,7 @@ static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int
 	// pass k+1 follows pass k by `lag` chunks: one more than the reach of a tile
 	// is enough for the claim order to be valid; a longer lag keeps the consumers
 	// away from producers that are still running (about 1.5 rounds are in flight)
-	*lag_ = std::max(1 + (int)div_up<long>(tmax, C), env_int("BFB_FDMT_PACKED_LAG", 2 + (int)div_up<long>(tmax, C)));
+	*lag_ = std::max(1 + (int)div_up<long>(tmax, C), env_int("BFB_FDMT_PACKED_LAG", 1 + (int)div_up<long>(tmax, C)));
 	return true;
 }
 static bool build_mega_template(BFfdmt_impl* plan) {
@@ -943,7 +943,7 @@ static size_t mega_geometry(std::vector<PackedPass> const& cps, long C, int lag,
 	int tmax = 0, lbmax = 0;
 	for( PackedPass const& cp : cps ) { tmax = std::max(tmax, cp.T); lbmax = std::max(lbmax, cp.lookback); }
 	// a writer must find its readers claimed in an earlier round (fdmt_packed.cuh)
-	const long want = C * (lag + div_up<long>(tmax + lbmax, C) + 1 + std::max(0, env_int("BFB_FDMT_PACKED_RING_EXTRA", 2)));
+	const long want = C * (lag + div_up<long>(tmax + lbmax, C) + 1 + std::max(0, env_int("BFB_FDMT_PACKED_RING_EXTRA", 0)));
 	long te = 0;
 	for( int k=0; k<n; ++k ) te = std::max(te, geom[k].te);
 	mg->nchunk = (int)div_up<long>(te - geom[0].tb, C);
