@@ -427,7 +427,7 @@ def main():
             ms = float(t.item())
         return ms
 
-    def timed(fn, nwarm, nstep, sampler=None):
+    def timed(fn, nwarm, nstep, sampler=None, post=None):
         for _ in range(nwarm):
             fn()
         barrier()
@@ -445,11 +445,14 @@ def main():
         clocks = None
         if sampler:
             # the timed region can be shorter than nvidia-smi's sampling period:
-            # keep the same load running (untimed) until a few samples exist
+            # keep the same load running (untimed) until a few samples exist.
+            # Only the rank that samples runs this, so with several ranks the
+            # post-roll must be collective-free (`post`): the other ranks are
+            # already waiting in max_over_ranks.
             t_end = time.time() + 1.5
             while len(sampler.lines) < 8 and time.time() < t_end:
                 for _ in range(5):
-                    fn()
+                    (post or fn)()
                 torch.cuda.synchronize()
             clocks = sampler.stop()
             clocks['window'] = 'timed steps + untimed post-roll of the same steps (nvidia-smi -lms 50)'
@@ -752,7 +755,7 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
         compute()
         gather()
 
-    ms_total, launches, clocks = timed(step_strong, args.warmup, args.steps, sampler)
+    ms_total, launches, clocks = timed(step_strong, args.warmup, args.steps, sampler, post=compute)
     ms_step = ms_total / args.steps
     ms_scatter = timed(scatter, 2, 5)[0] / 5
     ms_compute = timed(compute, 2, 5)[0] / 5

@@ -507,6 +507,11 @@ struct BFfdmt_impl {
 	int*   d_mega_tmpl = nullptr;
 	int*   d_mega_counters = nullptr;
 	size_t mega_counters_cap = 0;
+	// sharded execution (bfFdmtShardInit): this plan is rank `shard_rank` of
+	// `shard_nrank`; per pass the device list of the programs it runs
+	int    shard_rank = -1, shard_nrank = 0, shard_split = -1, shard_step = 0;
+	std::vector<std::vector<int> > shard_progs;
+	std::vector<int*> d_shard_progs;
 	// exec workspace
 	void*  own_exec_storage = nullptr;
 	size_t own_exec_size = 0;
@@ -538,6 +543,9 @@ struct BFfdmt_impl {
 			if( cp.d_hdr ) cudaFree(cp.d_hdr);
 		}
 		packed.clear();
+		for( int* q : d_shard_progs ) if( q ) cudaFree(q);
+		d_shard_progs.clear(); shard_progs.clear();
+		shard_rank = -1; shard_nrank = 0; shard_split = -1;
 		if( d_mega_tmpl ) cudaFree(d_mega_tmpl);
 		if( d_mega_counters ) cudaFree(d_mega_counters);
 		d_mega_tmpl = nullptr; d_mega_counters = nullptr; mega_counters_cap = 0; mega_ok = false;
@@ -735,7 +743,10 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 		PackedCfg cfg;
 		const size_t pi = passes.size();
 		cfg.D       = pi < Ds.size()  ? Ds[pi]  : (s0 == 1 ? 64 : 24);
-		cfg.nwarp   = std::max(1, std::min(8, pi < NWs.size() ? NWs[pi] : 8));
+		// 8 warps (three CTAs per SM) for the pass that reads the 1-byte input, 12 (two
+		// CTAs per SM, 24 warps) for the others -- measured: 0.866 vs 0.877 ms with 8
+		const bool nw8 = (s0 == 1 || (pi < LVs.size() && LVs[pi] == 5)) || env_int("BFB_FDMT_PACKED_MEGA", 0) != 0;   // (the persistent kernel runs 8 warps)
+		cfg.nwarp   = std::max(1, std::min(nw8 ? 8 : 16, pi < NWs.size() ? NWs[pi] : (nw8 ? 8 : 12)));
 		// three CTAs per SM for the pass that waits on HBM, two (larger delay blocks,
 		// fewer redundant rows) for the others -- measured optimum for config 2
 		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : (s0 == 1 ? 74 : 110));
@@ -743,6 +754,7 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 		cfg.fuse4   = env_int("BFB_FDMT_PACKED_FUSE", 1) != 0;
 		cfg.own_src = pi < PFs.size() ? PFs[pi] != 0 : (s0 == 1);    // default: the first pass (it reads HBM)
 		cfg.lv      = (pi < LVs.size() && LVs[pi] == 5) ? 5 : 3;
+		cfg.early   = env_int("BFB_FDMT_PACKED_EARLY", 1) != 0;
 		PackedPass cp;
 		bool ok = false;
 		// smaller delay blocks first (more programs, a little more redundancy),
@@ -757,6 +769,8 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 		}
 		if( !ok ) { passes.clear(); return false; }
 		cp.nrow_out = fin ? P.nrow(s1) : nout;
+		cp.out_rows.clear();
+		for( int r=0; r<P.nrow(s1); ++r ) if( out_index[r] >= 0 ) cp.out_rows.push_back(r);
 		passes.push_back(cp);
 		src_index = out_index;
 		s0 = s1 + 1;
@@ -765,9 +779,12 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 	return true;
 }
 
-static bool build_packed_schedule(FdmtPlan const& P, std::vector<PackedPass>* passes) {
+// `force_end` > 0: a pass must end at that step and ONE pass covers the steps
+// above it (sharded execution: bfFdmtShardInit).
+static bool build_packed_schedule(FdmtPlan const& P, std::vector<PackedPass>* passes, int force_end = 0) {
 	passes->clear();
-	if( env_int("BFB_FDMT_PACKED", 1) == 0 ) return false;
+	if( !force_end ) force_end = env_int("BFB_FDMT_PACKED_FORCE_END", 0);   // (CPU tests of the sharded schedule)
+	if( env_int("BFB_FDMT_PACKED", 1) == 0 && !force_end ) return false;
 	std::vector<std::vector<char> > used;
 	fdmt_used_rows(P, &used);
 	if( !fdmt_integer_safe(P, used) ) return false;
@@ -776,6 +793,21 @@ static bool build_packed_schedule(FdmtPlan const& P, std::vector<PackedPass>* pa
 	const int S16 = fdmt_last_u16_step(P);
 	const int U = std::min(S, S16 + 1);            // last step of the 16-bit part
 	std::vector<int> ends = env_int_list("BFB_FDMT_PACKED_SPLIT");
+	if( force_end ) {
+		if( force_end < 1 || force_end >= S || S - force_end > PK_MAXLEV ) return false;
+		if( force_end < U && U < S ) return false;   // (the steps above the split form one pass: it may not straddle the 16-bit limit)
+		for( int extra=0; extra<4; ++extra ) {
+			ends.clear();
+			int Ue = std::min(U, force_end);
+			int npu = std::min(Ue, div_up<int>(Ue, 5) + extra);
+			for( int k=1; k<=npu; ++k ) ends.push_back(std::min(Ue, div_up<int>(Ue * k, npu)));
+			int nf = force_end - Ue, npf = nf ? std::min(nf, div_up<int>(nf, 3) + extra) : 0;
+			for( int k=1; k<=npf; ++k ) ends.push_back(Ue + div_up<int>(nf * k, npf));
+			ends.push_back(S);
+			if( build_packed_passes(P, used, S, S16, U, ends, passes) ) return true;
+		}
+		return false;
+	}
 	if( !ends.empty() ) {
 		std::vector<int> e2;
 		for( int v : ends ) if( v >= 1 && v < S && (e2.empty() || v > e2.back()) ) e2.push_back(v);
@@ -840,20 +872,22 @@ static size_t packed_geometry(std::vector<PackedPass> const& passes, long ntime,
 	return std::max<size_t>(off, 512);
 }
 
-template<int ESZ, int SRCK, int DSTK, int LV>
+template<int ESZ, int SRCK, int DSTK, int LV, int NW = 8>
 static cudaError_t launch_packed_kernel(PackedParams const& q, dim3 grid, int threads, size_t smem, cudaStream_t st) {
 	static size_t attr_smem = 0;
 	if( smem > attr_smem ) {
-		cudaError_t e = cudaFuncSetAttribute(fdmt_packed_kernel<ESZ, SRCK, DSTK, LV>,
+		cudaError_t e = cudaFuncSetAttribute(fdmt_packed_kernel<ESZ, SRCK, DSTK, LV, NW>,
 		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if( e != cudaSuccess ) return e;
 		attr_smem = smem;
 	}
-	fdmt_packed_kernel<ESZ, SRCK, DSTK, LV><<<grid, threads, smem, st>>>(q);
+	fdmt_packed_kernel<ESZ, SRCK, DSTK, LV, NW><<<grid, threads, smem, st>>>(q);
 	return cudaGetLastError();
 }
 
-static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, long nbatch, cudaStream_t st) {
+static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, long nbatch, cudaStream_t st, int nprog = -1) {
+	if( nprog < 0 ) nprog = cp.nprog;
+	if( nprog == 0 ) return BF_STATUS_SUCCESS;
 	// CTAs walk their program's tiles with a stride: about `waves` launch waves
 	// of 2 CTAs per SM in total, so the op tables are copied to shared memory a
 	// few times per program instead of once per tile.
@@ -864,15 +898,17 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 		if( cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0 ) sm_count = 148;
 	}
 	const long waves = std::max(1, env_int("BFB_FDMT_PACKED_WAVES", 8));
-	long gx = div_up<long>(2L * sm_count * waves, (long)cp.nprog * nbatch);
+	long gx = div_up<long>(2L * sm_count * waves, (long)nprog * nbatch);
 	gx = std::max<long>(1, std::min<long>(gx, q.ntile));
 	gx = div_up<long>(q.ntile, div_up<long>(q.ntile, gx));      // equal shares
-	dim3 grid((unsigned)gx, (unsigned)cp.nprog, (unsigned)nbatch);
+	dim3 grid((unsigned)gx, (unsigned)nprog, (unsigned)nbatch);
 	const int threads = cp.nwarp * 32;
 	const size_t smem = cp.smem_bytes();
 	cudaError_t e = cudaErrorInvalidValue;
 #define BFB_CH_LAUNCH(E_, S_, D_) \
 	e = (cp.lv == 5 && S_ != PK_SRC_BYTES) ? launch_packed_kernel<E_, (S_ == PK_SRC_BYTES ? PK_SRC_SAME : S_), D_, 5>(q, grid, threads, smem, st) \
+	  : (cp.nwarp > 12 && S_ != PK_SRC_BYTES) ? launch_packed_kernel<E_, (S_ == PK_SRC_BYTES ? PK_SRC_SAME : S_), D_, 3, 16>(q, grid, threads, smem, st) \
+	  : (cp.nwarp > 8 && S_ != PK_SRC_BYTES)  ? launch_packed_kernel<E_, (S_ == PK_SRC_BYTES ? PK_SRC_SAME : S_), D_, 3, 12>(q, grid, threads, smem, st) \
 	                                        : launch_packed_kernel<E_, S_, D_, 3>(q, grid, threads, smem, st)
 	if( cp.esize == 2 ) {
 		if( cp.src_kind == PK_SRC_BYTES ) {
@@ -895,6 +931,44 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 }
 
 
+// Launches passes k0 .. k1-1 of the packed schedule (one kernel each).
+// `lists` (may be NULL): per pass a device list of the programs to run and
+// its length -- sharded execution.
+struct PackedProgList { const int* d = nullptr; int n = -1; };
+static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istride, long ibatch, bool is_signed,
+                                  void* outp, long ostride, long obatch, long ntime, long nbatch, char* ws,
+                                  std::vector<PackedGeom> const& geom, int k0, int k1, PackedProgList const* lists) {
+	cudaStream_t cst = plan->get_stream();
+	const int npass = (int)plan->packed.size();
+	for( int k=k0; k<k1; ++k ) {
+		PackedPass const& cp = plan->packed[k];
+		PackedParams q;
+		memset(&q, 0, sizeof(q));
+		if( k > 0 ) {
+			q.src = ws + geom[k-1].offset; q.sstride = geom[k-1].stride;
+			q.sbatch = (long)plan->packed[k-1].nrow_out * geom[k-1].stride; q.src_tb = geom[k-1].tb;
+		}
+		if( k == npass - 1 ) { q.dst = outp; q.dstride = ostride; q.dbatch = obatch; q.dst_tb = 0; }
+		else {
+			q.dst = ws + geom[k].offset; q.dstride = geom[k].stride;
+			q.dbatch = (long)cp.nrow_out * geom[k].stride; q.dst_tb = geom[k].tb;
+		}
+		q.ops = cp.d_ops; q.srcs = cp.d_src; q.hdr = cp.d_hdr;
+		q.raw = raw; q.rstride = istride; q.rbatch = ibatch;
+		q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
+		q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
+		q.is_signed = is_signed;
+		q.prefetch = cp.prefetch ? 1 : 0; q.early = cp.early ? 1 : 0;
+		q.src_rl = k > 0 ? geom[k-1].stride : 1;           // linear workspaces: the rings never wrap
+		q.dst_rl = k == npass - 1 ? (1L << 62) : geom[k].stride;
+		q.plist = lists ? lists[k].d : nullptr;
+		BFstatus ls = launch_packed_pass(cp, q, nbatch, cst, lists ? lists[k].n : -1);
+		if( ls != BF_STATUS_SUCCESS ) return ls;
+	}
+	return BF_STATUS_SUCCESS;
+}
+
+
 // ---- persistent single-launch form -------------------------------------------
 static int mega_kind(PackedPass const& cp) {
 	int kind = cp.esize == 2 ? cp.src_kind * 3 + cp.dst_kind : (cp.dst_kind == PK_DST_FINAL ? 7 : 6);
@@ -906,7 +980,10 @@ static int mega_kind(PackedPass const& cp) {
 static bool mega_template_host(std::vector<PackedPass> const& cps, long* C_, int* lag_, std::vector<int>* tmpl_) {
 	if( cps.empty() || (int)cps.size() > PK_MAXPASS || env_int("BFB_FDMT_PACKED_MEGA", 0) == 0 ) return false;
 	int tmax = 0;
-	for( PackedPass const& cp : cps ) tmax = std::max(tmax, cp.T);
+	for( PackedPass const& cp : cps ) {
+		tmax = std::max(tmax, cp.T);
+		if( cp.nwarp != 8 ) return false;          // (the persistent kernel runs 8 warps)
+	}
 	long C = std::max<long>(env_int("BFB_FDMT_PACKED_CHUNK", 2048), tmax);
 	// Items of one round: every (pass, program); the last pass first (measured:
 	// with the producers first the consumers of the next round find them still
@@ -1097,6 +1174,140 @@ BFstatus bfFdmtTileQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	return BF_STATUS_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------
+// Sharded execution (B200 extension): the FULL-BAND
+// transform over `nrank` cooperating plans, one per GPU.  Every rank calls
+// bfFdmtInit with the same (full-band) arguments and then bfFdmtShardInit.
+// The merge tree has `nrank` sub-bands at the split step; rank g owns the
+// channels of sub-band g.
+//   phase 0: the passes up to the split step, restricted to the programs of
+//            the own sub-tree (they read only the rank's channels and write
+//            only the rank's rows of the split-step workspace);
+//   exchange (the caller: NCCL over NVLink): every rank's block of rows of
+//            the split-step workspace to every other rank, same offsets;
+//   phase 1: the rank's share (every nrank-th delay block) of the programs of
+//            the last pass, from the now complete split-step rows, to `out`.
+// The rows written by all ranks in phase 1 are disjoint and together form the
+// bank of the single-GPU transform, bit for bit (same tables, same kernels).
+// ---------------------------------------------------------------------------
+BFstatus bfFdmtShardInit(BFfdmt plan, int rank, int nrank) {
+	BFB_ASSERT(plan, BF_STATUS_INVALID_HANDLE);
+	BFB_ASSERT(plan->planned, BF_STATUS_INVALID_STATE);
+	BFB_ASSERT(nrank >= 2 && nrank <= 8 && (nrank & (nrank - 1)) == 0 && rank >= 0 && rank < nrank, BF_STATUS_INVALID_ARGUMENT);
+	FdmtPlan const& P = plan->plan;
+	int sx = -1;
+	for( int s=1; s<P.nstep()-1; ++s ) if( (int)P.bands[s].size() == nrank ) sx = s;
+	BFB_ASSERT(sx >= 1 && P.nchan % nrank == 0, BF_STATUS_UNSUPPORTED_SHAPE);
+	const int cpr = P.nchan / nrank;
+	for( FdmtBand const& b : P.bands[sx] ) BFB_ASSERT(b.nchan == cpr, BF_STATUS_UNSUPPORTED_SHAPE);
+	std::vector<PackedPass> cps;
+	bool ok = false;
+	BFB_TRY(ok = build_packed_schedule(P, &cps, sx));
+	BFB_ASSERT(ok && cps.size() >= 2 && cps[cps.size()-2].s1 == sx, BF_STATUS_UNSUPPORTED);
+	// replace the plan's schedule
+	for( PackedPass& cp : plan->packed ) {
+		if( cp.d_ops ) cudaFree(cp.d_ops);
+		if( cp.d_src ) cudaFree(cp.d_src);
+		if( cp.d_hdr ) cudaFree(cp.d_hdr);
+	}
+	plan->packed.clear();
+	for( int* q : plan->d_shard_progs ) if( q ) cudaFree(q);
+	plan->d_shard_progs.clear(); plan->shard_progs.clear();
+	plan->mega_ok = false;
+	plan->packed.swap(cps);
+	BFB_ASSERT(upload_packed(&plan->packed), BF_STATUS_MEM_ALLOC_FAILED);
+	const int npass = (int)plan->packed.size();
+	plan->shard_progs.assign(npass, std::vector<int>());
+	plan->d_shard_progs.assign(npass, nullptr);
+	for( int k=0; k<npass; ++k ) {
+		PackedPass const& cp = plan->packed[k];
+		for( int p=0; p<cp.nprog; ++p ) {
+			bool mine = (k == npass - 1) ? (p % nrank == rank)
+			                             : (P.bands[cp.s1][cp.prog_band[p]].chan0 / cpr == rank);
+			if( mine ) plan->shard_progs[k].push_back(p);
+		}
+		size_t bytes = std::max<size_t>(1, plan->shard_progs[k].size()) * sizeof(int);
+		BFB_CUDA(cudaMalloc((void**)&plan->d_shard_progs[k], bytes), BF_STATUS_MEM_ALLOC_FAILED);
+		if( !plan->shard_progs[k].empty() )
+			BFB_CUDA(cudaMemcpy(plan->d_shard_progs[k], plan->shard_progs[k].data(), plan->shard_progs[k].size() * sizeof(int),
+			                    cudaMemcpyHostToDevice), BF_STATUS_MEM_OP_FAILED);
+	}
+	plan->shard_rank = rank; plan->shard_nrank = nrank; plan->shard_split = npass - 2; plan->shard_step = sx;
+	return BF_STATUS_SUCCESS;
+}
+
+// in: the rank's own channels [nchan/nrank][ntime] (i8 / u8, input order);
+// out: [max_delay][ntime] f32 (phase 1 writes the rank's delay blocks only).
+// Workspace protocol as bfFdmtExecute (exec_storage NULL: size query).
+BFstatus bfFdmtShardExecute(BFfdmt plan, int phase, BFarray const* in, BFarray const* out,
+                            void* exec_storage, BFsize* exec_storage_size) {
+	BFB_ASSERT(plan, BF_STATUS_INVALID_HANDLE);
+	BFB_ASSERT(in && out && exec_storage_size, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(plan->planned && plan->shard_nrank >= 2, BF_STATUS_INVALID_STATE);
+	BFB_ASSERT(phase == 0 || phase == 1, BF_STATUS_INVALID_ARGUMENT);
+	FdmtPlan const& P = plan->plan;
+	const int cpr = P.nchan / plan->shard_nrank;
+	BFB_ASSERT(in->ndim == 2 && out->ndim == 2, BF_STATUS_UNSUPPORTED_SHAPE);
+	BFB_ASSERT(in->shape[0] == cpr && out->shape[0] == P.max_delay && in->shape[1] == out->shape[1], BF_STATUS_INVALID_SHAPE);
+	BFB_ASSERT(in->dtype == BF_DTYPE_I8 || in->dtype == BF_DTYPE_U8, BF_STATUS_UNSUPPORTED_DTYPE);
+	BFB_ASSERT(out->dtype == BF_DTYPE_F32, BF_STATUS_UNSUPPORTED_DTYPE);
+	const long ntime = in->shape[1];
+	std::vector<PackedGeom> geom;
+	size_t need = 0;
+	BFB_TRY(need = packed_geometry(plan->packed, ntime, 1, &geom));
+	if( !exec_storage ) { *exec_storage_size = need; return BF_STATUS_SUCCESS; }
+	BFB_ASSERT(*exec_storage_size >= need, BF_STATUS_INSUFFICIENT_STORAGE);
+	BFB_ASSERT(space_on_device(in->space) && space_on_device(out->space), BF_STATUS_UNSUPPORTED_SPACE);
+	BFB_ASSERT(in->strides[1] == 1 && out->strides[1] == 4 && in->strides[0] > 0 &&
+	           out->strides[0] > 0 && out->strides[0] % 4 == 0, BF_STATUS_UNSUPPORTED_STRIDE);
+	if( ntime == 0 ) return BF_STATUS_SUCCESS;
+	const long istride = in->strides[0], ostride = out->strides[0] / 4;
+	// the tables index input channels of the full band: shift the base so that the
+	// rank's first channel lands on row 0 of `in`
+	const long c_first = P.reverse_band ? (long)P.nchan - (long)(plan->shard_rank + 1) * cpr : (long)plan->shard_rank * cpr;
+	const char* raw = (const char*)in->data - c_first * istride;
+	const int npass = (int)plan->packed.size();
+	std::vector<PackedProgList> lists(npass);
+	for( int k=0; k<npass; ++k ) { lists[k].d = plan->d_shard_progs[k]; lists[k].n = (int)plan->shard_progs[k].size(); }
+	const int k0 = phase == 0 ? 0 : npass - 1, k1 = phase == 0 ? npass - 1 : npass;
+	return run_packed_passes(plan, raw, istride, 0, in->dtype == BF_DTYPE_I8, out->data, ostride, 0,
+	                         ntime, 1, (char*)exec_storage, geom, k0, k1, lists.data());
+}
+
+// Layout of the exchange and of the output for a gulp of `ntime` samples:
+//   info[0] byte offset of the split-step rows in the workspace, [1] row pitch
+//   in bytes, [2] rows, [3] bytes per element, [4] nrank, [5] split step,
+//   [6 .. 6+nrank] first row of every rank's block (and the end),
+//   then n = number of delay blocks of the last pass and n triples
+//   (first delay, delays, owning rank).  *ninfo: capacity in / used out.
+BFstatus bfFdmtShardQuery(BFfdmt plan, long ntime, long* info, int* ninfo) {
+	BFB_ASSERT(plan, BF_STATUS_INVALID_HANDLE);
+	BFB_ASSERT(info && ninfo, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(plan->planned && plan->shard_nrank >= 2, BF_STATUS_INVALID_STATE);
+	FdmtPlan const& P = plan->plan;
+	std::vector<PackedGeom> geom;
+	BFB_TRY(packed_geometry(plan->packed, ntime, 1, &geom));
+	const int ks = plan->shard_split, nrank = plan->shard_nrank;
+	PackedPass const& sp = plan->packed[ks];
+	PackedPass const& fp = plan->packed.back();
+	const long esz = (sp.dst_kind == PK_DST_CVT) ? 4 : sp.esize;
+	std::vector<long> v;
+	v.push_back((long)geom[ks].offset); v.push_back(geom[ks].stride * esz); v.push_back(sp.nrow_out);
+	v.push_back(esz); v.push_back(nrank); v.push_back(plan->shard_step);
+	for( int g=0; g<=nrank; ++g ) {
+		// first compact row whose step row lies in band g or above
+		const int r0 = g < nrank ? P.bands[plan->shard_step][g].row0 : P.nrow(plan->shard_step);
+		long c = (long)(std::lower_bound(sp.out_rows.begin(), sp.out_rows.end(), r0) - sp.out_rows.begin());
+		v.push_back(c);
+	}
+	v.push_back(fp.nprog);
+	for( int p=0; p<fp.nprog; ++p ) { v.push_back(fp.prog_row0[p]); v.push_back(fp.prog_nrow[p]); v.push_back(p % nrank); }
+	BFB_ASSERT(*ninfo >= (int)v.size(), BF_STATUS_INSUFFICIENT_STORAGE);
+	memcpy(info, v.data(), v.size() * sizeof(long));
+	*ninfo = (int)v.size();
+	return BF_STATUS_SUCCESS;
+}
+
 // Test hook: the tables of pass `pass` of the packed-integer schedule
 // (pass < 0: only header[0] = number of passes, 0 when the schedule does not
 // apply).  tests/test_fdmt_packed_cpu.py interprets them with numpy.
@@ -1117,7 +1328,7 @@ BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 	int h[24] = { cp.s0, cp.s1, cp.nlev, cp.esize, cp.src_kind, cp.dst_kind, cp.T, cp.nprog,
 	              cp.nwarp, cp.slots, cp.src_slots, cp.data_bytes, cp.lookback, cp.nrow_out,
 	              (int)cp.smem_bytes(), (int)std::min<long>(cp.nops, 1L << 30), cp.lv, cp.fused ? 1 : 0,
-	              cp.prefetch ? 1 : 0, 0, 0, 0, 0, 0 };
+	              cp.prefetch ? 1 : 0, cp.early ? 1 : 0, 0, 0, 0, 0 };
 	memcpy(header, h, sizeof(h));
 	if( ops ) memcpy(ops, cp.ops.data(), cp.ops.size() * sizeof(int4));
 	if( src ) memcpy(src, cp.src.data(), cp.src.size() * sizeof(int4));
@@ -1410,7 +1621,7 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 				q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
 				q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
 				q.is_signed = (in->dtype == BF_DTYPE_I8);
-				q.prefetch = cp.prefetch ? 1 : 0;
+				q.prefetch = cp.prefetch ? 1 : 0; q.early = cp.early ? 1 : 0;
 				mp.kind = mega_kind(cp); mp.nprog = cp.nprog; mp.lookback = cp.lookback; mp.nt = geom[k].nt;
 			}
 			long grid = std::min<long>(M.total, (long)mega_blocks_per_sm * mega_sms);
@@ -1420,36 +1631,9 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
 		return BF_STATUS_SUCCESS;
 	}
-	if( use_packed ) {
-		cudaStream_t cst = plan->get_stream();
-		char* ws = (char*)exec_storage;
-		const int npass = (int)plan->packed.size();
-		for( int k=0; k<npass; ++k ) {
-			PackedPass const& cp = plan->packed[k];
-			PackedParams q;
-			memset(&q, 0, sizeof(q));
-			if( k > 0 ) {
-				q.src = ws + geom[k-1].offset; q.sstride = geom[k-1].stride;
-				q.sbatch = (long)plan->packed[k-1].nrow_out * geom[k-1].stride; q.src_tb = geom[k-1].tb;
-			}
-			if( k == npass - 1 ) { q.dst = out->data; q.dstride = ostride; q.dbatch = obatch; q.dst_tb = 0; }
-			else {
-				q.dst = ws + geom[k].offset; q.dstride = geom[k].stride;
-				q.dbatch = (long)cp.nrow_out * geom[k].stride; q.dst_tb = geom[k].tb;
-			}
-			q.ops = cp.d_ops; q.srcs = cp.d_src; q.hdr = cp.d_hdr;
-			q.raw = in->data; q.rstride = istride; q.rbatch = ibatch;
-			q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
-			q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
-			q.is_signed = (in->dtype == BF_DTYPE_I8);
-			q.prefetch = cp.prefetch ? 1 : 0;
-			q.src_rl = k > 0 ? geom[k-1].stride : 1;           // linear workspaces: the rings never wrap
-			q.dst_rl = k == npass - 1 ? (1L << 62) : geom[k].stride;
-			BFstatus ls = launch_packed_pass(cp, q, nbatch, cst);
-			if( ls != BF_STATUS_SUCCESS ) return ls;
-		}
-		return BF_STATUS_SUCCESS;
-	}
+	if( use_packed )
+		return run_packed_passes(plan, in->data, istride, ibatch, in->dtype == BF_DTYPE_I8, out->data, ostride, obatch,
+		                         ntime, nbatch, (char*)exec_storage, geom, 0, (int)plan->packed.size(), nullptr);
 
 	float* buf_a = (float*)exec_storage;
 	float* buf_b = buf_a + (size_t)nbatch * sbatchstride;

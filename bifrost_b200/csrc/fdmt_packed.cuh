@@ -79,6 +79,7 @@ struct PackedCfg {
 	bool fuse4 = true;       // fuse the first two steps of a byte pass where the plan allows
 	bool own_src = true;     // the staged source gets a shared-memory region of its own (next-tile prefetch)
 	int lv = 3;              // 16-byte vectors per lane per row (odd: conflict-free lane stride); 3 or 5
+	bool early = true;       // no region of its own for the source: request the next tile's rows before the last level
 };
 
 struct PackedPass {
@@ -86,6 +87,8 @@ struct PackedPass {
 	int esize = 2;           // 2: packed u16 accumulators, 4: fp32
 	bool fused = false;      // byte pass: op level 1 produces the rows of step s0+1 (PK_GROUP4)
 	bool prefetch = false;   // the source has its own region: the next tile's rows are requested early
+	bool early = false;      // the source shares region 0: the next tile's rows are requested before the last level
+	                         // (odd level counts: the two regions swap roles from tile to tile, hdr.w = region size)
 	int lv = 3;              // 16-byte vectors per lane per row
 	int src_kind = PK_SRC_SAME, dst_kind = PK_DST_SAME;
 	int T = 0, nprog = 0, nwarp = 0, slots = 0, src_slots = 0;
@@ -95,16 +98,16 @@ struct PackedPass {
 	long nops = 0;           // ops per time tile, all programs
 	std::vector<int4> ops;   // [prog][level-1][warp][slot]
 	std::vector<int4> src;   // [prog][slot]: x row, y -smax, z shared byte offset, w samples; w == 0 ends
-	std::vector<int4> hdr;   // [prog]: x channels of the output band, y source rows, z staged bytes (workspace sources)
+	std::vector<int4> hdr;   // [prog]: x channels of the output band, y source rows, z staged bytes (workspace sources), w region size (mirrored tiles)
+	std::vector<int> prog_band, prog_row0, prog_nrow;   // [prog]: band of step s1, first step-s1 row, rows (sharding)
+	std::vector<int> out_rows;                          // [compact output row] -> row of step s1 (filled by the pass builder's caller)
 	int4* d_ops = nullptr; int4* d_src = nullptr; int4* d_hdr = nullptr;
 	int vs() const { return 16 / esize; }
 	size_t table_bytes() const {
 		return 16 + ((size_t)nlev * nwarp * slots + src_slots + 1) * sizeof(int4) + (size_t)round_up<int>(src_slots, 16);
 	}
 	size_t smem_bytes() const {
-		size_t b = table_bytes();
-		if( dst_kind == PK_DST_FINAL ) b += (size_t)nwarp * 32 * lv * vs() * sizeof(float);
-		return b + (size_t)data_bytes;
+		return table_bytes() + (size_t)data_bytes;
 	}
 };
 
@@ -253,6 +256,11 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 	const int nopl = fuse ? nlev - 1 : nlev;
 	auto step_level = [&](int ol) { return fuse ? ol + 1 : ol; };     // op level -> tree level
 	cp->s0 = s0; cp->s1 = s1; cp->nlev = nopl; cp->esize = esize; cp->fused = fuse; cp->prefetch = cfg.own_src; cp->lv = LV;
+	// Source in region 0 (no region of its own): with an even number of op levels
+	// region 0 is free again while the last level runs (it reads region 1), with
+	// an odd number region 1 is -- then the next tile is laid out mirrored.
+	cp->early = cfg.early && !cfg.own_src && !bytes && nopl >= 2;
+	const bool swap = cp->early && (nopl & 1);
 	cp->src_kind = src_kind; cp->dst_kind = dst_kind;
 	cp->T = T; cp->nprog = (int)progs.size(); cp->nwarp = nwarp; cp->lookback = lookback;
 	int slots = 1, src_slots = 1;
@@ -303,6 +311,7 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 			const int rg = (sl == 0 && cfg.own_src) ? 2 : (sl & 1);
 			region[rg] = std::max(region[rg], o);
 		}
+		if( swap ) region[0] = region[1] = std::max(region[0], region[1]);
 		// layout: [source (if it has its own region)][even stored levels][odd stored levels]
 		for( int sl=(cfg.own_src ? 1 : 0); sl<nopl; ++sl ) {
 			const int li = sl == 0 ? 0 : step_level(sl);
@@ -321,7 +330,7 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 				staged += (long)len * esize;
 			}
 		}
-		cp->hdr[p] = make_int4(P.bands[s1][progs[p].band].nchan, (int)need[0].size(), bytes ? 0 : (int)staged, 0);
+		cp->hdr[p] = make_int4(P.bands[s1][progs[p].band].nchan, (int)need[0].size(), bytes ? 0 : (int)staged, swap ? region[0] : 0);
 		for( int ol=1; ol<=nopl; ++ol ) {
 			const int li = step_level(ol);
 			int4* base = &cp->ops[((size_t)p * nopl + (ol - 1)) * nwarp * slots];
@@ -393,6 +402,12 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 			}
 		}
 	}
+	cp->prog_band.clear(); cp->prog_row0.clear(); cp->prog_nrow.clear();
+	for( size_t p=0; p<progs.size(); ++p ) {
+		cp->prog_band.push_back(progs[p].band);
+		cp->prog_row0.push_back(progs[p].rows.front());
+		cp->prog_nrow.push_back((int)progs[p].rows.size());
+	}
 	cp->data_bytes = data_max + (32 * LV + 4) * 16;        // slack: lanes past a row's end still load
 	if( cp->smem_bytes() > (size_t)cfg.smem_cap ) PK_FAIL(12);
 	return true;
@@ -413,7 +428,9 @@ struct PackedParams {
 	int  T, nlev, slots, src_slots;
 	int  is_signed;
 	int  prefetch;                                   // the source region is not reused by merged rows
+	int  early;                                      // else: request the next tile's rows before the last level
 	long src_rl, dst_rl;                             // ring lengths (columns) of the workspaces; >= width: linear
+	const int* plist;                                // programs to run (grid.y entries), NULL: all of them
 };
 
 // Per (CTA, tile) values.
@@ -426,7 +443,7 @@ struct PackedTile {
 };
 
 struct PackedSmem {
-	uint64_t* mbar; int4* sops; int4* ssrc; int4* shdr; unsigned char* smis; float* scratch; unsigned char* dbase;
+	uint64_t* mbar; int4* sops; int4* ssrc; int4* shdr; unsigned char* smis; unsigned char* dbase;
 };
 
 namespace packed_dev {
@@ -460,15 +477,13 @@ template<int ESZ> __device__ __forceinline__ uint32_t pk_add(uint32_t a, uint32_
 
 template<int ESZ, int DSTK, int LV>
 __device__ __forceinline__ PackedSmem pk_carve(unsigned char* smem, const PackedParams& P, int nwarp) {
-	constexpr int LS = LV * (16 / ESZ);
 	PackedSmem S;
 	S.mbar = (uint64_t*)smem;                       // fixed place: it outlives the items of the persistent kernel
 	S.sops = (int4*)(smem + 16);
 	S.ssrc = S.sops + P.nlev * nwarp * P.slots;
 	S.shdr = S.ssrc + P.src_slots;
 	S.smis = (unsigned char*)(S.shdr + 1);
-	S.scratch = (float*)(S.smis + ((P.src_slots + 15) & ~15));
-	S.dbase = (unsigned char*)(S.scratch + (DSTK == PK_DST_FINAL ? nwarp * 32 * LS : 0));
+	S.dbase = S.smis + ((P.src_slots + 15) & ~15);
 	return S;
 }
 // Copies the program's tables to shared memory (no barrier inside).
@@ -493,7 +508,7 @@ __device__ __forceinline__ void pk_load_tables(const PackedSmem& S, const Packed
 //     outside the gulp, then every warp's lane 0 waits on the mbarrier.
 template<int ESZ, int SRCK>
 __device__ __forceinline__ void pk_stage_issue(const PackedSmem& S, const PackedParams& P, long t0, long soff, long roff,
-                                               int lane) {
+                                               int lane, int flip = 0) {
 	const int4 hdr = S.shdr[0];
 	// (the rows may have been written by other SMs through the generic proxy
 	// moments ago -- persistent kernel -- and shared memory was last read by
@@ -532,7 +547,7 @@ __device__ __forceinline__ void pk_stage_issue(const PackedSmem& S, const Packed
 			const int4 e = S.ssrc[k];
 			const long c0 = (t0 + e.y - P.src_tb) % P.src_rl;
 			const unsigned char* g = src + (long)e.x * P.sstride * ESZ;
-			unsigned char* d = S.dbase + e.z;
+			unsigned char* d = S.dbase + e.z + flip;
 			const long n1 = min((long)e.w, P.src_rl - c0);
 			bulk_g2s(d, g + c0 * ESZ, (uint32_t)n1 * ESZ, S.mbar);
 			if( n1 < e.w ) bulk_g2s(d + n1 * ESZ, g, (uint32_t)(e.w - n1) * ESZ, S.mbar);
@@ -563,27 +578,67 @@ __device__ __forceinline__ void pk_stage_finish(const PackedSmem& S, const Packe
 	__syncwarp();
 }
 
+// Diagonal store of fdmt.cu:141-147: sample i of the tile (lane l holds
+// i = LS*l .. LS*l + LS-1 in f[]) belongs at row[t0 + i - d] for d <= t0 + i <
+// ntime.  The row's start has whatever alignment d, t0 and the caller's pitch
+// give it, so the lanes regroup their samples on the 16-byte lines of the
+// OUTPUT (three values come from the next lane by shuffle) and write float4s;
+// what is left at the ends of the tile / gulp goes out as scalars.
+template<int LS, int E>
+__device__ __forceinline__ void pk_diag_groups(const float (&x)[LS + 3], float* g, int ibase, int lo, int hi, int lane) {
+#pragma unroll
+	for( int q=0; q<LS/4; ++q ) {
+		const int i0 = ibase + E + 4 * q;
+		const float v0 = x[E + 4*q], v1 = x[E + 4*q + 1], v2 = x[E + 4*q + 2], v3 = x[E + 4*q + 3];
+		if( i0 >= lo && i0 + 4 <= hi ) __stcs((float4*)(g + i0), make_float4(v0, v1, v2, v3));
+		else if( i0 + 4 > lo && i0 < hi ) {
+			if( i0     >= lo && i0     < hi ) __stcs(g + i0,     v0);
+			if( i0 + 1 >= lo && i0 + 1 < hi ) __stcs(g + i0 + 1, v1);
+			if( i0 + 2 >= lo && i0 + 2 < hi ) __stcs(g + i0 + 2, v2);
+			if( i0 + 3 >= lo && i0 + 3 < hi ) __stcs(g + i0 + 3, v3);
+		}
+	}
+	if( E > 0 && lane == 0 ) {
+		// the tile's first E samples precede the first full line
+#pragma unroll
+		for( int j=0; j<E; ++j ) if( j >= lo && j < hi ) __stcs(g + j, x[j]);
+	}
+}
+template<int LS>
+__device__ __forceinline__ void pk_store_diag(const float (&f)[LS], long d, const PackedParams& P, const PackedTile& tl, int lane) {
+	float* row = (float*)P.dst + tl.doff + d * P.dstride;
+	const long c0 = tl.t0 - d;                              // column of the tile's first sample
+	float* g = row + c0;                                    // g[i]: where sample i goes
+	const int e = (int)((-(long)(((uintptr_t)row >> 2) + c0)) & 3);   // first i on a 16-byte line
+	const long lo_l = d - tl.t0, hi_l = P.ntime - tl.t0;
+	const int lo = lo_l > 0 ? (int)min(lo_l, (long)P.T) : 0;
+	const int hi = hi_l < (long)P.T ? (int)max(hi_l, 0L) : P.T;
+	float x[LS + 3];
+#pragma unroll
+	for( int k=0; k<LS; ++k ) x[k] = f[k];
+#pragma unroll
+	for( int k=0; k<3; ++k ) x[LS + k] = __shfl_down_sync(0xffffffffu, f[k], 1);
+	const int ibase = LS * lane;
+	switch( e ) {
+	case 0:  pk_diag_groups<LS, 0>(x, g, ibase, lo, hi, lane); break;
+	case 1:  pk_diag_groups<LS, 1>(x, g, ibase, lo, hi, lane); break;
+	case 2:  pk_diag_groups<LS, 2>(x, g, ibase, lo, hi, lane); break;
+	default: pk_diag_groups<LS, 3>(x, g, ibase, lo, hi, lane); break;
+	}
+}
+
 // A finished row of the pass's top level -> pass output (same element type),
-// or, for an fp32 pass that ends the plan, the diagonal store of fdmt.cu:141-147.
+// or, for an fp32 pass that ends the plan, the diagonal store.
 // Workspaces are rings in time: column = (t - tb) mod ring length.
 template<int ESZ, int DSTK, int LV>
 __device__ __forceinline__ void pk_store_out(const uint32_t (&o)[4*LV], const int4& op, int nvec,
-                                             const PackedParams& P, const PackedTile& tl, float* scratch, int lane, int warp) {
-	constexpr int VS = 16 / ESZ, LS = LV * VS;
+                                             const PackedParams& P, const PackedTile& tl, int lane) {
+	constexpr int VS = 16 / ESZ;
 	if( DSTK == PK_DST_FINAL ) {
-		float* sc = scratch + (size_t)warp * 32 * LS;
-		__syncwarp();
+		float f[4*LV];
 #pragma unroll
-		for( int j=0; j<LV; ++j )
-			*(uint4*)(sc + LS * lane + 4 * j) = make_uint4(o[4*j], o[4*j+1], o[4*j+2], o[4*j+3]);
-		__syncwarp();
-		const long d = op.x;
-		float* g = (float*)P.dst + tl.doff + d * P.dstride - d + tl.t0;
-#pragma unroll 4
-		for( int i=lane; i<P.T; i+=32 ) {
-			const long t = tl.t0 + i;
-			if( t >= d && t < P.ntime ) __stcs(g + i, sc[i]);
-		}
+		for( int k=0; k<4*LV; ++k ) f[k] = __uint_as_float(o[k]);
+		pk_store_diag<4*LV>(f, (long)op.x, P, tl, lane);
 	} else {
 		unsigned char* g = (unsigned char*)P.dst + (tl.doff + (long)op.x * P.dstride) * ESZ;
 #pragma unroll
@@ -599,8 +654,7 @@ __device__ __forceinline__ void pk_store_out(const uint32_t (&o)[4*LV], const in
 // removed, converted (exact), stored to the fp32 workspace or diagonally.
 template<int DSTK, int LV>
 __device__ __forceinline__ void pk_store_wide(const uint32_t (&av)[4*LV], const uint32_t (&bt)[4*LV], const int4& op,
-                                              int nvec, const PackedParams& P, const PackedTile& tl,
-                                              float* scratch, int lane, int warp) {
+                                              int nvec, const PackedParams& P, const PackedTile& tl, int lane) {
 	constexpr int LS = LV * 8;
 	float f[8*LV];
 #pragma unroll
@@ -619,18 +673,7 @@ __device__ __forceinline__ void pk_store_wide(const uint32_t (&av)[4*LV], const 
 				*(float4*)(g + c) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
 			}
 	} else {
-		float* sc = scratch + (size_t)warp * 32 * LS;
-		__syncwarp();
-#pragma unroll
-		for( int j=0; j<2*LV; ++j ) *(float4*)(sc + LS * lane + 4 * j) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
-		__syncwarp();
-		const long d = op.x;
-		float* g = (float*)P.dst + tl.doff + d * P.dstride - d + tl.t0;
-#pragma unroll 4
-		for( int i=lane; i<P.T; i+=32 ) {
-			const long t = tl.t0 + i;
-			if( t >= d && t < P.ntime ) __stcs(g + i, sc[i]);
-		}
+		pk_store_diag<8*LV>(f, (long)op.x, P, tl, lane);
 	}
 }
 
@@ -724,7 +767,8 @@ __device__ __forceinline__ void pk_group4_op(const int4& A, const int4& B, const
 // memory or to the pass output.
 template<int ESZ, int SRCK, int DSTK, int LV>
 __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, const PackedParams& P,
-                                          const PackedTile& tl, int lane, int warp) {
+                                          const PackedTile& tl, int lane, int warp,
+                                          const unsigned char* abase, unsigned char* obase) {
 	unsigned char* dbase = S.dbase;
 	const int nvec = op.w >> PK_NVEC_SHIFT;
 	const int wo = (op.w >> PK_WO_SHIFT) & 3;
@@ -749,7 +793,7 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 			const int kb = op.z & 0xFFF;
 			pk_bytes_widen(dbase, (uint32_t)S.ssrc[kb].z + S.smis[kb] + ((uint32_t)op.z >> 12) + 24u * lane, tl.flip, bt);
 		}
-		if( wide ) { pk_store_wide<DSTK, LV>(av, bt, op, nvec, P, tl, S.scratch, lane, warp); return; }
+		if( wide ) { pk_store_wide<DSTK, LV>(av, bt, op, nvec, P, tl, lane); return; }
 #pragma unroll
 		for( int k=0; k<12; ++k ) av[k] += bt[k];
 		done = true;
@@ -762,7 +806,7 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 #pragma unroll
 				for( int k=0; k<4*LV; ++k ) av[k] = 0u;
 			} else {
-				const uint4* a = (const uint4*)(dbase + op.y) + LV * lane;
+				const uint4* a = (const uint4*)(abase + op.y) + LV * lane;
 #pragma unroll
 				for( int j=0; j<LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
 			}
@@ -770,13 +814,13 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 #pragma unroll
 				for( int k=0; k<4*LV+4; ++k ) bw[k] = 0u;
 			} else {
-				const uint4* b = (const uint4*)(dbase + op.z) + LV * lane;
+				const uint4* b = (const uint4*)(abase + op.z) + LV * lane;
 #pragma unroll
 				for( int j=0; j<LV+1; ++j ) { uint4 v = b[j]; bw[4*j] = v.x; bw[4*j+1] = v.y; bw[4*j+2] = v.z; bw[4*j+3] = v.w; }
 			}
 		} else {
-			const uint4* a = (const uint4*)(dbase + op.y) + LV * lane;
-			const uint4* b = (const uint4*)(dbase + op.z) + LV * lane;
+			const uint4* a = (const uint4*)(abase + op.y) + LV * lane;
+			const uint4* b = (const uint4*)(abase + op.z) + LV * lane;
 #pragma unroll
 			for( int j=0; j<LV; ++j ) { uint4 v = a[j]; av[4*j] = v.x; av[4*j+1] = v.y; av[4*j+2] = v.z; av[4*j+3] = v.w; }
 #pragma unroll
@@ -791,7 +835,7 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 			case 2:  _Pragma("unroll") for( int k=0; k<4*LV; ++k ) bt[k] = BFB_PK_SHIFTED(2, k); break;
 			default: _Pragma("unroll") for( int k=0; k<4*LV; ++k ) bt[k] = BFB_PK_SHIFTED(3, k); break;
 			}
-			pk_store_wide<DSTK, LV>(av, bt, op, nvec, P, tl, S.scratch, lane, warp);
+			pk_store_wide<DSTK, LV>(av, bt, op, nvec, P, tl, lane);
 			return;
 		}
 		switch( wo ) {
@@ -803,11 +847,11 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 #undef BFB_PK_SHIFTED
 	}
 	if( op.w & PK_STORE_G ) {
-		pk_store_out<ESZ, DSTK, LV>(av, op, nvec, P, tl, S.scratch, lane, warp);
+		pk_store_out<ESZ, DSTK, LV>(av, op, nvec, P, tl, lane);
 	} else {
 		// (rows have room for all 32 * LV vectors: lanes past the window write junk
 		// nobody reads)
-		uint4* d = (uint4*)(dbase + op.x) + LV * lane;
+		uint4* d = (uint4*)(obase + op.x) + LV * lane;
 #pragma unroll
 		for( int j=0; j<LV; ++j ) d[j] = make_uint4(av[4*j], av[4*j+1], av[4*j+2], av[4*j+3]);
 	}
@@ -815,10 +859,14 @@ __device__ __forceinline__ void pk_row_op(const int4& op, const PackedSmem& S, c
 
 template<int ESZ, int SRCK, int DSTK, int LV>
 __device__ __forceinline__ void pk_levels(const PackedSmem& S, const PackedParams& P, const PackedTile& tl,
-                                          int lev0, int lev1, int lane, int warp, int nwarp) {
+                                          int lev0, int lev1, int lane, int warp, int nwarp, int flip = 0) {
 	const int slots = P.slots;
 	const int4* list = S.sops + ((lev0 - 1) * nwarp + warp) * slots;
 	for( int lev=lev0; lev<=lev1; ++lev, list += nwarp * slots ) {
+		// mirrored tile (flip = region size): level lev reads the region that holds
+		// stored level lev-1 and writes the other one
+		const unsigned char* abase = S.dbase + ((lev & 1) ? flip : -flip);
+		unsigned char*       obase = S.dbase + ((lev & 1) ? -flip : flip);
 		int4 nxt = list[0];
 		for( int m=0; m<slots; ++m ) {
 			const int4 op = nxt;
@@ -830,7 +878,7 @@ __device__ __forceinline__ void pk_levels(const PackedSmem& S, const PackedParam
 				nxt = list[m + 1];
 				continue;
 			}
-			pk_row_op<ESZ, SRCK, DSTK, LV>(op, S, P, tl, lane, warp);
+			pk_row_op<ESZ, SRCK, DSTK, LV>(op, S, P, tl, lane, warp, abase, obase);
 		}
 		__syncthreads();
 	}
@@ -838,12 +886,18 @@ __device__ __forceinline__ void pk_levels(const PackedSmem& S, const PackedParam
 
 // The tiles first, first + stride, ... (count of them) of one program, tables
 // already in shared memory.  The source rows of tile i+1 are requested as soon
-// as level 1 of tile i has consumed tile i's.
+// as the shared memory they land in is free: after level 1 of tile i when the
+// source has a region of its own (prefetch), before the last level when it
+// shares region 0 with the merged rows (early; with an odd number of levels
+// the two regions swap roles from tile to tile), else after the last level.
 template<int ESZ, int SRCK, int DSTK, int LV>
 __device__ __forceinline__ void pk_tiles(const PackedSmem& S, const PackedParams& P, long first, long stride, long count,
                                          long soff, long roff, long doff, uint32_t& parity, int lane, int warp, int nwarp) {
 	if( count <= 0 ) return;
+	const int R = (SRCK == PK_SRC_SAME && P.early) ? S.shdr[0].w : 0;   // region size when tiles alternate
+	const bool early = SRCK == PK_SRC_SAME && P.early && P.nlev >= 2;
 	if( warp == 0 ) pk_stage_issue<ESZ, SRCK>(S, P, P.t_begin + first * P.T, soff, roff, lane);
+	int flip = 0;
 	for( long n=0; n<count; ++n ) {
 		const long t0 = P.t_begin + (first + n * stride) * P.T;
 		__syncthreads();                               // smis / staged rows of this tile were requested by warp 0
@@ -853,26 +907,34 @@ __device__ __forceinline__ void pk_tiles(const PackedSmem& S, const PackedParams
 		tl.t0 = t0; tl.dcol = (t0 - P.dst_tb) % P.dst_rl; tl.doff = doff;
 		tl.bias = P.is_signed ? 128 * S.shdr[0].x : 0;
 		tl.flip = P.is_signed ? 0x80808080u : 0u;
-		pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, 1, 1, lane, warp, nwarp);
 		const bool more = n + 1 < count && warp == 0;
-		if( more && P.prefetch )
-			pk_stage_issue<ESZ, SRCK>(S, P, P.t_begin + (first + (n + 1) * stride) * P.T, soff, roff, lane);
-		pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, 2, P.nlev, lane, warp, nwarp);
-		if( more && !P.prefetch )
-			pk_stage_issue<ESZ, SRCK>(S, P, P.t_begin + (first + (n + 1) * stride) * P.T, soff, roff, lane);
+		const long tn = P.t_begin + (first + (n + 1) * stride) * P.T;
+		if( early ) {
+			pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, 1, P.nlev - 1, lane, warp, nwarp, flip);
+			if( more ) pk_stage_issue<ESZ, SRCK>(S, P, tn, soff, roff, lane, R - flip);
+			pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, P.nlev, P.nlev, lane, warp, nwarp, flip);
+			flip = R - flip;
+		} else {
+			pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, 1, 1, lane, warp, nwarp);
+			if( more && P.prefetch ) pk_stage_issue<ESZ, SRCK>(S, P, tn, soff, roff, lane);
+			pk_levels<ESZ, SRCK, DSTK, LV>(S, P, tl, 2, P.nlev, lane, warp, nwarp);
+			if( more && !P.prefetch ) pk_stage_issue<ESZ, SRCK>(S, P, tn, soff, roff, lane);
+		}
 	}
 }
 } // namespace packed_dev
 
 // One pass per launch: grid (tile stride, program, batch).
-template<int ESZ, int SRCK, int DSTK, int LV>
-__global__ void __launch_bounds__(256, LV == 3 ? 3 : 2)
+// (NW = warps per CTA the kernel is compiled for: 8 -> three CTAs per SM with
+// three vectors per lane, 12 / 16 -> two)
+template<int ESZ, int SRCK, int DSTK, int LV, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW == 8 && LV == 3) ? 3 : 2)
 fdmt_packed_kernel(const __grid_constant__ PackedParams P) {
 	using namespace packed_dev;
 	extern __shared__ __align__(16) unsigned char pk_smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
 	const PackedSmem S = pk_carve<ESZ, DSTK, LV>(pk_smem, P, nwarp);
-	pk_load_tables(S, P, blockIdx.y, nwarp);
+	pk_load_tables(S, P, P.plist ? __ldg(P.plist + blockIdx.y) : (int)blockIdx.y, nwarp);
 	if( threadIdx.x == 0 ) {
 		mbar_init(S.mbar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

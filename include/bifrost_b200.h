@@ -350,6 +350,31 @@ BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 BFstatus bfFdmtPackedMegaQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                               double exponent, long ntime, long* header, int* tmpl);
 
+/* B200 extension: the FULL-BAND FDMT over `nrank` (2, 4 or 8) cooperating
+ * plans, one per GPU (the reference runs one bfFdmt per GPU on
+ * independent sub-bands only, python/bifrost/blocks/fdmt.py:59-124).  Every
+ * rank calls bfFdmtInit with the full-band arguments, then bfFdmtShardInit.
+ * Rank g owns the channels of sub-band g of the merge-tree step that has
+ * `nrank` sub-bands (src/fdmt.cu:366-387).
+ *   bfFdmtShardExecute(phase 0): the steps up to the split step on the rank's
+ *     own channels (`in` = [nchan/nrank][ntime] i8/u8), into the rank's block
+ *     of rows of the split-step workspace;
+ *   the caller exchanges the blocks (NCCL all-gather over NVLink; layout from
+ *     bfFdmtShardQuery: same byte offsets on every rank);
+ *   bfFdmtShardExecute(phase 1): the rank's delay blocks of the remaining
+ *     steps into `out` = [max_delay][ntime] f32 (other rows untouched).
+ * All ranks' phase-1 rows together equal bfFdmtExecute's output bit for bit.
+ * Workspace protocol as bfFdmtExecute (exec_storage NULL: size query). */
+BFstatus bfFdmtShardInit(BFfdmt plan, int rank, int nrank);
+BFstatus bfFdmtShardExecute(BFfdmt plan, int phase, BFarray const* in, BFarray const* out,
+                            void* exec_storage, BFsize* exec_storage_size);
+/* info: [0] byte offset of the split-step rows in the workspace, [1] row pitch
+ * (bytes), [2] rows, [3] bytes per element, [4] nrank, [5] split step,
+ * [6 .. 6+nrank] first row of each rank's block and the end; then n and n
+ * triples (first delay, delays, owning rank) of the last pass's delay blocks.
+ * *ninfo: capacity (longs) in, used out. */
+BFstatus bfFdmtShardQuery(BFfdmt plan, long ntime, long* info, int* ninfo);
+
 /* Number of kernels this library has launched since load (all threads). */
 BFstatus bfGetLaunchCount(unsigned long long* count);
 

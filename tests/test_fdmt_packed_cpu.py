@@ -32,7 +32,7 @@ def query(nchan, md, f0, df):
         h = np.zeros(24, np.int32)
         assert _bf.bfFdmtPackedQuery(nchan, md, f0, df, -2.0, k, _ip(h), None, None, None) == 0
         keys = ('s0 s1 nlev esize src_kind dst_kind T nprog nwarp slots src_slots data_bytes '
-                'lookback nrow_out smem_bytes nops lv fused prefetch').split()
+                'lookback nrow_out smem_bytes nops lv fused prefetch early').split()
         p = dict(zip(keys, (int(v) for v in h)))
         p['fused'] = bool(p['fused'])
         ops = np.zeros((p['nprog'], p['nlev'], p['nwarp'], p['slots'], 4), np.int32)
@@ -73,7 +73,11 @@ class Machine(object):
         esz = p['esize']
         VS = 16 // esz
         final = p['dst_kind'] == 2
-        nchan_band, nsrc, staged, _ = (int(v) for v in p['hdr'][prog])
+        nchan_band, nsrc, staged, region = (int(v) for v in p['hdr'][prog])
+        # a pass whose source shares region 0 and has an odd number of levels lays
+        # every other tile out mirrored (pk_tiles): region 0 <-> region 1
+        assert region == 0 or (p['early'] and p['nlev'] % 2 == 1 and p['src_kind'] == 1)
+        flip = region if (tile & 1) else 0
         bias = 128 * nchan_band if signed else 0
         t0 = g['tb'] + tile * p['T']
         nelem = p['data_bytes']          # one cell per BYTE offset keeps byte and word rows in one array
@@ -95,6 +99,8 @@ class Machine(object):
                 assert c0 >= 0 and c0 % VS == 0 and c0 + w <= self.ws_prev_width
                 cols = (c0 + np.arange(w)) % self.ring_prev
                 vals = self.ws_prev[row, cols]
+                assert region == 0 or z + w * esz <= region
+                z += flip
                 data[z:z + w * esz:esz] = vals
                 nbytes += w * esz
         if p['src_kind'] != 0:
@@ -102,6 +108,7 @@ class Machine(object):
         if nsrc < p['src_slots']:
             assert srcs[nsrc][3] == 0
         for lev in range(1, p['nlev'] + 1):
+            aflip, oflip = (flip, -flip) if lev & 1 else (-flip, flip)
             for warp in range(p['nwarp']):
                 oplist = p['ops'][prog, lev - 1, warp]
                 skip = False
@@ -149,6 +156,9 @@ class Machine(object):
                         if esz == 4:
                             assert (ctl >> H_SHIFT) & 1 == 0
                         assert ay % 16 == 0 and bz % 16 == 0
+                        ay += aflip
+                        bz += aflip
+                        assert (ctl & NO_A) or 0 <= ay < 2 * region or not region
                         a = np.zeros(n, data.dtype) if ctl & NO_A else data[ay: ay + n * esz: esz]
                         b = np.zeros(n, data.dtype) if ctl & NO_B else data[bz + sub * esz: bz + (sub + n) * esz: esz]
                     if esz == 4:
@@ -157,6 +167,8 @@ class Machine(object):
                         r = a + b
                     if not (ctl & STORE_G):
                         assert dst % 16 == 0 and lev < p['nlev']
+                        dst += oflip
+                        assert dst >= 0
                         if esz == 2:
                             assert (r >= 0).all() and (r < 65536).all()
                         data[dst: dst + n * esz: esz] = r
@@ -248,6 +260,29 @@ def test_packed_schedule_of_the_baseline_plan():
     gold = np.zeros((md, ntime), np.float32)
     ofdmt.fdmt(x, md, f0, df, out=gold)
     got = np.zeros((md, ntime), np.float32)
+    run_schedule(x, passes, got)
+    assert np.array_equal(got.view(np.uint32), gold.view(np.uint32))
+
+
+@pytest.mark.parametrize("nchan,md,f0,df,ntime,nrank", [
+    (256, 130, 1000.0, 1.5, 1100, 2),
+    (256, 130, 1000.0, 1.5, 1100, 8),
+    (1024, 300, 1000.0, 400. / 1024, 800, 2),      # split at the 16-bit limit (fp32 exchange rows)
+    (64, 50, 1200.0, -3.0, 700, 2),                # reversed band
+])
+def test_sharded_schedule_tables_reproduce_the_oracle(nchan, md, f0, df, ntime, nrank, monkeypatch):
+    """bfFdmtShardInit cuts the passes at the step that has `nrank` sub-bands and
+    runs ONE pass above it; the tables of that schedule (whatever rank runs
+    which program) must still be the transform."""
+    sx = int(np.log2(nchan // nrank))
+    monkeypatch.setenv('BFB_FDMT_PACKED_FORCE_END', str(sx))
+    passes = query(nchan, md, f0, df)
+    assert passes and passes[-2]['s1'] == sx and passes[-1]['s0'] == sx + 1
+    rng = np.random.default_rng(nchan + nrank)
+    x = rng.integers(-128, 128, size=(nchan, ntime)).astype(np.int8)
+    gold = np.full((md, ntime), -12345.0, np.float32)
+    ofdmt.fdmt(x, md, f0, df, out=gold)
+    got = np.full((md, ntime), -12345.0, np.float32)
     run_schedule(x, passes, got)
     assert np.array_equal(got.view(np.uint32), gold.view(np.uint32))
 
