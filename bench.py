@@ -380,6 +380,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-chain', action='store_true')
+    ap.add_argument('--no-fullband', action='store_true', help='N > 1: skip the cross-GPU full-band transform')
     ap.add_argument('--no-traffic', action='store_true')
     ap.add_argument('--no-gpu-reference', action='store_true')
     ap.add_argument('--dry-run', action='store_true')
@@ -798,6 +799,45 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
     ms_e2e = timed(step_e2e, 2, e2e_steps)[0] / e2e_steps
     del pinned_in, pinned_bank
 
+    # cross-GPU FULL-BAND transform of the same gulp: every rank
+    # keeps its sub-band's channels, the merge tree is cut where it has `world`
+    # sub-bands, the cut-step rows are exchanged with NCCL, rank 0 gathers the
+    # bank.  The sub-bands of the scatter above are exactly the shards.
+    fullband = None
+    if not args.no_fullband:
+        from bifrost_b200.fdmt_sharded import ShardedFdmt
+        try:
+            sf = ShardedFdmt().init(full['nchan'], full['max_delay'], full['f0'], full['df'])
+            shard_ok = 1
+        except Exception as e:                         # e.g. a world size the tree does not split into
+            sf, shard_ok, shard_err = None, 0, str(e)
+        agree = torch.tensor([shard_ok], device='cuda')
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 1:
+            x_loc = t_full[:nc] if rank == 0 else t_in
+            t_fb = torch.zeros((full['max_delay'], ntime), dtype=torch.float32, device='cuda')
+            ms_fb = timed(lambda: sf.execute(x_loc, t_fb, gather_to=0), 2, 5)[0] / 5
+            ms_fb_nogather = timed(lambda: sf.execute(x_loc, t_fb), 2, 5)[0] / 5
+            lay = sf.layout(ntime)
+            sf.execute(x_loc, t_fb, gather_to=0)
+            torch.cuda.synchronize()
+            fb_par = None
+            if rank == 0:
+                fb_par = oracle_window_check(x_full, lambda a, n: t_fb[:, a:a + n].cpu().numpy(), full,
+                                             [(0, 2048), (70000 + 1, 2048), (ntime - 2048 - full['max_delay'], 2048 + full['max_delay'])])
+            blk = lay['row_start']
+            fullband = dict(what='ONE full-band dispersion bank [max_delay, ntime] of the gulp, channels partitioned over the '
+                                 'ranks: local steps -> NCCL broadcast of every rank\'s block of cut-step rows -> each rank\'s '
+                                 'delay blocks of the remaining steps -> NCCL gather on rank 0 (bifrost_b200/fdmt_sharded.py)',
+                            split_step=lay['split_step'], ms_per_step=ms_fb, ms_per_step_without_gather=ms_fb_nogather,
+                            value=NCHAN * NTIME_OUT / (ms_fb * 1e-3) / 1e6, unit='Msamples/s',
+                            exchange_bytes_per_rank=int((blk[-1] - (blk[rank + 1] - blk[rank])) * lay['pitch']),
+                            gather_bytes=int(sum(nd for _, nd, o in lay['blocks'] if o != 0) * ntime * 4),
+                            parity=fb_par)
+            del t_fb, sf
+        else:
+            fullband = dict(available=False, note=shard_err if not shard_ok else 'another rank could not build the sharded plan')
+
     # replicas (weak scaling, no collective): every rank its own full gulp
     del ws
     wr = workload(rank)
@@ -844,6 +884,7 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
                          how='every rank: pinned host sub-band -> H2D -> Fdmt.execute -> NCCL gather; rank 0: D2H of '
                              'the whole bank to pinned host memory; one stream per rank, max over ranks',
                          h2d_bytes_per_step=int(NCHAN * ntime), d2h_bytes_per_step=int(offs[-1]) * ntime * 4),
+                fullband=fullband,
                 replicas=dict(scaling='weak', what='every rank its own full 4096-chan gulp (sub-band above the '
                                                    'previous rank\'s), no collective; max over ranks',
                               ms_per_step=ms_rep, value=samples * world / (ms_rep * 1e-3) / 1e6, unit='Msamples/s'),

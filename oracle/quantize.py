@@ -24,3 +24,30 @@ def quantize(x, kind, scale=1.0):
     v = np.clip(v, np.float32(lo), np.float32(hi))
     r = np.rint(v.astype(np.float64))
     return np.minimum(r, hi).astype(_NP[kind])
+
+
+def quantize_packed(x, nbit, scale=1.0):
+    """Sub-byte outputs (src/guantize.cu:146-348): values clip to [-7, 7] (4-bit)
+    or [-1, 1] (2-bit) and round half to even; 1-bit is (x * scale >= 0).  The
+    first value of every byte goes to the most significant bits.  Returns uint8
+    [..., n * nbit / 8].  NOTE: the reference's 1-bit kernel masks its first
+    three values away (0x08 / 0x04 / 0x02 on bits 7..5); `reference_1bit_mask`
+    is the part of the byte on which it agrees with this definition."""
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        x = np.stack([x.real, x.imag], -1).reshape(x.shape[:-1] + (2 * x.shape[-1],))
+    v = (x.astype(np.float32) * np.float32(scale)).astype(np.float32)
+    if nbit == 1:
+        q = (v >= 0).astype(np.uint8)
+    else:
+        lim = 7 if nbit == 4 else 1
+        q = np.rint(np.clip(v, -lim, lim)).astype(np.int8).view(np.uint8) & np.uint8((1 << nbit) - 1)
+    per = 8 // nbit
+    q = q.reshape(q.shape[:-1] + (q.shape[-1] // per, per))
+    out = np.zeros(q.shape[:-1], np.uint8)
+    for k in range(per):
+        out |= (q[..., k] << np.uint8(8 - nbit * (k + 1))).astype(np.uint8)
+    return out
+
+
+reference_1bit_mask = 0x1F

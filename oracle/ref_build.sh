@@ -63,7 +63,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100,code=sm_100 -O3 -std=c++17 -Xcompiler -fPIC -w \
        -I$OUT/include -I$REF/src -DBF_CUDA_ENABLED=1"
 SRCS="common.cpp memory.cpp array.cpp cuda.cpp fdmt.cu reduce.cu transpose.cu \
-      linalg.cu linalg_kernels.cu unpack.cpp gunpack.cu"
+      linalg.cu linalg_kernels.cu unpack.cpp gunpack.cu quantize.cpp guantize.cu"
 OBJS=""
 pids=""
 for s in $SRCS; do
