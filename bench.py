@@ -431,10 +431,12 @@ def main():
     def timed(fn, nwarm, nstep, sampler=None, post=None):
         for _ in range(nwarm):
             fn()
-        barrier()
         if sampler:
+            # (before the barrier: only one rank samples, and a rank that entered
+            # the timed region late would make its peers wait inside it)
             sampler.start()
             time.sleep(0.1)
+        barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = bf.launch_count()
         ev0.record(stream)

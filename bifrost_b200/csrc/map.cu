@@ -20,6 +20,12 @@
 
 namespace bfb {
 
+// map_jit.cu
+BFstatus map_jit(int ndim, long const* shape, char const* const* axis_names, int narg,
+                 BFarray const* const* args, char const* const* arg_names, char const* func_name,
+                 char const* func, char const* extra_code, int const* block_axes, bool compile_only, int* mode_out);
+void map_jit_clear_cache();
+
 enum DetectMode { DET_SCALAR = 0, DET_JONES = 1, DET_STOKES = 2, DET_STOKES_I = 3, DET_COHERENCE = 4 };
 
 struct EltParams {
@@ -376,60 +382,84 @@ BFstatus bfAccumulate(BFarray const* a, BFarray const* b, double beta) {
 	BFB_TRY(return accumulate_impl(a, b, beta));
 }
 
-BFstatus bfMapClearCache(void) { return BF_STATUS_SUCCESS; }
+BFstatus bfMapClearCache(void) { BFB_TRY(bfb::map_jit_clear_cache(); return BF_STATUS_SUCCESS); }
+
+// The expressions of the hot-path blocks run as the compiled kernels above
+// (same results as the JIT form, no compile step); everything else goes to
+// the NVRTC front end in map_jit.cu.  `matched` tells the caller which it was.
+static BFstatus map_fixed_kernels(int narg, BFarray const* const* args, char const* const* arg_names,
+                                  char const* func, bool* matched) {
+	*matched = true;
+	std::string f = squeeze(func);
+	int ia = find_arg(narg, arg_names, "a");
+	int ib = find_arg(narg, arg_names, "b");
+	if( ia < 0 || ib < 0 ) { *matched = false; return BF_STATUS_SUCCESS; }
+	BFarray const* a = args[ia];
+	BFarray const* b = args[ib];
+	// blocks/accumulate.py:67
+	if( f == "b=beta*b+(b_type)a" ) {
+		int ibeta = find_arg(narg, arg_names, "beta");
+		double beta = 0;
+		if( ibeta < 0 || !read_scalar(args[ibeta], &beta) ) BFB_FAIL(BF_STATUS_INVALID_ARGUMENT);
+		return accumulate_impl(a, b, beta);
+	}
+	// blocks/detect.py:87
+	if( f == "b=Complex<b_type>(a).mag2()" ) return detect_impl(a, b, DET_SCALAR, 0);
+	// blocks/detect.py:96-136: the pol axis is the literal index in a(...)
+	size_t open = f.find("=a(");
+	if( open != std::string::npos ) {
+		size_t close = f.find(')', open);
+		if( close == std::string::npos ) { *matched = false; return BF_STATUS_SUCCESS; }
+		std::string inds = f.substr(open + 3, close - open - 3);
+		int axis = -1, pos = 0;
+		size_t start = 0;
+		while( start <= inds.size() ) {
+			size_t comma = inds.find(',', start);
+			std::string tok = inds.substr(start, comma == std::string::npos ? std::string::npos : comma - start);
+			if( !tok.empty() && std::isdigit((unsigned char)tok[0]) ) axis = pos;
+			++pos;
+			if( comma == std::string::npos ) break;
+			start = comma + 1;
+		}
+		int mode = -1;
+		if(      f.find(".assign(x.mag2(),y.mag2())") != std::string::npos ) mode = DET_JONES;
+		else if( f.find("=-2*xy.imag") != std::string::npos )                mode = DET_STOKES;
+		else if( f.find("x.conj()*y") != std::string::npos )                 mode = DET_COHERENCE;
+		else if( f.find("=xx+yy;") != std::string::npos )                    mode = DET_STOKES_I;
+		if( axis >= 0 && mode >= 0 ) return detect_impl(a, b, mode, axis);
+	}
+	*matched = false;
+	return BF_STATUS_SUCCESS;
+}
 
 BFstatus bfMap(int ndim, long const* shape, char const* const* axis_names,
                int narg, BFarray const* const* args, char const* const* arg_names,
                char const* func_name, char const* func, char const* extra_code,
                int const* block_shape, int const* block_axes) {
-	(void)ndim; (void)shape; (void)axis_names; (void)func_name; (void)extra_code;
-	(void)block_shape; (void)block_axes;
-	BFB_ASSERT(func,      BF_STATUS_INVALID_POINTER);
-	BFB_ASSERT(args,      BF_STATUS_INVALID_POINTER);
-	BFB_ASSERT(arg_names, BF_STATUS_INVALID_POINTER);
+	(void)block_shape;
+	BFB_ASSERT(func, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(!narg || (args && arg_names), BF_STATUS_INVALID_POINTER);
 	BFB_TRY(
-		std::string f = squeeze(func);
-		int ia = find_arg(narg, arg_names, "a");
-		int ib = find_arg(narg, arg_names, "b");
-		if( ia < 0 || ib < 0 ) BFB_FAIL(BF_STATUS_UNSUPPORTED);
-		BFarray const* a = args[ia];
-		BFarray const* b = args[ib];
-		// blocks/accumulate.py:67
-		if( f == "b=beta*b+(b_type)a" ) {
-			int ibeta = find_arg(narg, arg_names, "beta");
-			double beta = 0;
-			if( ibeta < 0 || !read_scalar(args[ibeta], &beta) ) BFB_FAIL(BF_STATUS_INVALID_ARGUMENT);
-			return accumulate_impl(a, b, beta);
+		bool matched = false;
+		if( !extra_code && !getenv("BFB_MAP_JIT_ONLY") ) {
+			BFstatus st = map_fixed_kernels(narg, args, arg_names, func, &matched);
+			if( matched ) return st;
 		}
-		// blocks/detect.py:87
-		if( f == "b=Complex<b_type>(a).mag2()" ) return detect_impl(a, b, DET_SCALAR, 0);
-		// blocks/detect.py:96-136: the pol axis is the literal index in a(...)
-		size_t open = f.find("=a(");
-		if( open != std::string::npos ) {
-			size_t close = f.find(')', open);
-			if( close == std::string::npos ) BFB_FAIL(BF_STATUS_UNSUPPORTED);
-			std::string inds = f.substr(open + 3, close - open - 3);
-			int axis = -1, pos = 0;
-			size_t start = 0;
-			while( start <= inds.size() ) {
-				size_t comma = inds.find(',', start);
-				std::string tok = inds.substr(start, comma == std::string::npos ? std::string::npos : comma - start);
-				if( !tok.empty() && std::isdigit((unsigned char)tok[0]) ) axis = pos;
-				++pos;
-				if( comma == std::string::npos ) break;
-				start = comma + 1;
-			}
-			if( axis < 0 ) BFB_FAIL(BF_STATUS_UNSUPPORTED);
-			int mode;
-			if(      f.find(".assign(x.mag2(),y.mag2())") != std::string::npos ) mode = DET_JONES;
-			else if( f.find("=-2*xy.imag") != std::string::npos )                mode = DET_STOKES;
-			else if( f.find("x.conj()*y") != std::string::npos )                 mode = DET_COHERENCE;
-			else if( f.find("=xx+yy;") != std::string::npos )                    mode = DET_STOKES_I;
-			else BFB_FAIL(BF_STATUS_UNSUPPORTED);
-			return detect_impl(a, b, mode, axis);
-		}
-		BFB_FAIL(BF_STATUS_UNSUPPORTED);
+		return bfb::map_jit(ndim, shape, axis_names, narg, args, arg_names, func_name, func, extra_code,
+		                    block_axes, false, nullptr);
 	);
+}
+
+// B200 extension (test hook): compiles the kernel bfMap would run for this
+// call and stops; works without a device.  *mode = 0: array names are plain
+// element references, 1: callable views.
+BFstatus bfMapCompile(int ndim, long const* shape, char const* const* axis_names,
+                      int narg, BFarray const* const* args, char const* const* arg_names,
+                      char const* func_name, char const* func, char const* extra_code,
+                      int const* block_axes, int* mode) {
+	BFB_ASSERT(func, BF_STATUS_INVALID_POINTER);
+	BFB_TRY(return bfb::map_jit(ndim, shape, axis_names, narg, args, arg_names, func_name, func, extra_code,
+	                            block_axes, true, mode));
 }
 
 } // extern "C"

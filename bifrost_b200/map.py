@@ -1,11 +1,13 @@
-"""bf.map and the fixed-kernel entry points behind it.
+"""bf.map (python/bifrost/map.py -> bfMap) and the fixed-kernel entry points
+behind the hot-path expressions.
 
-The reference's ``bf.map`` JIT-compiles arbitrary expressions with NVRTC
-(python/bifrost/map.py -> bfMap, src/map.cpp).  On the hot path it is used for
-exactly two things: the detect expressions (blocks/detect.py:87-136) and the
-accumulate expression (blocks/accumulate.py:67).  This build ships those as
-fixed sm_100a kernels; ``bf.map`` recognises those expressions and returns
-BF_STATUS_UNSUPPORTED (RuntimeError) for anything else.
+``bf.map`` takes an arbitrary C++ expression over named arrays, like the
+reference's: the library compiles it at run time with NVRTC for sm_100a
+(csrc/map_jit.cu).  The two expression families the hot-path blocks use -- the
+detect products (blocks/detect.py:87-136) and the accumulate update
+(blocks/accumulate.py:67) -- are recognised and run as compiled kernels
+(``bfDetect`` / ``bfAccumulate``), which is also what ``detect`` /
+``accumulate`` below call directly.
 """
 import ctypes
 
@@ -39,36 +41,75 @@ def _is_scalar(x):
     return isinstance(x, (int, float, complex, np.number))
 
 
-def map(func_string, data, axis_names=None, shape=None, func_name=None,
-        extra_code=None, block_shape=None, block_axes=None):
-    """Apply `func_string` to the arrays in `data` (dict name -> array/scalar).
-    Signature of python/bifrost/map.py:map; only the hot-path expressions are
-    compiled in (see module docstring)."""
-    narg = len(data)
-    ndim = len(shape) if shape is not None else 0
+def _convert_to_array(arg):
+    """Literals become immutable 1-element system arrays, which bfMap passes to
+    the kernel by value (python/bifrost/map.py:44-56: int32 / float32 /
+    complex64)."""
+    if _is_scalar(arg):
+        arr = np.array(arg)
+        if isinstance(arg, (int, np.integer)) and -(1 << 31) <= int(arg) < (1 << 31):
+            arr = arr.astype(np.int32)
+        elif isinstance(arg, (float, np.floating)):
+            arr = arr.astype(np.float32)
+        elif isinstance(arg, (complex, np.complexfloating)):
+            arr = arr.astype(np.complex64)
+        arr = arr.reshape(1).view(ndarray)
+        arr.flags['WRITEABLE'] = False
+        arg = arr
+    return asarray(arg)
+
+
+def _marshal(data, shape, axis_names, block_axes):
     arg_arrays, arg_names, keepalive = [], [], []
     for key, arg in data.items():
-        if _is_scalar(arg):
-            arr = np.array(arg)
-            if isinstance(arg, int):
-                arr = arr.astype(np.int64)
-            elif isinstance(arg, float):
-                arr = arr.astype(np.float64)
-            arr = arr.reshape(1).view(ndarray)
-            arr.flags['WRITEABLE'] = False
-            arg = arr
-        arg = asarray(arg)
+        arg = _convert_to_array(arg)
         keepalive.append(arg)
         arg_arrays.append(arg.as_BFarray())
         arg_names.append(key)
     if block_axes is not None and axis_names is not None:
-        block_axes = [axis_names.index(a) if isinstance(a, str) else a for a in block_axes]
+        block_axes = [list(axis_names).index(a) if isinstance(a, str) else a for a in block_axes]
+    if block_axes is not None and len(block_axes) != 2:
+        raise ValueError("block_axes must contain exactly 2 entries")
+    return arg_arrays, arg_names, keepalive, block_axes
+
+
+def _enc(x):
+    return x.encode() if isinstance(x, str) else x
+
+
+def map(func_string, data, axis_names=None, shape=None, func_name=None,
+        extra_code=None, block_shape=None, block_axes=None):
+    """Apply `func_string` to the arrays in `data` (dict name -> array/scalar).
+    Signature and semantics of python/bifrost/map.py:map, e.g.
+
+      bf.map("c = a + b", {'c': c, 'a': a, 'b': b})
+      bf.map("c(i,j) = a(i) * b(j)", {'c': c, 'a': a, 'b': b}, axis_names=('i','j'))
+      bf.map("c(i) = a(i,k)", {'c': c, 'a': a, 'k': 7}, ['i'], shape=c.shape)
+
+    block_shape / block_axes are accepted for compatibility (tuning hints of
+    the reference's launch; this implementation runs one flat grid-stride loop)."""
+    if block_shape is not None and len(block_shape) != 2:
+        raise ValueError("block_shape must contain exactly 2 entries")
+    ndim = len(shape) if shape is not None else 0
+    arg_arrays, arg_names, keepalive, block_axes = _marshal(data, shape, axis_names, block_axes)
     _check(_bf.bfMap(ndim, _array(shape, dtype=ctypes.c_long), _array(axis_names),
-                     narg, _array(arg_arrays), _array(arg_names),
-                     func_name.encode() if isinstance(func_name, str) else func_name,
-                     func_string.encode() if isinstance(func_string, str) else func_string,
-                     extra_code.encode() if isinstance(extra_code, str) else extra_code,
+                     len(arg_arrays), _array(arg_arrays), _array(arg_names),
+                     _enc(func_name), _enc(func_string), _enc(extra_code),
                      _array(block_shape), _array(block_axes)))
+
+
+def compile_only(func_string, data, axis_names=None, shape=None, func_name=None,
+                 extra_code=None, block_axes=None):
+    """Compiles the kernel ``map`` would launch and returns 0 (array names are
+    element references) or 1 (callable views).  Needs no GPU (bfMapCompile)."""
+    ndim = len(shape) if shape is not None else 0
+    arg_arrays, arg_names, keepalive, block_axes = _marshal(data, shape, axis_names, block_axes)
+    mode = ctypes.c_int(-1)
+    _check(_bf.bfMapCompile(ndim, _array(shape, dtype=ctypes.c_long), _array(axis_names),
+                            len(arg_arrays), _array(arg_arrays), _array(arg_names),
+                            _enc(func_name), _enc(func_string), _enc(extra_code),
+                            _array(block_axes), ctypes.byref(mode)))
+    return mode.value
 
 
 def clear_map_cache():

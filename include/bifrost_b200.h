@@ -350,6 +350,15 @@ BFstatus bfFdmtPackedQuery(BFsize nchan, BFsize max_delay, double f0, double df,
 BFstatus bfFdmtPackedMegaQuery(BFsize nchan, BFsize max_delay, double f0, double df,
                               double exponent, long ntime, long* header, int* tmpl);
 
+/* B200 extension (test hook): compiles the kernel bfMap would run for this
+ * call (NVRTC, sm_100a) and stops; needs no device.  *mode = 0: the array
+ * names are plain element references, 1: callable views (src/map.cpp:712-735
+ * tries them in this order). */
+BFstatus bfMapCompile(int ndim, long const* shape, char const* const* axis_names,
+                      int narg, BFarray const* const* args, char const* const* arg_names,
+                      char const* func_name, char const* func, char const* extra_code,
+                      int const* block_axes, int* mode);
+
 /* B200 extension: the FULL-BAND FDMT over `nrank` (2, 4 or 8) cooperating
  * plans, one per GPU (the reference runs one bfFdmt per GPU on
  * independent sub-bands only, python/bifrost/blocks/fdmt.py:59-124).  Every
