@@ -18,7 +18,7 @@ from bifrost_b200.reduce import reduce
 from bifrost_b200.transpose import transpose
 from bifrost_b200.unpack import unpack
 from bifrost_b200.quantize import quantize
-from bifrost_b200.map import map, detect, accumulate
+from bifrost_b200.map import map, detect, accumulate, clear_map_cache
 from bifrost_b200.spectrometer import spectrometer
 from bifrost_b200 import views
 from bifrost_b200 import blocks

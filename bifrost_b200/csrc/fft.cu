@@ -898,6 +898,154 @@ BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 	return BF_STATUS_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------
+// Real transforms longer than one pass (n > FFT_NMAX_SMEM; the reference's own
+// tests run r2c / c2r at 2^24 points, test/test_fft.py:57,194-201): the even-
+// length real transform is ONE complex transform of half the length on the
+// input read as (even, odd) pairs, plus an O(n) fix-up:
+//   r2c:  z[m] = x[2m] + i x[2m+1],  Z = FFT_{n/2}(z),
+//         X[k] = (Z[k] + conj Z[n/2-k])/2 - (i/2) e^{-2 pi i k/n} (Z[k] - conj Z[n/2-k])
+//   c2r:  Z[k] = (X[k] + conj X[n/2-k]) + i e^{+2 pi i k/n} (X[k] - conj X[n/2-k]),
+//         z = IFFT_{n/2}(Z) (unnormalised),  x[2m] = Re z[m], x[2m+1] = Im z[m].
+// The twiddles are evaluated in double (sincospi), so the fix-up adds no
+// error beyond one rounding.
+// ---------------------------------------------------------------------------
+struct RealFixParams {
+	int  ndim;
+	long shape[BF_MAX_DIMS];                 // batch shape, the transform axis set to 1
+	long sa[BF_MAX_DIMS], sb[BF_MAX_DIMS];   // byte strides of the two arrays over the batch dims
+	long axa, axb;                           // byte strides along the transform axis
+	long m;                                  // n / 2
+	char* a; char* b;
+	long nline;
+};
+template<typename T> struct Cplx2 { T x, y; };
+__device__ __forceinline__ void real_fix_line(const RealFixParams& P, long line, long* oa, long* ob) {
+	long ra = 0, rb = 0, rem = line;
+	for( int d=P.ndim-1; d>=0; --d ) {
+		long q = rem / P.shape[d], r = rem - q * P.shape[d];
+		ra += r * P.sa[d]; rb += r * P.sb[d]; rem = q;
+	}
+	*oa = ra; *ob = rb;
+}
+// in place on `a` (n/2 + 1 complex per line, the first n/2 hold Z)
+template<typename T>
+__global__ void __launch_bounds__(256) fft_r2c_fix_kernel(RealFixParams P) {
+	const long per = P.m / 2 + 1;
+	for( long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < P.nline * per; idx += (long)gridDim.x * blockDim.x ) {
+		const long line = idx / per, k = idx - line * per;
+		long oa, ob;
+		real_fix_line(P, line, &oa, &ob);
+		char* base = P.a + oa;
+		typedef Cplx2<T> C;
+		if( k == 0 ) {
+			C z0 = *(C*)base;
+			C x0 = { z0.x + z0.y, (T)0 }, xm = { z0.x - z0.y, (T)0 };
+			*(C*)base = x0;
+			*(C*)(base + P.m * P.axa) = xm;
+			continue;
+		}
+		const long k2 = P.m - k;
+		C zk = *(C*)(base + k * P.axa), zm = *(C*)(base + k2 * P.axa);
+		double sn, cs;
+		sincospi(-2.0 * (double)k / (double)(2 * P.m), &sn, &cs);       // w^k = e^{-2 pi i k / n}
+		const T wr = (T)cs, wi = (T)sn;
+		// E = (zk + conj zm)/2, D = (zk - conj zm)/2
+		const T er = (zk.x + zm.x) * (T)0.5, ei = (zk.y - zm.y) * (T)0.5;
+		const T dr = (zk.x - zm.x) * (T)0.5, di = (zk.y + zm.y) * (T)0.5;
+		// O = -i w^k D
+		const T pr = wr * dr - wi * di, pi_ = wr * di + wi * dr;           // w^k D
+		const T o_r = pi_, o_i = -pr;
+		C xk = { er + o_r, ei + o_i };
+		// X[m-k] = conj(E) - i w^{m-k} conj(-D)... directly: = conj(E) + conj(O) * (-1) * (-1) -> conj(E - O) ... see derivation:
+		// X[m-k] = conj(X[n-(m-k)]) and X is Hermitian: X[m-k] = conj(E) - conj(O)
+		C xm = { er - o_r, -(ei - o_i) };
+		*(C*)(base + k * P.axa) = xk;
+		if( k2 != k ) *(C*)(base + k2 * P.axa) = xm;
+	}
+}
+// a: Hermitian input (n/2 + 1 per line), b: Z (n/2 per line)
+template<typename T>
+__global__ void __launch_bounds__(256) fft_c2r_fix_kernel(RealFixParams P) {
+	for( long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < P.nline * P.m; idx += (long)gridDim.x * blockDim.x ) {
+		const long line = idx / P.m, k = idx - line * P.m;
+		long oa, ob;
+		real_fix_line(P, line, &oa, &ob);
+		typedef Cplx2<T> C;
+		const C xk = *(const C*)(P.a + oa + k * P.axa), xm = *(const C*)(P.a + oa + (P.m - k) * P.axa);
+		double sn, cs;
+		sincospi(2.0 * (double)k / (double)(2 * P.m), &sn, &cs);
+		const T wr = (T)cs, wi = (T)sn;
+		const T er = xk.x + xm.x, ei = xk.y - xm.y;          // X[k] + conj X[m-k]
+		const T dr = xk.x - xm.x, di = xk.y + xm.y;          // X[k] - conj X[m-k]
+		const T pr = wr * dr - wi * di, pi_ = wr * di + wi * dr;
+		C z = { er - pi_, ei + pr };                           // E + i w D
+		*(C*)(P.b + ob + k * P.axb) = z;
+	}
+}
+
+template<typename T>
+BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
+                  PassArray const& in, PassArray const& out, bool in_real, bool in_herm,
+                  bool out_real, long n_out, bool inverse, bool fftshift, void* tmp,
+                  cudaStream_t st);
+
+template<typename T>
+BFstatus run_axis_real_long(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
+                            PassArray const& in, PassArray const& out, bool in_real, void* tmp, cudaStream_t st) {
+	BFB_ASSERT(n % 2 == 0 && tmp, BF_STATUS_UNSUPPORTED_SHAPE);
+	const long m = n / 2, csize = 2 * sizeof(T);
+	long hshape[BF_MAX_DIMS];
+	RealFixParams P;
+	memset(&P, 0, sizeof(P));
+	P.ndim = ndim; P.m = m; P.nline = 1;
+	for( int d=0; d<ndim; ++d ) {
+		hshape[d] = d == axis ? m : batch_shape[d];
+		P.shape[d] = d == axis ? 1 : batch_shape[d];
+		P.nline *= P.shape[d];
+	}
+	unsigned grid = (unsigned)std::min<long>(div_up<long>(P.nline * (m / 2 + 1), 256), 148L * 16);
+	if( in_real ) {
+		// the real input, two values at a time, is the complex input of the half-length transform
+		int ck = in.kind == FK_F32 ? FK_CF32 : in.kind == FK_F64 ? FK_CF64 : in.kind == FK_I8 ? FK_CI8 : in.kind == FK_I16 ? FK_CI16 : -1;
+		BFB_ASSERT(ck >= 0, BF_STATUS_UNSUPPORTED_DTYPE);
+		const long esz = ck == FK_CF64 ? 8 : ck == FK_CF32 ? 4 : ck == FK_CI16 ? 2 : 1;
+		BFB_ASSERT(in.strides[axis] == esz && ((uintptr_t)in.data % (2 * esz)) == 0, BF_STATUS_UNSUPPORTED_STRIDE);
+		for( int d=0; d<ndim; ++d ) if( d != axis && batch_shape[d] > 1 ) BFB_ASSERT(in.strides[d] % (2 * esz) == 0, BF_STATUS_UNSUPPORTED_STRIDE);
+		PassArray ic = in;
+		ic.kind = ck; ic.strides[axis] = 2 * esz;
+		BFstatus s = run_axis<T>(plan, ndim, hshape, axis, m, ic, out, false, false, false, m, false, false, tmp, st);
+		if( s != BF_STATUS_SUCCESS ) return s;
+		P.a = (char*)out.data; P.axa = out.strides[axis];
+		for( int d=0; d<ndim; ++d ) P.sa[d] = d == axis ? 0 : out.strides[d];
+		fft_r2c_fix_kernel<T><<<grid, 256, 0, st>>>(P);
+		count_launch();
+		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+		return BF_STATUS_SUCCESS;
+	}
+	// c2r: Z into the first half of the workspace, the half-length inverse
+	// transform writes the real output two values at a time
+	BFB_ASSERT(in.kind == (sizeof(T) == 8 ? FK_CF64 : FK_CF32), BF_STATUS_UNSUPPORTED_DTYPE);
+	BFB_ASSERT(out.strides[axis] == (long)sizeof(T) && ((uintptr_t)out.data % csize) == 0, BF_STATUS_UNSUPPORTED_STRIDE);
+	for( int d=0; d<ndim; ++d ) if( d != axis && batch_shape[d] > 1 ) BFB_ASSERT(out.strides[d] % csize == 0, BF_STATUS_UNSUPPORTED_STRIDE);
+	PassArray z;
+	z.data = tmp; z.kind = sizeof(T) == 8 ? FK_CF64 : FK_CF32;
+	long acc = csize;
+	z.strides[axis] = csize; acc *= m;
+	for( int d=ndim-1; d>=0; --d ) { if( d == axis ) continue; z.strides[d] = acc; acc *= batch_shape[d]; }
+	P.a = (char*)in.data; P.axa = in.strides[axis];
+	P.b = (char*)z.data;  P.axb = csize;
+	for( int d=0; d<ndim; ++d ) { P.sa[d] = d == axis ? 0 : in.strides[d]; P.sb[d] = d == axis ? 0 : z.strides[d]; }
+	grid = (unsigned)std::min<long>(div_up<long>(P.nline * m, 256), 148L * 16);
+	fft_c2r_fix_kernel<T><<<grid, 256, 0, st>>>(P);
+	count_launch();
+	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+	PassArray oc = out;
+	oc.kind = z.kind; oc.strides[axis] = csize;
+	void* tmp2 = (char*)tmp + round_up<size_t>((size_t)acc, 512);
+	return run_axis<T>(plan, ndim, hshape, axis, m, z, oc, false, false, false, m, true, false, tmp2, st);
+}
+
 // A full 1-D transform of length n along `axis` (splits into two passes
 // through `tmp` when n exceeds the shared-memory limit).
 template<typename T>
@@ -913,8 +1061,10 @@ BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 		return run_pass<T>(plan, ndim, batch_shape, axis, n, in, out, in_real, in_herm,
 		                   out_real, n_out, inverse, shift, st);
 	}
+	if( in_real || in_herm || out_real )
+		return run_axis_real_long<T>(plan, ndim, batch_shape, axis, n, in, out, in_real, tmp, st);
 	// ---- four-step: n = n1 * n2 (c2c, power of two only)
-	BFB_ASSERT(is_pow2(n) && !in_real && !in_herm && !out_real, BF_STATUS_UNSUPPORTED_SHAPE);
+	BFB_ASSERT(is_pow2(n), BF_STATUS_UNSUPPORTED_SHAPE);
 	BFB_ASSERT(tmp, BF_STATUS_INSUFFICIENT_STORAGE);
 	// n2 = 4096 when that leaves n1 >= 16 (n >= 65536); 16384 and 32768 split as 16 x n/16
 	long n2 = std::min<long>(4096, n / 16), n1 = n / n2;
@@ -1028,11 +1178,15 @@ BFstatus bfFftInit(BFfft plan, BFarray const* in, BFarray const* out, int rank,
 			ws = std::max(ws, elems * csize);
 		}
 		if( n > FFT_NMAX_SMEM ) {
-			BFB_ASSERT(is_pow2(n) && !plan->real_in && !plan->real_out, BF_STATUS_UNSUPPORTED_SHAPE);
-			BFB_ASSERT(n / 4096 <= FFT_NMAX_SMEM, BF_STATUS_UNSUPPORTED_SHAPE);
+			const bool real = plan->real_in || plan->real_out;
+			// real transforms beyond one pass: one axis, even length (run_axis_real_long)
+			if( real ) BFB_ASSERT(rank == 1 && n % 2 == 0, BF_STATUS_UNSUPPORTED_SHAPE);
+			const long nc = real ? n / 2 : n;                         // length of the complex transform behind it
+			BFB_ASSERT(nc <= FFT_NMAX_SMEM || (is_pow2(nc) && nc / 4096 <= FFT_NMAX_SMEM), BF_STATUS_UNSUPPORTED_SHAPE);
 			size_t elems = 1;
-			for( int e=0; e<ndim; ++e ) elems *= out->shape[e];
-			ws = std::max(ws, elems * csize);
+			for( int e=0; e<ndim; ++e ) elems *= std::max(in->shape[e], out->shape[e]);
+			// c2r keeps Z and the four-step buffer side by side
+			ws = std::max(ws, (real ? 2 : 1) * (round_up<size_t>(elems * csize, 512) + 512));
 		}
 	}
 	plan->workspace_size = ws;

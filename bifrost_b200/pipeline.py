@@ -1,31 +1,36 @@
-"""A small in-process executor with the block API of the reference's
-``bifrost.pipeline`` (python/bifrost/pipeline.py): ``SourceBlock`` /
-``TransformBlock`` / ``SinkBlock`` with ``on_sequence`` / ``on_data``,
-``block_view``, ``block_scope`` and ``Pipeline.run()``.
+"""The block executor: the block API of the reference's ``bifrost.pipeline``
+(python/bifrost/pipeline.py) -- ``SourceBlock`` / ``TransformBlock`` /
+``SinkBlock`` with ``on_sequence`` / ``on_data``, ``block_view``,
+``block_scope`` and ``Pipeline.run()`` -- on ring buffers that live in the
+memory space of the data (bifrost_b200/ring.py).
 
-Scope note: the reference runs one OS thread per block connected
-by ring buffers (pipeline.py:249-261, ring2.py).  That scheduler is host code
-outside the GPU hot path and is not rebuilt here; this executor runs the same
-block graph synchronously, gulp by gulp, on the calling thread, handing each
-block ``ispan.data`` / ``ospan.data`` arrays exactly as the reference does:
-  * headers are dicts with a ``_tensor`` entry (dtype, shape with -1 on the
-    frame axis, labels, scales, units) -- ring2.py:229-255;
-  * spans expose ``.data`` (bf.ndarray in the ring's space), ``.nframe``,
-    ``.frame_offset``, ``.tensor``;
+As in the reference (pipeline.py:249-261, 558-650):
+  * every block runs its own OS thread and its own CUDA stream (the library's
+    per-thread stream), bound to the device named by ``gpu=`` and the core
+    named by ``core=``;
+  * blocks are connected by rings: the writer reserves a span, the block's
+    ``on_data`` fills it, one stream synchronisation per gulp, commit; readers
+    acquire spans of ``gulp + overlap`` frames and release them gulp by gulp;
+  * a 'cuda' ring is device memory end to end -- a span handed to ``on_data``
+    is a view of the ring, and wrapping is handled by device-side ghost copies;
+  * headers are dicts with a ``_tensor`` entry (ring2.py:229-255), spans expose
+    ``.data`` / ``.nframe`` / ``.frame_offset`` / ``.tensor``;
   * ``define_input_overlap_nframe`` re-presents the tail of each gulp to the
-    next one (blocks/fdmt.py:112-115) and ``on_data`` may return the number of
+    next one (blocks/fdmt.py:112-115); ``on_data`` may return the number of
     frames to commit (blocks/accumulate.py:63-74).
-One stream synchronisation per gulp per block, as in pipeline.py:628.
+An exception in any block stops the pipeline and is re-raised by ``run()``.
 """
+import os
 import threading
 from copy import deepcopy
 
 import numpy as np
 
 from bifrost_b200 import device
-from bifrost_b200.DataType import DataType
-from bifrost_b200.ndarray import ndarray, empty, copy_array, memset_array
+from bifrost_b200.ndarray import memset_array
 from bifrost_b200.memory import space_accessible
+from bifrost_b200.ring import (Ring, ViewRing, Span, Sequence, PipelineAborted,      # noqa: F401
+                               frame_axis as _frame_axis, slice_frames as _slice_frames)
 
 _tls = threading.local()
 
@@ -45,12 +50,12 @@ def _scope_stack():
 class block_scope(object):
     """Attribute scope inherited by blocks created inside it (gulp_nframe,
     buffer_nframe, buffer_factor, core, gpu, share_temp_storage, fuse) --
-    pipeline.py:84-134.  ``gpu`` selects the device of the blocks' thread;
-    ``fuse=True`` collapses chains that have a fused kernel into one launch
-    (Pipeline._fuse_chains); ``core``, ``buffer_factor`` and
-    ``share_temp_storage`` configure the reference's thread-per-block ring
-    scheduler, which this synchronous executor does not have: they are accepted
-    and have no effect here."""
+    pipeline.py:84-134.  ``gpu`` selects the device of the blocks' threads,
+    ``core`` the CPU core they are bound to, ``buffer_nframe`` /
+    ``buffer_factor`` size the blocks' output rings, ``fuse=True`` collapses
+    chains that have a fused kernel into one launch (Pipeline._fuse_chains).
+    ``share_temp_storage`` is accepted and has no effect (the ops own their
+    workspaces)."""
 
     def __init__(self, **kwargs):
         self.kwargs = kwargs
@@ -70,6 +75,8 @@ class Pipeline(object):
         self.name = name or 'Pipeline'
         self.blocks = []
         self.kwargs = kwargs
+        self._abort = threading.Event()
+        self._errors = []
 
     def __enter__(self):
         if not hasattr(_tls, 'pipeline_stack'):
@@ -80,11 +87,49 @@ class Pipeline(object):
     def __exit__(self, *exc):
         _tls.pipeline_stack.pop()
 
+    def _rings(self):
+        rings = []
+        for b in self.blocks:
+            for r in list(b.orings) + list(b.irings):
+                root = r.root()
+                if root not in rings:
+                    rings.append(root)
+        return rings
+
     def run(self):
+        """One thread per block; returns when every block has finished."""
         self._fuse_chains()
-        sources = [b for b in self.blocks if isinstance(b, SourceBlock)]
-        for src in sources:
-            src._run()
+        self._abort.clear()
+        self._errors = []
+        for ring in self._rings():
+            ring.set_abort_event(self._abort)
+        for b in self.blocks:                  # readers exist before any writer starts
+            b._readers = [r.open_reader(b) for r in b.irings]
+        threads = [threading.Thread(target=self._run_block, args=(b,), name=b.name, daemon=True) for b in self.blocks]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if self._errors:
+            raise self._errors[0]
+
+    def _run_block(self, block):
+        try:
+            if block.core is not None and hasattr(os, 'sched_setaffinity'):
+                try:
+                    os.sched_setaffinity(0, {int(block.core)})
+                except OSError:
+                    pass
+            if block.gpu is not None:
+                device.set_device(block.gpu)
+            block.main()
+        except PipelineAborted:
+            pass
+        except BaseException as e:             # noqa: BLE001 -- re-raised by run()
+            self._errors.append(e)
+            self._abort.set()
+            for ring in self._rings():
+                ring.wake()
 
     def _fuse_chains(self):
         """Honours ``block_scope(fuse=True)`` (pipeline.py:84-134 of the reference,
@@ -142,105 +187,16 @@ class Pipeline(object):
                 self.blocks.remove(b)
 
     def shutdown(self):
-        pass
-
-
-class Ring(object):
-    """Stand-in for a ring: remembers its space, owner, consumers and any
-    header-only views (``block_view``) hanging off it, and fans sequences and
-    spans out to them."""
-
-    def __init__(self, space, owner, header_transform=None):
-        self.space = space
-        self.owner = owner
-        self.consumers = []
-        self.views = []
-        self.header_transform = header_transform
-        self.name = f"ring_{id(self):x}"
-        self._seq = None
-
-    def begin(self, hdr):
-        self._seq = Sequence(deepcopy(hdr))
-        for c in self.consumers:
-            c._begin_sequence(self._seq)
-        for v in self.views:
-            vh = v.header_transform(deepcopy(hdr))
-            if vh is None:
-                raise ValueError("Header transform returned None")
-            v.begin(vh)
-        return self._seq
-
-    def push(self, data, frame_offset):
-        for c in self.consumers:
-            c._push(self._seq, data, frame_offset)
-        for v in self.views:
-            v.push(v._reinterpret(data), frame_offset)
-
-    def end(self):
-        for c in self.consumers:
-            c._end_sequence(self._seq)
-        for v in self.views:
-            v.end()
-
-    def _reinterpret(self, data):
-        """Present `data` with this view's tensor shape/dtype (no copy)."""
-        tensor = self._seq.tensor
-        shape = list(tensor['shape'])
-        fax = shape.index(-1)
-        known = int(np.prod([s for s in shape if s != -1])) if len(shape) > 1 else 1
-        dt = DataType(tensor['dtype'])
-        nbyte = data.nbytes
-        shape[fax] = (nbyte * 8) // (known * dt.itemsize_bits)
-        if list(data.shape) == shape and data.bf.dtype == dt:
-            return data
-        if not data.flags['C_CONTIGUOUS']:
-            raise ValueError("Header views need C-contiguous spans")
-        return ndarray(space=data.bf.space, buffer=data.ctypes.data, shape=shape, dtype=dt,
-                       native=data.bf.native, conjugated=data.bf.conjugated)
-
-
-class Sequence(object):
-    def __init__(self, header):
-        self.header = header
-        self.tensor = header['_tensor']
-        self.name = header.get('name', '')
-        self.time_tag = header.get('time_tag', 0)
-
-
-class Span(object):
-    def __init__(self, sequence, data, frame_offset, frame_axis):
-        self.sequence = sequence
-        self.tensor = sequence.tensor
-        self.data = data
-        self.frame_offset = frame_offset
-        self.frame_axis = frame_axis
-        self.nframe = data.shape[frame_axis]
-        self.nframe_skipped = 0
-        self.nframe_overwritten = 0
-        self.frame_nbyte = 0 if self.nframe == 0 else data.nbytes // max(self.nframe, 1)
+        self._abort.set()
+        for ring in self._rings():
+            ring.wake()
 
 
 def _sync(*spaces):
-    """One stream synchronisation per gulp per block (pipeline.py:628), skipped
-    when every ring involved lives in plain system memory."""
+    """The per-gulp stream synchronisation (pipeline.py:628), skipped when
+    every ring involved lives in plain system memory."""
     if any(str(sp) != 'system' for sp in spaces):
         device.stream_synchronize()
-
-
-def _frame_axis(tensor):
-    return tensor['shape'].index(-1)
-
-
-def _alloc(tensor, nframe, space):
-    shape = list(tensor['shape'])
-    shape[_frame_axis(tensor)] = nframe
-    return empty(shape, dtype=tensor['dtype'], space=space)
-
-
-def _slice_frames(arr, axis, lo, hi):
-    sl = [slice(None)] * arr.ndim
-    sl[axis] = slice(lo, hi)
-    return arr[tuple(sl)]
 
 
 class Block(object):
@@ -265,12 +221,18 @@ class Block(object):
         for r in self.irings:
             r.consumers.append(self)
         self.orings = []
+        self._readers = []
 
     def create_ring(self, space):
-        return Ring(space, self)
+        ring = Ring(space, self)
+        ring.buffer_nframe, ring.buffer_factor = self.buffer_nframe, self.buffer_factor
+        return ring
 
     def get_temp_storage(self, space):
         return None
+
+    def main(self):
+        raise NotImplementedError
 
 
 class SourceBlock(Block):
@@ -289,99 +251,69 @@ class SourceBlock(Block):
     def on_data(self, reader, ospans):
         raise NotImplementedError
 
-    def _run(self):
-        if self.gpu is not None:
-            device.set_device(self.gpu)
-        for sourcename in self.sourcenames:
-            with self.create_reader(sourcename) as reader:
-                ohdrs = self.on_sequence(reader, sourcename)
-                for ohdr in ohdrs:
-                    ohdr.setdefault('time_tag', self._seq_count)
-                    ohdr.setdefault('name', f"unnamed-sequence-{self._seq_count}")
-                    ohdr.setdefault('gulp_nframe', self.gulp_nframe)
-                self._seq_count += 1
-                ring = self.orings[0]
-                seq = ring.begin(ohdrs[0])
-                fax = _frame_axis(seq.tensor)
-                offset = 0
-                while True:
-                    data = _alloc(seq.tensor, self.gulp_nframe, ring.space)
-                    ospan = Span(seq, data, offset, fax)
-                    nframes = self.on_data(reader, [ospan])
-                    _sync(ring.space)
-                    n = nframes[0]
-                    if n > 0:
-                        out = data if n == ospan.nframe else _slice_frames(data, fax, 0, n)
-                        ring.push(out, offset)
-                        offset += n
-                    if n == 0 or n < ospan.nframe:
-                        break
-                ring.end()
+    def main(self):
+        ring = self.orings[0]
+        try:
+            for sourcename in self.sourcenames:
+                with self.create_reader(sourcename) as reader:
+                    ohdrs = self.on_sequence(reader, sourcename)
+                    for ohdr in ohdrs:
+                        ohdr.setdefault('time_tag', self._seq_count)
+                        ohdr.setdefault('name', f"unnamed-sequence-{self._seq_count}")
+                        ohdr.setdefault('gulp_nframe', self.gulp_nframe)
+                    self._seq_count += 1
+                    st = ring.begin_sequence(ohdrs[0], self.gulp_nframe)
+                    try:
+                        while True:
+                            ospan = ring.reserve(st, self.gulp_nframe)
+                            n = self.on_data(reader, [ospan])[0]
+                            ring.commit(st, n)
+                            if n == 0 or n < ospan.nframe:
+                                break
+                    finally:
+                        ring.end_sequence(st)
+        finally:
+            ring.end_writing()
 
 
 class _ConsumerMixin(object):
-    """Input-side buffering shared by transform and sink blocks."""
+    """Input side shared by transform and sink blocks: one reader on the input
+    ring, spans of gulp + overlap frames advanced gulp by gulp."""
 
-    def _begin_sequence(self, iseq):
+    def _check_space(self):
         valid = self.define_valid_input_spaces()
         if valid != 'any' and not any(space_accessible(self.irings[0].space, [s]) for s in valid):
             raise ValueError(f"{self.name}: input space '{self.irings[0].space}' not in {valid}")
-        if self.gpu is not None:
-            device.set_device(self.gpu)
-        self._iseq = iseq
-        self._ifax = _frame_axis(iseq.tensor)
-        self._pending = None            # frames carried between pushes
-        self._pending_offset = 0
-        self._overlap = 0
-        self._open_outputs(iseq)
 
-    def _gulp(self):
-        return self.gulp_nframe or self._iseq.header.get('gulp_nframe') or 1
+    def _gulp(self, iseq):
+        return self.gulp_nframe or iseq.header.get('gulp_nframe') or 1
 
-    def _push(self, iseq, data, frame_offset):
-        """Cuts the pushed span into gulps of gulp + overlap frames.  Gulps are
-        *views* of one buffer walked with a read cursor; only the tail that is
-        left over (fewer than gulp + overlap frames) is copied, once per push,
-        in front of the next span -- so the work is linear in the frames pushed
-        even when the consumer's gulp is much smaller than the producer's."""
-        fax = self._ifax
-        gulp, ovl = self._gulp(), self._overlap
-        if self._pending is None and ovl == 0 and data.shape[fax] == gulp:
-            self._process(data, frame_offset)                 # zero-copy fast path
-            return
-        if self._pending is None:
-            buf, self._pending_offset = data, frame_offset
-        else:
-            n0, n1 = self._pending.shape[fax], data.shape[fax]
-            shape = list(self._pending.shape)
-            shape[fax] = n0 + n1
-            buf = empty(shape, dtype=self._pending.bf.dtype, space=self._pending.bf.space)
-            copy_array(_slice_frames(buf, fax, 0, n0), self._pending)
-            copy_array(_slice_frames(buf, fax, n0, n0 + n1), data)
-        nbuf, pos = buf.shape[fax], 0
-        while nbuf - pos >= gulp + ovl:
-            self._process(_slice_frames(buf, fax, pos, pos + gulp + ovl), self._pending_offset)
-            pos += gulp
-            self._pending_offset += gulp
-        if pos == nbuf:
-            self._pending = None
-        elif pos == 0 and buf is not data:
-            self._pending = buf
-        else:
-            # own copy of the tail: `data` belongs to the producer, and a view
-            # would keep the whole span alive
-            tail = _slice_frames(buf, fax, pos, nbuf)
-            keep = empty(tail.shape, dtype=tail.bf.dtype, space=tail.bf.space)
-            copy_array(keep, tail)
-            self._pending = keep
-
-    def _end_sequence(self, iseq):
-        fax = self._ifax
-        if self._pending is not None and self._pending.shape[fax] > self._overlap:
-            self._process(self._pending, self._pending_offset)      # ragged final gulp
-        self._pending = None
-        self.on_sequence_end(iseq)
-        self._close_outputs()
+    def main(self):
+        reader = self._readers[0]
+        try:
+            for st, iseq in reader.sequences():
+                self._check_space()
+                overlap = self._open_sequence(iseq)
+                gulp = self._gulp(iseq)
+                reader.open(st, gulp, overlap)
+                try:
+                    self._begin_outputs(iseq, gulp, overlap)
+                    offset = 0
+                    while True:
+                        ispan = reader.acquire(st, iseq, offset, gulp + overlap)
+                        if ispan.nframe <= overlap:            # nothing new (or nothing at all)
+                            break
+                        self._process(ispan, overlap)
+                        offset += gulp
+                        reader.release(st, offset)
+                        if ispan.nframe < gulp + overlap:      # ragged final gulp
+                            break
+                    self.on_sequence_end(iseq)
+                finally:
+                    self._end_outputs()
+                    reader.close(st)
+        finally:
+            self._stop_outputs()
 
 
 class TransformBlock(_ConsumerMixin, Block):
@@ -389,6 +321,7 @@ class TransformBlock(_ConsumerMixin, Block):
         super(TransformBlock, self).__init__([iring], *args, **kwargs)
         self.iring = self.irings[0]
         self.orings = [self.create_ring(space=self.iring.space)]
+        self._ost = None
 
     # ---- user hooks (same names/meaning as pipeline.py:703-748)
     def define_valid_input_spaces(self):
@@ -413,39 +346,34 @@ class TransformBlock(_ConsumerMixin, Block):
         memset_array(ospan.data, 0)
 
     # ---- executor internals
-    def _open_outputs(self, iseq):
-        ohdr = self.on_sequence(iseq)
-        ohdr.setdefault('gulp_nframe', iseq.header.get('gulp_nframe'))
-        self._overlap = self.define_input_overlap_nframe(iseq)
-        ring = self.orings[0]
-        self._oseq = Sequence(deepcopy(ohdr))
-        self._ofax = _frame_axis(self._oseq.tensor)
-        self._ooffset = 0
-        self._ohold = None
-        ring.begin(ohdr)
+    def _open_sequence(self, iseq):
+        self._ohdr = self.on_sequence(iseq)
+        self._ohdr.setdefault('gulp_nframe', iseq.header.get('gulp_nframe'))
+        return self.define_input_overlap_nframe(iseq)
 
-    def _process(self, idata, frame_offset):
+    def _begin_outputs(self, iseq, gulp, overlap):
+        self._ost = self.orings[0].begin_sequence(self._ohdr, self.define_output_nframes(gulp + overlap))
+
+    def _process(self, ispan, overlap):
         ring = self.orings[0]
-        ispan = Span(self._iseq, idata, frame_offset, self._ifax)
         onframe = self.define_output_nframes(ispan.nframe)
-        # Blocks that commit rarely (accumulate) keep writing the same output
-        odata = self._ohold if self._ohold is not None else _alloc(self._oseq.tensor, onframe, ring.space)
-        ospan = Span(self._oseq, odata, self._ooffset, self._ofax)
+        # a block that commits rarely (accumulate) is handed the same frames again
+        ospan = ring.reserve(self._ost, onframe)
         ncommit = self.on_data(ispan, ospan)
-        _sync(ring.space, self.irings[0].space)
         if ncommit is None:
-            ooverlap = self.define_output_nframes(self._overlap) if self._overlap else 0
+            ooverlap = self.define_output_nframes(overlap) if overlap else 0
             ncommit = max(onframe - ooverlap, 0)
-        if ncommit == 0:
-            self._ohold = odata
-            return
-        self._ohold = None
-        out = odata if ncommit == onframe else _slice_frames(odata, self._ofax, 0, ncommit)
-        ring.push(out, self._ooffset)
-        self._ooffset += ncommit
+        if str(ring.space) == 'system':
+            _sync(self.irings[0].space)        # (commit synchronises for device rings)
+        ring.commit(self._ost, ncommit)
 
-    def _close_outputs(self):
-        self.orings[0].end()
+    def _end_outputs(self):
+        if self._ost is not None:
+            self.orings[0].end_sequence(self._ost)
+            self._ost = None
+
+    def _stop_outputs(self):
+        self.orings[0].end_writing()
 
 
 class SinkBlock(_ConsumerMixin, Block):
@@ -468,15 +396,21 @@ class SinkBlock(_ConsumerMixin, Block):
     def on_data(self, ispan):
         raise NotImplementedError
 
-    def _open_outputs(self, iseq):
+    def _open_sequence(self, iseq):
         self.on_sequence(iseq)
-        self._overlap = self.define_input_overlap_nframe(iseq)
+        return self.define_input_overlap_nframe(iseq)
 
-    def _process(self, idata, frame_offset):
-        self.on_data(Span(self._iseq, idata, frame_offset, self._ifax))
+    def _begin_outputs(self, iseq, gulp, overlap):
+        pass
+
+    def _process(self, ispan, overlap):
+        self.on_data(ispan)
         _sync(self.irings[0].space)
 
-    def _close_outputs(self):
+    def _end_outputs(self):
+        pass
+
+    def _stop_outputs(self):
         pass
 
 
@@ -491,8 +425,9 @@ class BlockView(object):
 
 def block_view(block, header_transform):
     """A view of `block` whose output header is passed through
-    `header_transform(hdr) -> hdr` (pipeline.py:block_view); no data moves."""
+    `header_transform(hdr) -> hdr` (pipeline.py:block_view); no data moves:
+    readers of the view read the parent ring's storage."""
     parent = block.orings[0]
-    ring = Ring(parent.space, parent.owner, header_transform)
+    ring = ViewRing(parent, header_transform)
     parent.views.append(ring)
     return BlockView(ring, block)

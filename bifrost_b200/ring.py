@@ -1,0 +1,328 @@
+"""Ring buffers between blocks, in the memory space of the data they carry.
+
+The reference's ring (src/ring_impl.cpp, python/bifrost/ring2.py) is a
+byte-addressed circular buffer with a *ghost region*: the first `ghost` bytes
+are mirrored behind the end of the buffer so that every span a reader or
+writer asks for is contiguous, and the mirror is maintained when spans are
+committed (ring_impl.cpp:273-288: `_ghost_write` / `_ghost_read`).  This is the
+same machine, frame-addressed, for the blocks of the hot path:
+
+  * one allocation per sequence, in the ring's space -- 'cuda' rings live in
+    device memory and their ghost copies are device-to-device copies issued
+    on the committing thread's stream (bfArrayCopy), never staged on the host;
+  * the tensor's frame axis is the circular axis; axes in front of it are
+    the reference's "ringlets" (ring2.py:87-107): a span is then a strided
+    view, which is what the kernels take;
+  * one writer, any number of guaranteed readers, each with its own cursor;
+    the writer blocks when it would overwrite frames a reader has not
+    released, a reader blocks until the frames it wants are committed or the
+    sequence ends (ring_impl.cpp:open_read_at / reserve_span);
+  * storage is sized when the sequence starts, from the spans the writer and
+    every reader declare (gulp + overlap), `buffer_nframe` / `buffer_factor`
+    of the block scope (pipeline.py:84-134 of the reference).
+
+Everything here is host-side bookkeeping (a mutex and a condition variable per
+ring); the data path is the copies at the seam.
+"""
+import threading
+from copy import deepcopy
+
+import numpy as np
+
+from bifrost_b200 import device
+from bifrost_b200.DataType import DataType
+from bifrost_b200.ndarray import ndarray, empty, copy_array
+
+
+class PipelineAborted(Exception):
+    """Raised inside blocked ring calls when another block failed."""
+
+
+class EndOfData(Exception):
+    pass
+
+
+def frame_axis(tensor):
+    return tensor['shape'].index(-1)
+
+
+def slice_frames(arr, axis, lo, hi):
+    sl = [slice(None)] * arr.ndim
+    sl[axis] = slice(lo, hi)
+    return arr[tuple(sl)]
+
+
+class Sequence(object):
+    """One sequence as readers see it: header + tensor description."""
+
+    def __init__(self, header, index=0):
+        self.header = header
+        self.tensor = header['_tensor']
+        self.name = header.get('name', '')
+        self.time_tag = header.get('time_tag', 0)
+        self.index = index
+
+
+class Span(object):
+    def __init__(self, sequence, data, frame_offset, faxis):
+        self.sequence = sequence
+        self.tensor = sequence.tensor
+        self.data = data
+        self.frame_offset = frame_offset
+        self.frame_axis = faxis
+        self.nframe = data.shape[faxis]
+        self.nframe_skipped = 0
+        self.nframe_overwritten = 0
+        self.frame_nbyte = 0 if self.nframe == 0 else data.nbytes // max(self.nframe, 1)
+
+
+class _SeqState(object):
+    """Writer-side state of one sequence (shared with the readers under the ring lock)."""
+
+    def __init__(self, header, index, writer_span):
+        self.seq = Sequence(header, index)
+        self.faxis = frame_axis(self.seq.tensor)
+        self.writer_span = max(1, int(writer_span))
+        self.storage = None         # bf.ndarray [.., cap + ghost, ..]
+        self.cap = 0
+        self.ghost = 0
+        self.head = 0               # frames committed
+        self.ended = False
+        self.opened = {}            # reader -> (gulp, overlap) once it has seen the header
+        self.tails = {}             # reader -> frames released
+        self.closed = set()
+
+
+class Ring(object):
+    def __init__(self, space, owner=None, name=None):
+        self.space = str(space)
+        self.owner = owner
+        self.consumers = []         # blocks (graph bookkeeping; readers are opened by Pipeline.run)
+        self.views = []
+        self.name = name or f"ring_{id(self):x}"
+        self.header_transform = None
+        self.base = None
+        self._lock = threading.Lock()
+        self._cond = threading.Condition(self._lock)
+        self._readers = []
+        self._seqs = []             # _SeqState, in order
+        self._writing = True
+        self._abort = None
+        self.buffer_nframe = None
+        self.buffer_factor = None
+        self.stats = dict(ghost_copies=0, ghost_frames=0, allocations=0)
+
+    # ------------------------------------------------------------- plumbing
+    def _check_abort(self):
+        if self._abort is not None and self._abort.is_set():
+            raise PipelineAborted()
+
+    def _wait(self):
+        self._cond.wait(0.2)
+        self._check_abort()
+
+    def set_abort_event(self, ev):
+        self._abort = ev
+
+    def wake(self):
+        with self._cond:
+            self._cond.notify_all()
+
+    def root(self):
+        return self
+
+    def transform_header(self, hdr):
+        return hdr
+
+    def reinterpret(self, seq, data):
+        return data
+
+    # --------------------------------------------------------------- writer
+    def begin_sequence(self, header, gulp_nframe):
+        """Publishes a new sequence.  Storage is allocated by the first
+        reserve(), once every reader has declared its span."""
+        with self._cond:
+            # readers must be done with the previous sequence before its storage goes away
+            while self._seqs and len(self._seqs[-1].closed) < len(self._readers):
+                self._wait()
+            if self._seqs:
+                self._seqs[-1].storage = None
+            st = _SeqState(deepcopy(header), len(self._seqs), gulp_nframe)
+            self._seqs.append(st)
+            self._cond.notify_all()
+            return st
+
+    def _allocate(self, st):
+        span = st.writer_span
+        for gulp, ovl in st.opened.values():
+            span = max(span, gulp + ovl)
+        factor = self.buffer_factor or 4
+        cap = max(int(self.buffer_nframe or 0), factor * span, 2 * span)
+        shape = list(st.seq.tensor['shape'])
+        shape[st.faxis] = cap + span
+        st.storage = empty(shape, dtype=st.seq.tensor['dtype'], space=self.space)
+        st.cap, st.ghost = cap, span
+        self.stats['allocations'] += 1
+
+    def reserve(self, st, nframe):
+        """A writable span of `nframe` frames following the committed ones."""
+        with self._cond:
+            while len(st.opened) < len(self._readers):       # every reader has seen the header
+                self._wait()
+            if st.storage is None:
+                self._allocate(st)
+            assert nframe <= st.ghost, "write span longer than declared"
+            while st.tails and st.head + nframe - st.cap > min(st.tails.values()):
+                self._wait()
+            b = st.head % st.cap
+            return Span(st.seq, slice_frames(st.storage, st.faxis, b, b + nframe), st.head, st.faxis)
+
+    def commit(self, st, nframe):
+        """Makes the first `nframe` frames of the last reserved span visible:
+        ghost maintenance (device copies on this thread's stream, behind the
+        kernels that filled the span), ONE stream synchronisation -- the
+        per-gulp synchronisation of the reference's block loop
+        (pipeline.py:628) -- and only then the new head."""
+        if nframe > 0:
+            b, cap, g = st.head % st.cap, st.cap, st.ghost
+            e = b + nframe
+            if e > cap:        # the span ran into the ghost region: fold it back to the start
+                self._ghost_copy(st, cap, e, 0)
+            if b < g:          # the span covers mirrored frames: refresh the mirror
+                self._ghost_copy(st, b, min(e, g), cap + b)
+        if self.space != 'system':
+            device.stream_synchronize()
+        with self._cond:
+            st.head += nframe
+            self._cond.notify_all()
+
+    def _ghost_copy(self, st, lo, hi, dst_lo):
+        if hi <= lo:
+            return
+        copy_array(slice_frames(st.storage, st.faxis, dst_lo, dst_lo + hi - lo),
+                   slice_frames(st.storage, st.faxis, lo, hi))
+        self.stats['ghost_copies'] += 1
+        self.stats['ghost_frames'] += hi - lo
+
+    def end_sequence(self, st):
+        with self._cond:
+            st.ended = True
+            self._cond.notify_all()
+
+    def end_writing(self):
+        with self._cond:
+            self._writing = False
+            self._cond.notify_all()
+
+    # --------------------------------------------------------------- readers
+    def open_reader(self, who=None):
+        r = Reader(self, who)
+        with self._cond:
+            self._readers.append(r)
+        return r
+
+
+class ViewRing(object):
+    """``block_view``: the parent's storage and cursors, another header."""
+
+    def __init__(self, parent, header_transform):
+        self.parent = parent
+        self.header_transform = header_transform
+        self.space = parent.space
+        self.owner = parent.owner
+        self.consumers = []
+        self.views = []
+        self.name = f"view_{id(self):x}"
+
+    def root(self):
+        return self.parent.root()
+
+    def transform_header(self, hdr):
+        hdr = self.parent.transform_header(hdr)
+        out = self.header_transform(deepcopy(hdr))
+        if out is None:
+            raise ValueError("Header transform returned None")
+        return out
+
+    def open_reader(self, who=None):
+        r = self.root().open_reader(who)
+        r.view = self
+        return r
+
+    def reinterpret(self, seq, data):
+        """Present `data` (a span of the parent) with this view's tensor."""
+        tensor = seq.tensor
+        shape = list(tensor['shape'])
+        fax = shape.index(-1)
+        known = int(np.prod([s for s in shape if s != -1])) if len(shape) > 1 else 1
+        dt = DataType(tensor['dtype'])
+        shape[fax] = (data.nbytes * 8) // (known * dt.itemsize_bits)
+        if list(data.shape) == shape and data.bf.dtype == dt:
+            return data
+        if not data.flags['C_CONTIGUOUS']:
+            raise ValueError("Header views need C-contiguous spans")
+        return ndarray(space=data.bf.space, buffer=data.ctypes.data, shape=shape, dtype=dt,
+                       native=data.bf.native, conjugated=data.bf.conjugated)
+
+
+class Reader(object):
+    """One consumer's cursor into a ring."""
+
+    def __init__(self, ring, who=None):
+        self.ring = ring
+        self.who = who
+        self.view = None
+        self._next = 0
+
+    def sequences(self):
+        """Yields (state, Sequence-as-this-reader-sees-it) until the writer stops."""
+        ring = self.ring
+        while True:
+            with ring._cond:
+                while len(ring._seqs) <= self._next:
+                    if not ring._writing:
+                        return
+                    ring._wait()
+                st = ring._seqs[self._next]
+            self._next += 1
+            hdr = deepcopy(st.seq.header)
+            if self.view is not None:
+                hdr = self.view.transform_header(hdr)
+            yield st, Sequence(hdr, st.seq.index)
+
+    def open(self, st, gulp, overlap):
+        with self.ring._cond:
+            st.opened[self] = (max(1, int(gulp)), max(0, int(overlap)))
+            st.tails[self] = 0
+            self.ring._cond.notify_all()
+
+    def acquire(self, st, seq, frame_offset, nframe):
+        """Frames [frame_offset, frame_offset + nframe) -- fewer at the end of the
+        sequence, none (nframe 0) once it is exhausted."""
+        ring = self.ring
+        with ring._cond:
+            while st.head < frame_offset + nframe and not st.ended:
+                ring._wait()
+            n = max(0, min(nframe, st.head - frame_offset))
+            if st.storage is None:
+                n = 0
+        if n == 0:
+            shape = list(seq.tensor['shape'])
+            shape[frame_axis(seq.tensor)] = 0
+            return Span(seq, empty(shape, dtype=seq.tensor['dtype'], space='system'), frame_offset, frame_axis(seq.tensor))
+        b = frame_offset % st.cap
+        data = slice_frames(st.storage, st.faxis, b, b + n)
+        if self.view is not None:
+            data = self.view.reinterpret(seq, data)
+        return Span(seq, data, frame_offset, frame_axis(seq.tensor))
+
+    def release(self, st, upto_frame):
+        with self.ring._cond:
+            st.tails[self] = max(st.tails.get(self, 0), upto_frame)
+            self.ring._cond.notify_all()
+
+    def close(self, st):
+        with self.ring._cond:
+            st.tails[self] = 1 << 62
+            st.closed.add(self)
+            self.ring._cond.notify_all()

@@ -109,6 +109,23 @@ def test_r2c_and_c2r():
             compare(back, np.fft.irfftn(spec.astype(np.complex128), s=[shape[a] for a in axes], axes=axes) * norm)
 
 
+@pytest.mark.parametrize("n,batch", [(1 << 14, 3), (1 << 15, 1), (16000, 2), (1 << 20, 2), (1 << 24, 1)])
+def test_r2c_and_c2r_longer_than_one_pass(n, batch):
+    """test/test_fft.py:57,194-201 runs r2c / c2r at 2^24 points: the half-length
+    complex transform + fix-up path (run_axis_real_long), f32 and integer inputs."""
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(batch, n)).astype(np.float32)
+    spec = np.fft.rfft(x.astype(np.float64), axis=1)
+    compare(run(x, (batch, n // 2 + 1), 'cf32', [1]), spec)
+    back = run(spec.astype(np.complex64), (batch, n), 'f32', [1])
+    compare(back, np.fft.irfft(spec.astype(np.complex64).astype(np.complex128), n=n, axis=1) * n)
+    if n <= (1 << 20):
+        for dtype, scale in [(np.int16, 32767), (np.int8, 127)]:
+            xi = (rng.normal(size=(batch, n)) * scale / 4).astype(dtype)
+            compare(run(xi, (batch, n // 2 + 1), 'cf32', [1]),
+                    np.fft.rfft(xi.astype(np.float64) / (scale + 1), axis=1))
+
+
 def test_r2c_integer_and_misaligned():
     """test/test_fft.py:83-99: i8/i16 inputs at odd byte offsets."""
     rng = np.random.default_rng(6)
