@@ -125,3 +125,23 @@ def test_two_rank_gloo_exchange():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert 'SHARDED_FDMT_OK' in out.stdout
+
+
+def test_two_rank_gloo_packed_schedule():
+    """The schedule bfFdmtShardInit builds (packed-integer passes cut at the
+    step with `world` sub-bands), run by two gloo ranks with the numpy
+    interpreter: local programs touch one rank's sub-tree only, the cut-step
+    rows form one block per rank, and the ranks' delay blocks assemble the
+    oracle's bank bit for bit."""
+    import socket
+    import subprocess
+    sock = socket.socket()
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fdmt_packed_shard_worker.py')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), worker],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert 'SHARDED_PACKED_OK' in out.stdout, out.stdout[-2000:]
