@@ -872,16 +872,16 @@ static size_t packed_geometry(std::vector<PackedPass> const& passes, long ntime,
 	return std::max<size_t>(off, 512);
 }
 
-template<int ESZ, int SRCK, int DSTK, int LV, int NW = 8>
+template<int ESZ, int SRCK, int DSTK, int LV, int NW = 8, int MINB = 0>
 static cudaError_t launch_packed_kernel(PackedParams const& q, dim3 grid, int threads, size_t smem, cudaStream_t st) {
 	static size_t attr_smem = 0;
 	if( smem > attr_smem ) {
-		cudaError_t e = cudaFuncSetAttribute(fdmt_packed_kernel<ESZ, SRCK, DSTK, LV, NW>,
+		cudaError_t e = cudaFuncSetAttribute(fdmt_packed_kernel<ESZ, SRCK, DSTK, LV, NW, MINB>,
 		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if( e != cudaSuccess ) return e;
 		attr_smem = smem;
 	}
-	fdmt_packed_kernel<ESZ, SRCK, DSTK, LV, NW><<<grid, threads, smem, st>>>(q);
+	fdmt_packed_kernel<ESZ, SRCK, DSTK, LV, NW, MINB><<<grid, threads, smem, st>>>(q);
 	return cudaGetLastError();
 }
 
@@ -904,11 +904,14 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 	dim3 grid((unsigned)gx, (unsigned)nprog, (unsigned)nbatch);
 	const int threads = cp.nwarp * 32;
 	const size_t smem = cp.smem_bytes();
+	// four CTAs per SM for a byte pass that fits them (no source region of its own)
+	const bool minb4 = cp.src_kind == PK_SRC_BYTES && !cp.prefetch && smem <= 56 * 1024 && env_int("BFB_FDMT_PACKED_MINB4", 1) != 0;
 	cudaError_t e = cudaErrorInvalidValue;
 #define BFB_CH_LAUNCH(E_, S_, D_) \
 	e = (cp.lv == 5 && S_ != PK_SRC_BYTES) ? launch_packed_kernel<E_, (S_ == PK_SRC_BYTES ? PK_SRC_SAME : S_), D_, 5>(q, grid, threads, smem, st) \
 	  : (cp.nwarp > 12 && S_ != PK_SRC_BYTES) ? launch_packed_kernel<E_, (S_ == PK_SRC_BYTES ? PK_SRC_SAME : S_), D_, 3, 16>(q, grid, threads, smem, st) \
 	  : (cp.nwarp > 8 && S_ != PK_SRC_BYTES)  ? launch_packed_kernel<E_, (S_ == PK_SRC_BYTES ? PK_SRC_SAME : S_), D_, 3, 12>(q, grid, threads, smem, st) \
+	  : (S_ == PK_SRC_BYTES && minb4)         ? launch_packed_kernel<E_, S_, D_, 3, 8, (S_ == PK_SRC_BYTES ? 4 : 0)>(q, grid, threads, smem, st) \
 	                                        : launch_packed_kernel<E_, S_, D_, 3>(q, grid, threads, smem, st)
 	if( cp.esize == 2 ) {
 		if( cp.src_kind == PK_SRC_BYTES ) {

@@ -259,8 +259,8 @@ inline bool build_packed_pass(FdmtPlan const& P, std::vector<std::vector<char> >
 	// Source in region 0 (no region of its own): with an even number of op levels
 	// region 0 is free again while the last level runs (it reads region 1), with
 	// an odd number region 1 is -- then the next tile is laid out mirrored.
-	cp->early = cfg.early && !cfg.own_src && !bytes && nopl >= 2;
-	const bool swap = cp->early && (nopl & 1);
+	cp->early = cfg.early && !cfg.own_src && nopl >= 2 && (!bytes || (nopl % 2) == 0);   // (byte rows are not mirrored)
+	const bool swap = cp->early && (nopl & 1) && !bytes;
 	cp->src_kind = src_kind; cp->dst_kind = dst_kind;
 	cp->T = T; cp->nprog = (int)progs.size(); cp->nwarp = nwarp; cp->lookback = lookback;
 	int slots = 1, src_slots = 1;
@@ -895,7 +895,7 @@ __device__ __forceinline__ void pk_tiles(const PackedSmem& S, const PackedParams
                                          long soff, long roff, long doff, uint32_t& parity, int lane, int warp, int nwarp) {
 	if( count <= 0 ) return;
 	const int R = (SRCK == PK_SRC_SAME && P.early) ? S.shdr[0].w : 0;   // region size when tiles alternate
-	const bool early = SRCK == PK_SRC_SAME && P.early && P.nlev >= 2;
+	const bool early = P.early && P.nlev >= 2;
 	if( warp == 0 ) pk_stage_issue<ESZ, SRCK>(S, P, P.t_begin + first * P.T, soff, roff, lane);
 	int flip = 0;
 	for( long n=0; n<count; ++n ) {
@@ -927,8 +927,10 @@ __device__ __forceinline__ void pk_tiles(const PackedSmem& S, const PackedParams
 // One pass per launch: grid (tile stride, program, batch).
 // (NW = warps per CTA the kernel is compiled for: 8 -> three CTAs per SM with
 // three vectors per lane, 12 / 16 -> two)
-template<int ESZ, int SRCK, int DSTK, int LV, int NW>
-__global__ void __launch_bounds__(NW * 32, (NW == 8 && LV == 3) ? 3 : 2)
+// MINB = 4: the byte pass without a source region of its own fits four CTAs per
+// SM (64 registers per thread).
+template<int ESZ, int SRCK, int DSTK, int LV, int NW, int MINB = 0>
+__global__ void __launch_bounds__(NW * 32, MINB ? MINB : ((NW == 8 && LV == 3) ? 3 : 2))
 fdmt_packed_kernel(const __grid_constant__ PackedParams P) {
 	using namespace packed_dev;
 	extern __shared__ __align__(16) unsigned char pk_smem[];

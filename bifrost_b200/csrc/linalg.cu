@@ -479,6 +479,187 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap tmap, TcParams P) {
 	cluster_sync_all();
 }
 
+// ---------------------------------------------------------------------------
+// c = alpha a.b + beta c for ci8 operands on the tensor cores (the reference
+// hands this case to cublasCgemmEx with CUDA_C_8I inputs, src/linalg.cu:406-424;
+// it is the beamformer's product: weights x voltages).  Same machine as the
+// correlator above, with two different operands: with At = a^T (k slow) read as
+// the real matrix At[k][2m+p] and b as B[k][2n+q] (p, q = re/im), the real
+// int8 product G = At^T B holds the four real products of every (m, n):
+//   Re c = G[2m][2n] - G[2m+1][2n+1],   Im c = G[2m][2n+1] + G[2m+1][2n]
+// (signs flip with the operands' conjugation flags).  Both operands are
+// MN-major exactly like the correlator's, so TMA boxes, UMMA descriptors, the
+// stage pipeline and the TMEM epilogue are shared; the sums are exact integers.
+// A work unit is a 128 x 256 tile of G = 64 x 128 complex outputs.
+// ---------------------------------------------------------------------------
+struct AbTcParams {
+	float2* c; long c_row, c_batch;      // float2 units
+	int   M, N, K;                       // complex rows, complex columns, reduction length
+	int   njj;                           // column-block pairs per row block
+	int   a_batched;                     // 0: one At for every batch entry
+	float alpha, beta;
+	float s_re, s_01, s_10;              // Re = G00 + s_re G11, Im = s_01 G01 + s_10 G10
+};
+
+__device__ __forceinline__ void ab_epilogue(uint64_t* tmem_bar, uint32_t tmem_base, float2* staging,
+                                            AbTcParams const& P, int batch, int I, int J0, int nb,
+                                            int warp, int lane) {
+	mbar_wait(tmem_bar, 0);
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const int quarter = warp & 3;
+	const int m = quarter * 32 + lane;
+	const int il = m >> 1, par = m & 1;
+	float* stf = (float*)staging;
+	const int te = threadIdx.x - 64;
+	float2* cb = P.c + (long)batch * P.c_batch;
+	for( int h=0; h<nb; ++h ) {
+		const int J = J0 + h;
+#pragma unroll 1
+		for( int c0=0; c0<128; c0+=32 ) {
+			uint32_t r[32];
+			const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * h + c0);
+			asm volatile(
+				"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+				"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+				"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+				: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+				  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+				  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+				  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+				: "r"(taddr));
+			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+			for( int q=0; q<16; ++q ) {
+				// even row 2m: (G00, G01); odd row 2m+1: (G10, G11); swap the second entries
+				const int mine0 = (int)r[2*q], mine1 = (int)r[2*q+1];
+				const int other1 = __shfl_xor_sync(0xffffffffu, mine1, 1);
+				const float v = par ? (P.s_01 * (float)other1 + P.s_10 * (float)mine0)
+				                    : ((float)mine0 + P.s_re * (float)other1);
+				const int jl = (c0 >> 1) + q;
+				stf[(il * 65 + jl) * 2 + par] = v;
+			}
+		}
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+		for( int idx = te; idx < 64 * 64; idx += 128 ) {
+			const int il2 = idx >> 6, jl2 = idx & 63;
+			const int i = I * 64 + il2, j = J * 64 + jl2;
+			if( i < P.M && j < P.N ) {
+				const float2 v = staging[il2 * 65 + jl2];
+				float2 o = make_float2(P.alpha * v.x, P.alpha * v.y);
+				float2* dst = cb + (long)i * P.c_row + j;
+				if( P.beta != 0.f ) { float2 old = *dst; o.x += P.beta * old.x; o.y += P.beta * old.y; }
+				*dst = o;
+			}
+		}
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+	}
+}
+
+template<int TC_STAGES>
+__global__ void __launch_bounds__(TC_THREADS)
+ab_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, AbTcParams P) {
+	extern __shared__ __align__(1024) unsigned char tc_smem[];
+	unsigned char* tiles = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
+	float2* staging = (float2*)(tiles + TC_STAGES * TC_STAGE_BYTES);
+	uint64_t* full_bar  = (uint64_t*)(staging + 64 * 65);
+	uint64_t* empty_bar = full_bar + TC_STAGES;
+	uint64_t* tmem_bar  = empty_bar + TC_STAGES;
+	uint32_t* tmem_slot = (uint32_t*)(tmem_bar + 1);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int batch = blockIdx.y;
+	const int I = blockIdx.x / P.njj, J0 = 2 * (blockIdx.x % P.njj);
+	const int nb = ((J0 + 1) * 64 < P.N) ? 2 : 1;
+	const int nk = (P.K + TC_KT - 1) / TC_KT;
+
+	if( threadIdx.x == 0 ) {
+		for( int s=0; s<TC_STAGES; ++s ) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+		mbar_init(tmem_bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if( warp == 1 ) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+		             :: "r"(smem_u32(tmem_slot)), "n"(256));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const uint32_t tmem_base = *tmem_slot;
+
+	if( warp == 0 ) {
+		if( lane == 0 ) {
+			const uint32_t bytes = (uint32_t)TC_TILE_BYTES * (1 + nb);
+			for( int it=0; it<nk; ++it ) {
+				const int s = it % TC_STAGES;
+				const uint32_t ph = (it / TC_STAGES) & 1;
+				mbar_wait(&empty_bar[s], ph ^ 1);
+				unsigned char* a = tiles + (size_t)s * TC_STAGE_BYTES;
+				mbar_expect_tx(&full_bar[s], bytes);
+				tma_load_3d(a, &tmap_a, &full_bar[s], 128 * I, it * TC_KT, P.a_batched ? batch : 0);
+				tma_load_3d(a + TC_TILE_BYTES, &tmap_b, &full_bar[s], 128 * J0, it * TC_KT, batch);
+				if( nb == 2 ) tma_load_3d(a + 2 * TC_TILE_BYTES, &tmap_b, &full_bar[s], 128 * (J0 + 1), it * TC_KT, batch);
+			}
+		}
+	} else if( warp == 1 ) {
+		const uint32_t idesc = umma_idesc_i8(nb == 2 ? 256u : 128u);
+		for( int it=0; it<nk; ++it ) {
+			const int s = it % TC_STAGES;
+			const uint32_t ph = (it / TC_STAGES) & 1;
+			mbar_wait(&full_bar[s], ph);
+			asm volatile("tcgen05.fence::after_thread_sync;");
+			if( lane == 0 ) {
+				const uint32_t a_addr = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES);
+				const uint32_t b_addr = a_addr + TC_TILE_BYTES;
+#pragma unroll
+				for( int kk=0; kk<TC_KT/32; ++kk ) {
+					const uint64_t da = umma_desc_mn_sw128(a_addr + kk * 32 * 128);
+					const uint64_t db = umma_desc_mn_sw128(b_addr + kk * 32 * 128);
+					const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+					asm volatile(
+						"{\n\t.reg .pred p;\n\t"
+						"setp.ne.b32 p, %4, 0;\n\t"
+						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+						:: "r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+				}
+				asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+				             :: "r"(smem_u32(&empty_bar[s])) : "memory");
+				if( it == nk - 1 ) {
+					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+					             :: "r"(smem_u32(tmem_bar)) : "memory");
+				}
+			}
+			__syncwarp();
+		}
+	} else {
+		ab_epilogue(tmem_bar, tmem_base, staging, P, batch, I, J0, nb, warp, lane);
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	if( warp == 1 ) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(256));
+	}
+}
+
+// a[m][k] (any strides) -> At[batch][k][m] ci8, row pitch `pitch` bytes
+__global__ void __launch_bounds__(256)
+ab_transpose_a_kernel(const char* a, long sm, long sk, long sbatch, char* at, long pitch, long at_batch, int M, int K) {
+	__shared__ short tile[32][33];
+	const int bx = blockIdx.x * 32, by = blockIdx.y * 32;          // bx: k, by: m
+	const char* ab = a + (long)blockIdx.z * sbatch;
+	char* tb = at + (long)blockIdx.z * at_batch;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	for( int r=ty; r<32; r+=8 ) {
+		const int m = by + r, k = bx + tx;
+		tile[r][tx] = (m < M && k < K) ? *(const short*)(ab + (long)m * sm + (long)k * sk) : (short)0;
+	}
+	__syncthreads();
+	for( int r=ty; r<32; r+=8 ) {
+		const int k = bx + r, m = by + tx;
+		if( k < K && m < M ) *(short*)(tb + (long)k * pitch + 2L * m) = tile[tx][r];
+	}
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -505,7 +686,10 @@ static PFN_encodeTiled get_encode_fn() {
 using namespace bfb;
 
 struct BFlinalg_impl {
-	int dummy = 0;
+	// a^T staging of the tensor-core a.b path (ci8), grown on demand
+	void*  at_buf = nullptr;
+	size_t at_size = 0;
+	~BFlinalg_impl() { if( at_buf ) cudaFree(at_buf); }
 };
 
 namespace {
@@ -693,7 +877,75 @@ static bool ab_kind_ok(BFdtype t) {
 	       t == BF_DTYPE_F32 || t == BF_DTYPE_F64 || t == BF_DTYPE_I8;
 }
 
-static BFstatus matmul_ab(double alpha, BFarray const* a, BFarray const* b, double beta, BFarray const* c) {
+// The tensor-core form of the product, when the operands allow it (returns
+// false to leave the call to the SIMT kernel): ci8 x ci8 -> cf32, b rows
+// contiguous and 16-byte aligned (TMA), c rows contiguous, at most one batch
+// dimension, sums that fit int32.
+static bool matmul_ab_tc(BFlinalg_impl* h, AbParams const& P, long nbatch, BFstatus* status) {
+	*status = BF_STATUS_SUCCESS;
+	if( getenv("BFB_LINALG_SIMT") || !get_encode_fn() ) return false;
+	if( P.a.kind != BF_DTYPE_CI8 || P.b.kind != BF_DTYPE_CI8 || P.c_kind != BF_DTYPE_CF32 ) return false;
+	if( P.nb > 1 || P.c_n != 8 || P.c_m % 8 || P.b.sm != 2 || P.b.sk % 16 || ((uintptr_t)P.b.p % 16) ) return false;
+	if( P.nb == 1 && (P.b.sb[0] % 16 || P.c_b[0] % 8 || P.b.sb[0] == 0) ) return false;
+	if( (long)P.K * 2 * 127 * 127 >= (1L << 31) || P.K < 1 || P.M < 1 || P.N < 8 ) return false;
+	cudaStream_t st = thread_stream();
+	// a^T, k slow: [batch][K][pitch]
+	const bool a_batched = P.nb == 1 && P.a.sb[0] != 0;
+	const long na = a_batched ? nbatch : 1;
+	const long pitch = round_up<long>(2L * P.M, 16);
+	const size_t need = (size_t)na * P.K * pitch;
+	if( h->at_size < need ) {
+		cudaStreamSynchronize(st);
+		if( h->at_buf ) cudaFree(h->at_buf);
+		h->at_buf = nullptr; h->at_size = 0;
+		if( cudaMalloc(&h->at_buf, need) != cudaSuccess ) { *status = BF_STATUS_MEM_ALLOC_FAILED; return true; }
+		h->at_size = need;
+	}
+	{
+		dim3 grid((unsigned)div_up<int>(P.K, 32), (unsigned)div_up<int>(P.M, 32), (unsigned)na);
+		ab_transpose_a_kernel<<<grid, 256, 0, st>>>(P.a.p, P.a.sm, P.a.sk, a_batched ? P.a.sb[0] : 0,
+		                                            (char*)h->at_buf, pitch, (long)P.K * pitch, P.M, P.K);
+		count_launch();
+	}
+	CUtensorMap ta, tb;
+	cuuint32_t box[3] = {128, TC_KT, 1}, estr[3] = {1, 1, 1};
+	{
+		cuuint64_t gdim[3] = {(cuuint64_t)(2 * P.M), (cuuint64_t)P.K, (cuuint64_t)na};
+		cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)((long)P.K * pitch)};
+		if( get_encode_fn()(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->at_buf, gdim, gstr, box, estr,
+		                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+		                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ) return false;
+	}
+	{
+		cuuint64_t gdim[3] = {(cuuint64_t)(2 * P.N), (cuuint64_t)P.K, (cuuint64_t)nbatch};
+		cuuint64_t gstr[2] = {(cuuint64_t)P.b.sk, (cuuint64_t)(P.nb == 1 ? P.b.sb[0] : round_up<long>(P.b.sk * P.K, 16))};
+		if( get_encode_fn()(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)P.b.p, gdim, gstr, box, estr,
+		                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+		                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ) return false;
+	}
+	AbTcParams Q;
+	Q.c = (float2*)P.c; Q.c_row = P.c_m / 8; Q.c_batch = P.nb == 1 ? P.c_b[0] / 8 : 0;
+	Q.M = P.M; Q.N = P.N; Q.K = P.K;
+	Q.njj = div_up<int>(div_up<int>(P.N, 64), 2);
+	Q.a_batched = a_batched ? 1 : 0;
+	Q.alpha = (float)P.alpha; Q.beta = (float)P.beta;
+	const bool ca = P.a.conj != 0, cb = P.b.conj != 0;
+	Q.s_re = (ca != cb) ? 1.f : -1.f;
+	Q.s_01 = cb ? -1.f : 1.f;
+	Q.s_10 = ca ? -1.f : 1.f;
+	constexpr int STAGES = 3;
+	const size_t smem = (size_t)STAGES * TC_STAGE_BYTES + 64 * 65 * sizeof(float2) + (2 * STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
+	if( cudaFuncSetAttribute(ab_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ) {
+		*status = BF_STATUS_INTERNAL_ERROR; return true;
+	}
+	dim3 grid((unsigned)(div_up<int>(P.M, 64) * Q.njj), (unsigned)nbatch);
+	ab_tc_kernel<STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tb, Q);
+	count_launch();
+	if( cudaGetLastError() != cudaSuccess ) *status = BF_STATUS_INTERNAL_ERROR;
+	return true;
+}
+
+static BFstatus matmul_ab(BFlinalg_impl* handle, double alpha, BFarray const* a, BFarray const* b, double beta, BFarray const* c) {
 	BFB_ASSERT(space_on_device(a->space) && space_on_device(b->space), BF_STATUS_UNSUPPORTED_SPACE);
 	int nd = c->ndim;
 	BFB_ASSERT(a->ndim == nd && b->ndim == nd && nd >= 2 && nd <= BF_MAX_DIMS, BF_STATUS_INVALID_SHAPE);
@@ -726,6 +978,10 @@ static BFstatus matmul_ab(double alpha, BFarray const* a, BFarray const* b, doub
 	}
 	if( P.M == 0 || P.N == 0 || nbatch == 0 ) return BF_STATUS_SUCCESS;
 	BFB_ASSERT(nbatch <= 65535, BF_STATUS_UNSUPPORTED_SHAPE);
+	{
+		BFstatus tcs = BF_STATUS_SUCCESS;
+		if( matmul_ab_tc(handle, P, nbatch, &tcs) ) return tcs;
+	}
 	dim3 grid((unsigned)div_up<int>(P.N, 16), (unsigned)div_up<int>(P.M, 16), (unsigned)nbatch);
 	bool dbl = a->dtype == BF_DTYPE_F64 || a->dtype == BF_DTYPE_CF64 || b->dtype == BF_DTYPE_F64 ||
 	           b->dtype == BF_DTYPE_CF64;
@@ -759,7 +1015,7 @@ BFstatus bfLinAlgMatMul(BFlinalg handle, double alpha, BFarray const* a, BFarray
 	BFB_ASSERT(a || b, BF_STATUS_INVALID_ARGUMENT);
 	BFB_ASSERT(c, BF_STATUS_INVALID_POINTER);
 	BFB_ASSERT(space_on_device(c->space), BF_STATUS_UNSUPPORTED_SPACE);
-	if( a && b ) { BFB_TRY(return matmul_ab(alpha, a, b, beta, c)); }
+	if( a && b ) { BFB_TRY(return matmul_ab(handle, alpha, a, b, beta, c)); }
 	BFarray const* x = a ? a : b;
 	BFB_ASSERT(space_on_device(x->space), BF_STATUS_UNSUPPORTED_SPACE);
 	BFB_ASSERT(x->ndim == c->ndim && x->ndim >= 2 && x->ndim <= BF_MAX_DIMS, BF_STATUS_INVALID_SHAPE);

@@ -226,6 +226,57 @@ def test_matmul_ab_ci8_and_beamformer():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k,batch", [(5, 64, 32, None), (64, 128, 64, None), (111, 224, 77, None),
+                                         (65, 136, 500, 3), (200, 1000, 300, 2), (32, 4096, 512, 4)])
+def test_matmul_ab_ci8_on_the_tensor_cores(m, n, k, batch):
+    """ci8 x ci8 -> cf32 with TMA-friendly operands takes the tcgen05 kernel
+    (two launches: a^T staging + the product); exact integers, every
+    conjugation flag, alpha / beta, a shared or per-batch weight matrix."""
+    rng = np.random.default_rng(m * n + k)
+    bs = () if batch is None else (batch,)
+    a = rand_ci8(rng, bs + (m, k))
+    b = rand_ci8(rng, bs + (k, n))
+    ar, ai = a['re'].astype(np.int64), a['im'].astype(np.int64)
+    br, bi = b['re'].astype(np.int64), b['im'].astype(np.int64)
+
+    def gold(ca, cb):
+        sa, sb = (-1 if ca else 1), (-1 if cb else 1)
+        re = ar @ br - (sa * ai) @ (sb * bi)
+        im = ar @ (sb * bi) + (sa * ai) @ br
+        return (re + 1j * im).astype(np.complex64)
+
+    da, db = bf.asarray(a, space='cuda'), bf.asarray(b, space='cuda')
+    la = LinAlg()
+    for ca in (False, True):
+        for cb in (False, True):
+            dc = bf.asarray(np.full(bs + (m, n), 7 - 3j, np.complex64), space='cuda')
+            before = bf.launch_count()
+            la.matmul(1, da.conj() if ca else da, db.conj() if cb else db, 0, dc)
+            assert bf.launch_count() - before == 2, "the tensor-core path was not taken"
+            np.testing.assert_array_equal(np.asarray(dc.copy('system')), gold(ca, cb))
+    # alpha / beta
+    c0 = (rng.integers(-50, 50, size=bs + (m, n)) + 1j * rng.integers(-50, 50, size=bs + (m, n))).astype(np.complex64)
+    dc = bf.asarray(c0, space='cuda')
+    la.matmul(0.5, da, db, 2.0, dc)
+    np.testing.assert_allclose(np.asarray(dc.copy('system')), 0.5 * gold(False, False) + 2.0 * c0, rtol=1e-6)
+    # one weight matrix for every batch entry (broadcast batch dim of a)
+    if batch is not None:
+        a1 = bf.asarray(a[:1], space='cuda')
+        dc = bf.zeros(bs + (m, n), 'cf32', 'cuda')
+        la.matmul(1, a1, db, 0, dc)
+        ar, ai = np.broadcast_to(ar[:1], ar.shape), np.broadcast_to(ai[:1], ai.shape)
+        np.testing.assert_array_equal(np.asarray(dc.copy('system')), gold(False, False))
+    # same numbers from the SIMT kernel
+    os.environ['BFB_LINALG_SIMT'] = '1'
+    try:
+        dc2 = bf.zeros(bs + (m, n), 'cf32', 'cuda')
+        la.matmul(1, da if batch is None else bf.asarray(a[:1], space='cuda'), db, 0, dc2)
+    finally:
+        del os.environ['BFB_LINALG_SIMT']
+    np.testing.assert_array_equal(np.asarray(dc2.copy('system')), gold(False, False))
+
+
+@pytest.mark.gpu
 def test_invalid_forms_return_status():
     from bifrost_b200.libbifrost import _bf
     a = bf.empty((4, 8), 'cf32', 'cuda')
