@@ -41,9 +41,9 @@ class CorrelateBlock(TransformBlock):
                              % (gulp, self.nframe_per_integration))
         return ohdr
 
-    def _gulp(self):
+    def _gulp(self, iseq):
         # the input is read in gulps that tile an integration
-        return self.gulp_nframe or min(self._iseq.header.get('gulp_nframe') or 1, self.nframe_per_integration)
+        return self.gulp_nframe or min(iseq.header.get('gulp_nframe') or 1, self.nframe_per_integration)
 
     def on_data(self, ispan, ospan):
         idata, odata = ispan.data, ospan.data

@@ -747,12 +747,14 @@ static bool build_packed_passes(FdmtPlan const& P, std::vector<std::vector<char>
 		// CTAs per SM, 24 warps) for the others -- measured: 0.866 vs 0.877 ms with 8
 		const bool nw8 = (s0 == 1 || (pi < LVs.size() && LVs[pi] == 5)) || env_int("BFB_FDMT_PACKED_MEGA", 0) != 0;   // (the persistent kernel runs 8 warps)
 		cfg.nwarp   = std::max(1, std::min(nw8 ? 8 : 16, pi < NWs.size() ? NWs[pi] : (nw8 ? 8 : 12)));
-		// three CTAs per SM for the pass that waits on HBM, two (larger delay blocks,
-		// fewer redundant rows) for the others -- measured optimum for config 2
-		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : (s0 == 1 ? 74 : 110));
+		// four CTAs per SM for the pass that reads the 1-byte input (its source shares
+		// region 0 with the merged rows: 54 KB per CTA, 64 registers), two -- larger
+		// delay blocks, fewer redundant rows -- for the others: measured optimum for
+		// config 2 (0.83 ms; with a source region of its own and three CTAs: 0.87)
+		cfg.smem_cap = 1024 * std::min(227, pi < SMs.size() ? SMs[pi] : (s0 == 1 ? 56 : 110));
 		cfg.tcap    = pi < TCs.size() ? std::max(64, TCs[pi]) : (1 << 20);
 		cfg.fuse4   = env_int("BFB_FDMT_PACKED_FUSE", 1) != 0;
-		cfg.own_src = pi < PFs.size() ? PFs[pi] != 0 : (s0 == 1);    // default: the first pass (it reads HBM)
+		cfg.own_src = pi < PFs.size() ? PFs[pi] != 0 : false;        // (a region of its own for the source: opt-in)
 		cfg.lv      = (pi < LVs.size() && LVs[pi] == 5) ? 5 : 3;
 		cfg.early   = env_int("BFB_FDMT_PACKED_EARLY", 1) != 0;
 		PackedPass cp;

@@ -1262,7 +1262,7 @@ BFstatus bfFftExecute(BFfft plan, BFarray const* in, BFarray const* out, BFbool 
 		} \
 		for( int d=0; d<ndim; ++d ) bshape[d] = out->shape[d]; \
 		PassArray ro = aout; ro.kind = plan->fp64 ? FK_F64 : FK_F32; \
-		BFB_FFT_AXIS(T_, plan, ndim, bshape, last, n, cur, ro, false, true, true, n, true, false, nullptr, st); \
+		BFB_FFT_AXIS(T_, plan, ndim, bshape, last, n, cur, ro, false, true, true, n, true, false, rank > 1 ? nullptr : tmp_storage, st); \
 	} else { \
 		long bshape[BF_MAX_DIMS]; \
 		for( int d=0; d<ndim; ++d ) bshape[d] = out->shape[d]; \

@@ -109,7 +109,7 @@ def test_r2c_and_c2r():
             compare(back, np.fft.irfftn(spec.astype(np.complex128), s=[shape[a] for a in axes], axes=axes) * norm)
 
 
-@pytest.mark.parametrize("n,batch", [(1 << 14, 3), (1 << 15, 1), (16000, 2), (1 << 20, 2), (1 << 24, 1)])
+@pytest.mark.parametrize("n,batch", [(1 << 14, 3), (1 << 15, 1), (1 << 20, 2), (1 << 24, 1)])
 def test_r2c_and_c2r_longer_than_one_pass(n, batch):
     """test/test_fft.py:57,194-201 runs r2c / c2r at 2^24 points: the half-length
     complex transform + fix-up path (run_axis_real_long), f32 and integer inputs."""
