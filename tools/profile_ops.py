@@ -26,4 +26,33 @@ if 'correlate' in which:
     for _ in range(2):
         la.matmul(1, None, x.transpose(1, 0, 2), 0, c)
     bf.device.stream_synchronize()
+if 'beamform' in which:
+    # weights x voltages on the tensor cores (ab_tc_kernel): 64 beams, 512 inputs, 8192 samples, 64 channels
+    import time
+    nbeam, nin, ntime, nchan = 64, 512, 8192, 64
+    CI8 = bf.DataType('ci8').as_numpy_dtype()
+    w = bf.asarray(rng.integers(-127, 128, size=(nchan, nbeam, nin, 2), dtype=np.int8).view(CI8).reshape(nchan, nbeam, nin), space='cuda')
+    v = bf.asarray(rng.integers(-127, 128, size=(nchan, nin, ntime, 2), dtype=np.int8).view(CI8).reshape(nchan, nin, ntime), space='cuda')
+    c = bf.zeros((nchan, nbeam, ntime), 'cf32', 'cuda')
+    la = bf.linalg.LinAlg()
+    for _ in range(3):
+        la.matmul(1, w, v, 0, c)
+    bf.device.stream_synchronize()
+    if 'time' in which:
+        import json
+        for env in ('', '1'):
+            if env:
+                os.environ['BFB_LINALG_SIMT'] = '1'
+            la.matmul(1, w, v, 0, c)
+            bf.device.stream_synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                la.matmul(1, w, v, 0, c)
+            bf.device.stream_synchronize()
+            ms = (time.perf_counter() - t0) * 100
+            ops = 8.0 * nchan * nbeam * nin * ntime
+            print(json.dumps(dict(op='a.b ci8 beamformer %dx%dx%d x%d chan' % (nbeam, nin, ntime, nchan),
+                                  path='simt' if env else 'tcgen05', ms=ms, TOPs=ops / ms / 1e9,
+                                  out_GBps=nchan * nbeam * ntime * 8 / ms / 1e6)))
+        os.environ.pop('BFB_LINALG_SIMT', None)
 print('done')
