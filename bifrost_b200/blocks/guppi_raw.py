@@ -34,7 +34,8 @@ class GuppiRawSourceBlock(SourceBlock):
         return _mjd2unix(mjd), tsamp
 
     def on_sequence(self, reader, sourcename):
-        card = guppi_raw.read_header(reader)
+        card = guppi_raw.read_header(reader, 0)
+        self.stream_pos = card.nbyte
         nbit, nchan, ntime = card['NBITS'], card['OBSNCHAN'], card['NTIME']
         if nbit not in (4, 8, 16, 32, 64):
             raise ValueError("Unsupported NBITS: %r" % nbit)
@@ -42,6 +43,11 @@ class GuppiRawSourceBlock(SourceBlock):
         first_chan_MHz = card['OBSFREQ'] - 0.5 * (nchan - 1) * chan_bw_MHz
         t0, tsamp = self._time_axis(card)
         self.blocsize = card['BLOCSIZE']
+        # one block = one frame of the tensor below: an explicit NTIME card that
+        # disagrees with BLOCSIZE would silently misalign every frame
+        if self.blocsize * 8 != nchan * ntime * card['NPOL'] * 2 * nbit:
+            raise ValueError("BLOCSIZE (%d) does not match OBSNCHAN x NTIME x NPOL x 2 x NBITS / 8 (%d)"
+                             % (self.blocsize, nchan * ntime * card['NPOL'] * 2 * nbit // 8))
         tensor = dict(dtype='ci%d' % nbit,
                       shape=[-1, nchan, ntime, card['NPOL']],
                       labels=['time', 'freq', 'fine_time', 'pol'],       # 'time' counts blocks
@@ -71,9 +77,11 @@ class GuppiRawSourceBlock(SourceBlock):
         for i in range(ospan.nframe):
             if not self.already_read_header:
                 try:
-                    guppi_raw.read_header(reader)
-                except IOError:
+                    card = guppi_raw.read_header(reader, self.stream_pos)
+                except guppi_raw.EndOfFile:
                     break                                   # clean EOF between blocks
+                # (a file that stops inside a header raises: it is corrupt, not finished)
+                self.stream_pos += card.nbyte
             self.already_read_header = False
             view = buf[i * self.blocsize:(i + 1) * self.blocsize]
             nbyte = reader.readinto(view)
@@ -81,6 +89,7 @@ class GuppiRawSourceBlock(SourceBlock):
                 break
             if nbyte < self.blocsize:
                 raise IOError("Block data is truncated")
+            self.stream_pos += nbyte
             nframe += 1
         return [nframe]
 

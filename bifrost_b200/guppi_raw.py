@@ -23,14 +23,28 @@ def _parse_value(text):
     return text[1:-1].rstrip()
 
 
-def read_header(f):
+class Header(dict):
+    """A parsed block header; `nbyte` = bytes consumed from the stream (cards + padding)."""
+    nbyte = 0
+
+
+class EndOfFile(IOError):
+    """Clean end of the file: no byte of another header follows."""
+
+
+def read_header(f, offset=None):
     """Reads one block header from the binary file object `f` (positioned at its
     first card) and leaves `f` at the first data byte.  Works on pipes: padding
-    is consumed with read(), never seek()."""
-    hdr = {}
+    is consumed with read(), never seek(); a caller reading a pipe passes the
+    absolute byte `offset` of the header so that DIRECTIO padding is computed
+    from the position in the stream.  Raises EndOfFile when nothing follows,
+    IOError when the file stops inside a header."""
+    hdr = Header()
     nread = 0
     while True:
         record = f.read(RECORD_LEN)
+        if len(record) == 0 and nread == 0:
+            raise EndOfFile("no further block")
         if len(record) < RECORD_LEN:
             raise IOError("EOF reached in middle of header")
         nread += RECORD_LEN
@@ -47,8 +61,11 @@ def read_header(f):
         try:
             pos = f.tell()
         except (IOError, OSError):
-            pos = nread
-        f.read(DIRECTIO_ALIGN_NBYTE - pos % DIRECTIO_ALIGN_NBYTE)
+            pos = (offset or 0) + nread
+        npad = DIRECTIO_ALIGN_NBYTE - pos % DIRECTIO_ALIGN_NBYTE
+        f.read(npad)
+        nread += npad
+    hdr.nbyte = nread
     if 'NPOL' in hdr:
         hdr['NPOL'] = 1 if hdr['NPOL'] == 1 else 2
     if 'NTIME' not in hdr:

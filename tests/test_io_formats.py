@@ -173,3 +173,23 @@ def test_sigproc_dispersion_trials_one_tim_per_dm(tmp_path):
         assert h['data_type'] == 2 and h['refdm'] == dm and h['nchans'] == 1 and h['nifs'] == 1
         assert h['fch1'] == 1400.0 and h['foff'] == 400.0 and h['tsamp'] == 256e-6
         np.testing.assert_array_equal(body, x[d, :, 0])
+
+
+def test_guppi_truncated_header_is_an_error_and_clean_eof_is_not(tmp_path):
+    """A file that stops between blocks ends the sequence; one that stops inside
+    a header is corrupt (the advisor's round-1 finding); NTIME must agree with
+    BLOCSIZE."""
+    import io
+    import pytest
+    from bifrost_b200 import guppi_raw
+    hdr = {'OBSNCHAN': 2, 'NPOL': 4, 'NBITS': 8, 'BLOCSIZE': 2 * 4 * 2 * 2, 'OBSBW': 2.0, 'OBSFREQ': 100.0}
+    f = io.BytesIO()
+    guppi_raw.write_header(hdr, f)
+    whole = f.getvalue()
+    h = guppi_raw.read_header(io.BytesIO(whole))
+    assert h.nbyte == len(whole) and h['NTIME'] == 4
+    with pytest.raises(guppi_raw.EndOfFile):
+        guppi_raw.read_header(io.BytesIO(b''))
+    with pytest.raises(IOError) as e:
+        guppi_raw.read_header(io.BytesIO(whole[:len(whole) - 100]))
+    assert not isinstance(e.value, guppi_raw.EndOfFile)
