@@ -938,11 +938,16 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 
 // Launches passes k0 .. k1-1 of the packed schedule (one kernel each).
 // `lists` (may be NULL): per pass a device list of the programs to run and
-// its length -- sharded execution.
+// its length -- sharded execution.  `range` (may be NULL): per pass the tiles
+// [first, first + count) to run -- chunked execution; `ring` (may be NULL): ring
+// lengths / offsets of the workspaces instead of the linear ones of `geom`.
 struct PackedProgList { const int* d = nullptr; int n = -1; };
+struct PackedTileRange { long first = 0, count = -1; };
+struct PackedRings { long ring[PK_MAXPASS]; size_t offset[PK_MAXPASS]; };
 static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istride, long ibatch, bool is_signed,
                                   void* outp, long ostride, long obatch, long ntime, long nbatch, char* ws,
-                                  std::vector<PackedGeom> const& geom, int k0, int k1, PackedProgList const* lists) {
+                                  std::vector<PackedGeom> const& geom, int k0, int k1, PackedProgList const* lists,
+                                  PackedTileRange const* range = nullptr, PackedRings const* ring = nullptr) {
 	cudaStream_t cst = plan->get_stream();
 	const int npass = (int)plan->packed.size();
 	for( int k=k0; k<k1; ++k ) {
@@ -950,22 +955,29 @@ static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istri
 		PackedParams q;
 		memset(&q, 0, sizeof(q));
 		if( k > 0 ) {
-			q.src = ws + geom[k-1].offset; q.sstride = geom[k-1].stride;
-			q.sbatch = (long)plan->packed[k-1].nrow_out * geom[k-1].stride; q.src_tb = geom[k-1].tb;
+			const long pitch = ring ? ring->ring[k-1] : geom[k-1].stride;
+			q.src = ws + (ring ? ring->offset[k-1] : geom[k-1].offset); q.sstride = pitch;
+			q.sbatch = (long)plan->packed[k-1].nrow_out * pitch; q.src_tb = geom[k-1].tb;
 		}
 		if( k == npass - 1 ) { q.dst = outp; q.dstride = ostride; q.dbatch = obatch; q.dst_tb = 0; }
 		else {
-			q.dst = ws + geom[k].offset; q.dstride = geom[k].stride;
-			q.dbatch = (long)cp.nrow_out * geom[k].stride; q.dst_tb = geom[k].tb;
+			const long pitch = ring ? ring->ring[k] : geom[k].stride;
+			q.dst = ws + (ring ? ring->offset[k] : geom[k].offset); q.dstride = pitch;
+			q.dbatch = (long)cp.nrow_out * pitch; q.dst_tb = geom[k].tb;
 		}
 		q.ops = cp.d_ops; q.srcs = cp.d_src; q.hdr = cp.d_hdr;
 		q.raw = raw; q.rstride = istride; q.rbatch = ibatch;
 		q.ntime = ntime; q.t_begin = geom[k].tb; q.ntile = geom[k].nt;
+		if( range ) {
+			if( range[k].count == 0 ) continue;
+			q.t_begin = geom[k].tb + range[k].first * cp.T; q.ntile = range[k].count;
+		}
 		q.T = cp.T; q.nlev = cp.nlev; q.slots = cp.slots; q.src_slots = cp.src_slots;
 		q.is_signed = is_signed;
 		q.prefetch = cp.prefetch ? 1 : 0; q.early = cp.early ? 1 : 0;
-		q.src_rl = k > 0 ? geom[k-1].stride : 1;           // linear workspaces: the rings never wrap
-		q.dst_rl = k == npass - 1 ? (1L << 62) : geom[k].stride;
+		// linear workspaces: the rings never wrap
+		q.src_rl = k > 0 ? (ring ? ring->ring[k-1] : geom[k-1].stride) : 1;
+		q.dst_rl = k == npass - 1 ? (1L << 62) : (ring ? ring->ring[k] : geom[k].stride);
 		q.plist = lists ? lists[k].d : nullptr;
 		BFstatus ls = launch_packed_pass(cp, q, nbatch, cst, lists ? lists[k].n : -1);
 		if( ls != BF_STATUS_SUCCESS ) return ls;
@@ -973,6 +985,64 @@ static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istri
 	return BF_STATUS_SUCCESS;
 }
 
+// Chunked execution (BFB_FDMT_PACKED_CHUNKED=C samples): the passes advance
+// together, C output samples at a time -- pass k runs the tiles the later
+// passes need for the chunk, then pass k+1, ... -- so that a pass reads what
+// the previous one has just written while it is still in L2, and the
+// workspaces between passes shrink to RINGS a little longer than a chunk
+// (their lines are overwritten in L2 before they are ever evicted to HBM).
+struct ChunkPlan {
+	long C = 0; int nchunk = 0;
+	std::vector<std::vector<long> > upto;     // [pass][chunk]: tiles done after the chunk
+	PackedRings rings;
+	size_t bytes = 0;
+};
+static void plan_chunks(std::vector<PackedPass> const& cps, std::vector<PackedGeom> const& geom, long C, long nbatch,
+                        ChunkPlan* cpn) {
+	const int n = (int)cps.size();
+	cpn->C = C;
+	cpn->nchunk = (int)div_up<long>(geom[n-1].te, C);
+	cpn->upto.assign(n, std::vector<long>(cpn->nchunk, 0));
+	for( int c=0; c<cpn->nchunk; ++c ) {
+		cpn->upto[n-1][c] = std::min<long>(geom[n-1].nt, div_up<long>((long)(c + 1) * C, cps[n-1].T));
+		if( c == cpn->nchunk - 1 ) cpn->upto[n-1][c] = geom[n-1].nt;
+		for( int k=n-2; k>=0; --k ) {
+			const long need_until = geom[k+1].tb + cpn->upto[k+1][c] * cps[k+1].T;     // (sources reach backwards only)
+			cpn->upto[k][c] = std::min<long>(geom[k].nt, std::max<long>(0, div_up<long>(need_until - geom[k].tb, cps[k].T)));
+			if( c == cpn->nchunk - 1 ) cpn->upto[k][c] = geom[k].nt;
+		}
+	}
+	// ring k (between pass k and k+1): what pass k writes during a chunk may only
+	// overwrite columns older than everything pass k+1 still stages for that chunk
+	size_t off = 0;
+	for( int k=0; k<n-1; ++k ) {
+		long span = 0;
+		for( int c=0; c<cpn->nchunk; ++c )
+			span = std::max(span, (cpn->upto[k+1][c] - (c ? cpn->upto[k+1][c-1] : 0)) * (long)cps[k+1].T);
+		const long width = geom[k].te - geom[k].tb;
+		cpn->rings.ring[k] = round_up<long>(std::min(width, span + 2L * cps[k].T + cps[k+1].lookback + 64), 64);
+		cpn->rings.offset[k] = off;
+		const size_t esz = (cps[k].dst_kind == PK_DST_CVT) ? 4 : cps[k].esize;
+		off += round_up<size_t>((size_t)nbatch * cps[k].nrow_out * cpn->rings.ring[k] * esz, 512);
+	}
+	cpn->bytes = std::max<size_t>(off, 512);
+}
+static BFstatus run_packed_chunked(BFfdmt_impl* plan, const void* raw, long istride, long ibatch, bool is_signed,
+                                   void* outp, long ostride, long obatch, long ntime, long nbatch, char* ws,
+                                   std::vector<PackedGeom> const& geom, ChunkPlan const& cpn) {
+	const int n = (int)plan->packed.size();
+	std::vector<PackedTileRange> range(n);
+	for( int c=0; c<cpn.nchunk; ++c ) {
+		for( int k=0; k<n; ++k ) {
+			range[k].first = c ? cpn.upto[k][c-1] : 0;
+			range[k].count = cpn.upto[k][c] - range[k].first;
+		}
+		BFstatus s = run_packed_passes(plan, raw, istride, ibatch, is_signed, outp, ostride, obatch, ntime, nbatch, ws,
+		                               geom, 0, n, nullptr, range.data(), &cpn.rings);
+		if( s != BF_STATUS_SUCCESS ) return s;
+	}
+	return BF_STATUS_SUCCESS;
+}
 
 // ---- persistent single-launch form -------------------------------------------
 static int mega_kind(PackedPass const& cp) {
@@ -1536,9 +1606,15 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 	std::vector<PackedGeom> geom;
 	MegaGeom mgeom;
 	const bool use_mega = use_packed && plan->mega_ok;
+	ChunkPlan chunks;
+	const long chunk_C = (use_packed && !use_mega) ? env_int("BFB_FDMT_PACKED_CHUNKED", 0) : 0;
 	if( use_packed ) {
 		BFB_TRY(need = packed_geometry(plan->packed, ntime, nbatch, &geom));
 		if( use_mega ) { BFB_TRY(need = mega_geometry(plan->packed, plan->mega_chunk, plan->mega_lag, geom, &mgeom)); }
+		else if( chunk_C > 0 && plan->packed.size() <= PK_MAXPASS ) {
+			BFB_TRY(plan_chunks(plan->packed, geom, std::max<long>(chunk_C, 256), nbatch, &chunks));
+			need = chunks.bytes;
+		}
 	}
 	if( exec_storage_size ) {
 		if( !exec_storage ) { *exec_storage_size = need; return BF_STATUS_SUCCESS; }
@@ -1636,6 +1712,9 @@ BFstatus bfFdmtExecute(BFfdmt plan, BFarray const* in, BFarray const* out,
 		BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
 		return BF_STATUS_SUCCESS;
 	}
+	if( use_packed && chunks.nchunk > 0 )
+		return run_packed_chunked(plan, in->data, istride, ibatch, in->dtype == BF_DTYPE_I8, out->data, ostride, obatch,
+		                          ntime, nbatch, (char*)exec_storage, geom, chunks);
 	if( use_packed )
 		return run_packed_passes(plan, in->data, istride, ibatch, in->dtype == BF_DTYPE_I8, out->data, ostride, obatch,
 		                         ntime, nbatch, (char*)exec_storage, geom, 0, (int)plan->packed.size(), nullptr);
