@@ -659,6 +659,7 @@ struct BFfft_impl {
 	// device twiddle tables, keyed by length (pairs of T)
 	std::map<long, void*> twid;          // n -> table of n pairs
 	std::map<long, void*> tw_lo, tw_hi;  // four-step N -> tables
+	std::map<long, void*> chirp, chirp_spec;   // Bluestein: n -> exp(-i pi j^2 / n) and the spectrum of its conjugate, length m
 	void*  own_ws = nullptr;
 	size_t own_ws_size = 0;
 	bool   planned = false;
@@ -667,6 +668,8 @@ struct BFfft_impl {
 		for( auto& kv : twid )  cudaFree(kv.second);
 		for( auto& kv : tw_lo ) cudaFree(kv.second);
 		for( auto& kv : tw_hi ) cudaFree(kv.second);
+		for( auto& kv : chirp ) cudaFree(kv.second);
+		for( auto& kv : chirp_spec ) cudaFree(kv.second);
 		if( own_ws ) cudaFree(own_ws);
 	}
 };
@@ -899,6 +902,168 @@ BFstatus run_pass(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 }
 
 // ---------------------------------------------------------------------------
+// Lengths that are neither one pass nor a power of two (the reference takes any
+// length through cuFFT): Bluestein's chirp-z form on the power-of-two kernels.
+// With w[j] = exp(-i pi j^2 / n),  X[k] = w[k] * sum_j (x[j] w[j]) conj(w[k - j]):
+// a circular convolution of length m = 2^ceil(log2(2n - 1)) done with three
+// transforms of length m (the spectrum of conj(w) is computed once per plan).
+// The chirp is tabulated in double with j^2 reduced modulo 2n, so its phase
+// error does not grow with n.  fftshift is an index rotation of the output
+// (forward) or the input (inverse); the inverse transform is conj(F(conj(x))).
+// ---------------------------------------------------------------------------
+template<typename T> struct Cplx2 { T x, y; };
+struct BluesteinParams {
+	int  ndim;
+	long shape[BF_MAX_DIMS];                 // batch shape, transform axis = 1
+	long sa[BF_MAX_DIMS];                    // byte strides of the user array over the batch dims
+	long ax;                                 // byte stride along the axis
+	long n, m, nline;
+	int  kind, conj, rot;                    // element kind, conjugate (inverse), index rotation
+	double scale;
+	char* user;                              // input (pre) or output (post)
+	void* work;                              // [nline][m] complex
+	const void* chirp;                       // [n] complex
+	const void* spec;                        // [m] complex (point-wise kernel)
+};
+__device__ __forceinline__ long blue_line_offset(const BluesteinParams& P, long line) {
+	long off = 0, rem = line;
+	for( int d=P.ndim-1; d>=0; --d ) { long q = rem / P.shape[d], r = rem - q * P.shape[d]; off += r * P.sa[d]; rem = q; }
+	return off;
+}
+template<typename T>
+__global__ void __launch_bounds__(256) bluestein_pre_kernel(BluesteinParams P) {
+	typedef Cplx2<T> C;
+	for( long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < P.nline * P.m; idx += (long)gridDim.x * blockDim.x ) {
+		const long line = idx / P.m, j = idx - line * P.m;
+		C v = { (T)0, (T)0 };
+		if( j < P.n ) {
+			long e = j + P.rot; if( e >= P.n ) e -= P.n;
+			const char* p = P.user + blue_line_offset(P, line) + e * P.ax;
+			T r, i = 0;
+			switch( P.kind ) {
+			case FK_CF32: { float2 q = *(const float2*)p; r = (T)q.x; i = (T)q.y; break; }
+			case FK_CF64: { double2 q = *(const double2*)p; r = (T)q.x; i = (T)q.y; break; }
+			case FK_CI8:  { char2 q = *(const char2*)p; r = (T)q.x; i = (T)q.y; break; }
+			case FK_CI16: { short2 q = *(const short2*)p; r = (T)q.x; i = (T)q.y; break; }
+			default:      { signed char b = *(const signed char*)p; r = (T)(signed char)(b & 0xF0); i = (T)(signed char)(b << 4); break; }
+			}
+			r *= (T)P.scale; i *= (T)P.scale;
+			if( P.conj ) i = -i;
+			const C w = ((const C*)P.chirp)[j];
+			v.x = r * w.x - i * w.y; v.y = r * w.y + i * w.x;
+		}
+		((C*)P.work)[idx] = v;
+	}
+}
+template<typename T>
+__global__ void __launch_bounds__(256) bluestein_mul_kernel(BluesteinParams P) {
+	typedef Cplx2<T> C;
+	for( long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < P.nline * P.m; idx += (long)gridDim.x * blockDim.x ) {
+		const C a = ((C*)P.work)[idx], b = ((const C*)P.spec)[idx % P.m];
+		C o = { a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x };
+		((C*)P.work)[idx] = o;
+	}
+}
+template<typename T>
+__global__ void __launch_bounds__(256) bluestein_post_kernel(BluesteinParams P) {
+	typedef Cplx2<T> C;
+	const T inv_m = (T)(1.0 / (double)P.m);
+	for( long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < P.nline * P.n; idx += (long)gridDim.x * blockDim.x ) {
+		const long line = idx / P.n, k = idx - line * P.n;
+		const C c = ((const C*)P.work)[line * P.m + k], w = ((const C*)P.chirp)[k];
+		C o = { (c.x * w.x - c.y * w.y) * inv_m, (c.x * w.y + c.y * w.x) * inv_m };
+		if( P.conj ) o.y = -o.y;
+		long e = k + P.rot; if( e >= P.n ) e -= P.n;
+		*(C*)(P.user + blue_line_offset(P, line) + e * P.ax) = o;
+	}
+}
+
+template<typename T>
+BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
+                  PassArray const& in, PassArray const& out, bool in_real, bool in_herm,
+                  bool out_real, long n_out, bool inverse, bool fftshift, void* tmp,
+                  cudaStream_t st);
+
+inline long bluestein_length(long n) { long m = 1; while( m < 2 * n - 1 ) m <<= 1; return m; }
+
+template<typename T>
+BFstatus run_axis_bluestein(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
+                            PassArray const& in, PassArray const& out, bool inverse, bool fftshift,
+                            void* tmp, cudaStream_t st) {
+	BFB_ASSERT(tmp, BF_STATUS_INSUFFICIENT_STORAGE);
+	const long m = bluestein_length(n), csize = 2 * sizeof(T);
+	const long key = n * 2 + (sizeof(T) == 8);
+	BluesteinParams P;
+	memset(&P, 0, sizeof(P));
+	P.ndim = ndim; P.n = n; P.m = m; P.nline = 1;
+	long wshape[BF_MAX_DIMS];
+	for( int d=0; d<ndim; ++d ) {
+		P.shape[d] = d == axis ? 1 : batch_shape[d];
+		wshape[d] = d == axis ? m : batch_shape[d];
+		P.nline *= P.shape[d];
+	}
+	// work array: [lines (C order over the batch dims)][m]
+	PassArray w;
+	w.data = tmp; w.kind = sizeof(T) == 8 ? FK_CF64 : FK_CF32;
+	{
+		long acc = m * csize;
+		for( int d=ndim-1; d>=0; --d ) { if( d == axis ) { w.strides[d] = csize; continue; } w.strides[d] = acc; acc *= batch_shape[d]; }
+	}
+	void* tmp2 = (char*)tmp + round_up<size_t>((size_t)P.nline * m * csize, 512);
+	// ---- tables (once per plan and length)
+	if( !plan->chirp.count(key) ) {
+		std::vector<T> hw(2 * (size_t)n), hb(2 * (size_t)m, (T)0);
+		const double pi = 3.14159265358979323846264338327950288;
+		for( long j=0; j<n; ++j ) {
+			const long q = (long)(((unsigned long long)j * (unsigned long long)j) % (unsigned long long)(2 * n));
+			const double ph = pi * (double)q / (double)n;
+			hw[2*j] = (T)cos(ph); hw[2*j+1] = (T)(-sin(ph));
+			hb[2*j] = (T)cos(ph); hb[2*j+1] = (T)sin(ph);                       // conj(w[j])
+			if( j ) { hb[2*(m-j)] = hb[2*j]; hb[2*(m-j)+1] = hb[2*j+1]; }
+		}
+		void *dw = nullptr, *db = nullptr;
+		BFB_CUDA(cudaMalloc(&dw, hw.size() * sizeof(T)), BF_STATUS_MEM_ALLOC_FAILED);
+		BFB_CUDA(cudaMalloc(&db, hb.size() * sizeof(T)), BF_STATUS_MEM_ALLOC_FAILED);
+		BFB_CUDA(cudaMemcpyAsync(dw, hw.data(), hw.size() * sizeof(T), cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
+		BFB_CUDA(cudaMemcpyAsync(db, hb.data(), hb.size() * sizeof(T), cudaMemcpyHostToDevice, st), BF_STATUS_MEM_OP_FAILED);
+		BFB_CUDA(cudaStreamSynchronize(st), BF_STATUS_DEVICE_ERROR);
+		plan->chirp[key] = dw; plan->chirp_spec[key] = db;
+		// spectrum of the conjugate chirp, in place (one line of length m)
+		long one[BF_MAX_DIMS] = {m};
+		PassArray b; b.data = db; b.kind = w.kind; b.strides[0] = csize;
+		BFstatus s = run_axis<T>(plan, 1, one, 0, m, b, b, false, false, false, m, false, false, tmp2, st);
+		if( s != BF_STATUS_SUCCESS ) return s;
+	}
+	P.chirp = plan->chirp[key]; P.spec = plan->chirp_spec[key];
+	P.work = tmp;
+	const unsigned grid = (unsigned)std::min<long>(div_up<long>(P.nline * m, 256), 148L * 32);
+	// ---- a[j] = x[j] w[j]  (inverse: conj(x); inverse + shift: ifftshift of the input)
+	P.user = (char*)in.data; P.ax = in.strides[axis]; P.kind = in.kind; P.conj = inverse ? 1 : 0;
+	P.scale = scale_of(in.kind);
+	P.rot = (fftshift && inverse) ? (int)(n / 2) : 0;
+	for( int d=0; d<ndim; ++d ) P.sa[d] = d == axis ? 0 : in.strides[d];
+	BFB_ASSERT(in.kind == FK_CF32 || in.kind == FK_CF64 || in.kind == FK_CI8 || in.kind == FK_CI16 || in.kind == FK_CI4,
+	           BF_STATUS_UNSUPPORTED_DTYPE);
+	bluestein_pre_kernel<T><<<grid, 256, 0, st>>>(P);
+	count_launch();
+	// ---- A = F_m(a); A *= B; c = F_m^-1(A) (unnormalised)
+	BFstatus s = run_axis<T>(plan, ndim, wshape, axis, m, w, w, false, false, false, m, false, false, tmp2, st);
+	if( s != BF_STATUS_SUCCESS ) return s;
+	bluestein_mul_kernel<T><<<grid, 256, 0, st>>>(P);
+	count_launch();
+	s = run_axis<T>(plan, ndim, wshape, axis, m, w, w, false, false, false, m, true, false, tmp2, st);
+	if( s != BF_STATUS_SUCCESS ) return s;
+	// ---- X[k] = w[k] c[k] / m  (forward + shift: fftshift of the output)
+	P.user = (char*)out.data; P.ax = out.strides[axis];
+	P.rot = (fftshift && !inverse) ? (int)(n / 2) : 0;
+	for( int d=0; d<ndim; ++d ) P.sa[d] = d == axis ? 0 : out.strides[d];
+	bluestein_post_kernel<T><<<grid, 256, 0, st>>>(P);
+	count_launch();
+	BFB_CUDA(cudaGetLastError(), BF_STATUS_INTERNAL_ERROR);
+	return BF_STATUS_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
 // Real transforms longer than one pass (n > FFT_NMAX_SMEM; the reference's own
 // tests run r2c / c2r at 2^24 points, test/test_fft.py:57,194-201): the even-
 // length real transform is ONE complex transform of half the length on the
@@ -919,7 +1084,6 @@ struct RealFixParams {
 	char* a; char* b;
 	long nline;
 };
-template<typename T> struct Cplx2 { T x, y; };
 __device__ __forceinline__ void real_fix_line(const RealFixParams& P, long line, long* oa, long* ob) {
 	long ra = 0, rb = 0, rem = line;
 	for( int d=P.ndim-1; d>=0; --d ) {
@@ -983,12 +1147,6 @@ __global__ void __launch_bounds__(256) fft_c2r_fix_kernel(RealFixParams P) {
 		*(C*)(P.b + ob + k * P.axb) = z;
 	}
 }
-
-template<typename T>
-BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
-                  PassArray const& in, PassArray const& out, bool in_real, bool in_herm,
-                  bool out_real, long n_out, bool inverse, bool fftshift, void* tmp,
-                  cudaStream_t st);
 
 template<typename T>
 BFstatus run_axis_real_long(BFfft_impl* plan, int ndim, const long* batch_shape, int axis, long n,
@@ -1063,8 +1221,9 @@ BFstatus run_axis(BFfft_impl* plan, int ndim, const long* batch_shape, int axis,
 	}
 	if( in_real || in_herm || out_real )
 		return run_axis_real_long<T>(plan, ndim, batch_shape, axis, n, in, out, in_real, tmp, st);
-	// ---- four-step: n = n1 * n2 (c2c, power of two only)
-	BFB_ASSERT(is_pow2(n), BF_STATUS_UNSUPPORTED_SHAPE);
+	if( !is_pow2(n) )
+		return run_axis_bluestein<T>(plan, ndim, batch_shape, axis, n, in, out, inverse, fftshift, tmp, st);
+	// ---- four-step: n = n1 * n2 (c2c, power of two)
 	BFB_ASSERT(tmp, BF_STATUS_INSUFFICIENT_STORAGE);
 	// n2 = 4096 when that leaves n1 >= 16 (n >= 65536); 16384 and 32768 split as 16 x n/16
 	long n2 = std::min<long>(4096, n / 16), n1 = n / n2;
@@ -1182,9 +1341,18 @@ BFstatus bfFftInit(BFfft plan, BFarray const* in, BFarray const* out, int rank,
 			// real transforms beyond one pass: one axis, even length (run_axis_real_long)
 			if( real ) BFB_ASSERT(rank == 1 && n % 2 == 0, BF_STATUS_UNSUPPORTED_SHAPE);
 			const long nc = real ? n / 2 : n;                         // length of the complex transform behind it
-			BFB_ASSERT(nc <= FFT_NMAX_SMEM || (is_pow2(nc) && nc / 4096 <= FFT_NMAX_SMEM), BF_STATUS_UNSUPPORTED_SHAPE);
 			size_t elems = 1;
 			for( int e=0; e<ndim; ++e ) elems *= std::max(in->shape[e], out->shape[e]);
+			if( nc > FFT_NMAX_SMEM && !is_pow2(nc) ) {
+				// Bluestein: a work array and a four-step buffer of the padded length
+				BFB_ASSERT(!real, BF_STATUS_UNSUPPORTED_SHAPE);
+				const long m = bluestein_length(nc);
+				BFB_ASSERT(m / 4096 <= FFT_NMAX_SMEM, BF_STATUS_UNSUPPORTED_SHAPE);
+				const size_t welems = elems / (size_t)nc * (size_t)m;
+				ws = std::max(ws, 2 * (round_up<size_t>(welems * csize, 512) + 512));
+				continue;
+			}
+			BFB_ASSERT(nc <= FFT_NMAX_SMEM || nc / 4096 <= FFT_NMAX_SMEM, BF_STATUS_UNSUPPORTED_SHAPE);
 			// c2r keeps Z and the four-step buffer side by side
 			ws = std::max(ws, (real ? 2 : 1) * (round_up<size_t>(elems * csize, 512) + 512));
 		}

@@ -72,6 +72,15 @@ def test_c2c_large_four_step(n):
         compare(got, want)
 
 
+@pytest.mark.parametrize("shape,axes", [((2, 10000), [1]), ((12345,), [0]), ((3, 20000), [1]), ((100000,), [0]),
+                                        ((9000, 6), [0]), ((4, 9000), [0, 1])])
+def test_c2c_long_lengths_that_are_not_powers_of_two(shape, axes):
+    """Bluestein on the power-of-two kernels (the reference takes any length
+    through cuFFT): forward / inverse, with and without fftshift, odd lengths,
+    a strided axis, and a 2-D transform with one such axis."""
+    c2c_case(shape, axes, np.random.default_rng(shape[-1]))
+
+
 @pytest.mark.parametrize("dtype,scale", [('ci8', 127), ('ci16', 32767), ('ci4', 7)])
 def test_integer_complex_inputs(dtype, scale):
     """GUPPI-chain input: ci8 [time, pol, freq, fine_time], FFT over fine_time
