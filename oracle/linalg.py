@@ -4,13 +4,15 @@ c[..., i, j] = alpha * sum_t conj(x[..., t, i]) * x[..., t, j] + beta * c   for 
 (everything above the diagonal untouched) -- the b^H.b form of bfLinAlgMatMul
 as used by CorrelateBlock (python/bifrost/blocks/correlate.py:79-103); formula
 of test/test_linalg.py:168-185 and test/test_pipeline.py:258-298.  Integer
-inputs are summed exactly (int64) before the float32 conversion."""
+inputs are summed exactly before the float32 conversion: the products are
+formed in float64 (BLAS), which holds every partial sum of 16-bit inputs over
+up to 2^21 samples without rounding (|sum| < 2^53)."""
 import numpy as np
 
 
 def _to_int_pair(x):
     if x.dtype.names:
-        return x['re'].astype(np.int64), x['im'].astype(np.int64)
+        return x['re'].astype(np.float64), x['im'].astype(np.float64)
     return None
 
 
