@@ -821,12 +821,31 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
             ms_fb = timed(lambda: sf.execute(x_loc, t_fb, gather_to=0), 2, 5)[0] / 5
             ms_fb_nogather = timed(lambda: sf.execute(x_loc, t_fb), 2, 5)[0] / 5
             lay = sf.layout(ntime)
+            wins = [(0, 2048), (70000 + 1, 2048), (ntime - 2048 - full['max_delay'], 2048 + full['max_delay'])]
             sf.execute(x_loc, t_fb, gather_to=0)
             torch.cuda.synchronize()
             fb_par = None
             if rank == 0:
-                fb_par = oracle_window_check(x_full, lambda a, n: t_fb[:, a:a + n].cpu().numpy(), full,
-                                             [(0, 2048), (70000 + 1, 2048), (ntime - 2048 - full['max_delay'], 2048 + full['max_delay'])])
+                fb_par = oracle_window_check(x_full, lambda a, n: t_fb[:, a:a + n].cpu().numpy(), full, wins)
+            # the same with phase 1 reading the peers' rows in place over NVLink (no exchange)
+            peer = None
+            try:
+                t_fb.zero_()
+                sf.execute(x_loc, t_fb, gather_to=0, peer=True)
+                torch.cuda.synchronize()
+                peer_ok = 1
+            except Exception as e:
+                peer_ok, peer_err = 0, str(e)
+            agree = torch.tensor([peer_ok], device='cuda')
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if int(agree.item()) == 1:
+                peer_par = oracle_window_check(x_full, lambda a, n: t_fb[:, a:a + n].cpu().numpy(), full, wins) if rank == 0 else None
+                ms_peer = timed(lambda: sf.execute(x_loc, t_fb, peer=True), 2, 5)[0] / 5
+                peer = dict(what='phase 1 stages every cut-step row by TMA straight from the HBM of the rank that produced it '
+                                 '(CUDA IPC mappings, NVLink peer access); NCCL carries two barriers per gulp, no data',
+                            ms_per_step_without_gather=ms_peer, parity=peer_par)
+            else:
+                peer = dict(available=False, note=peer_err if not peer_ok else 'another rank failed')
             blk = lay['row_start']
             fullband = dict(what='ONE full-band dispersion bank [max_delay, ntime] of the gulp, channels partitioned over the '
                                  'ranks: local steps -> NCCL broadcast of every rank\'s block of cut-step rows -> each rank\'s '
@@ -835,7 +854,7 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
                             value=NCHAN * NTIME_OUT / (ms_fb * 1e-3) / 1e6, unit='Msamples/s',
                             exchange_bytes_per_rank=int((blk[-1] - (blk[rank + 1] - blk[rank])) * lay['pitch']),
                             gather_bytes=int(sum(nd for _, nd, o in lay['blocks'] if o != 0) * ntime * 4),
-                            parity=fb_par)
+                            parity=fb_par, peer_access=peer)
             del t_fb, sf
         else:
             fullband = dict(available=False, note=shard_err if not shard_ok else 'another rank could not build the sharded plan')

@@ -944,10 +944,12 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 struct PackedProgList { const int* d = nullptr; int n = -1; };
 struct PackedTileRange { long first = 0, count = -1; };
 struct PackedRings { long ring[PK_MAXPASS]; size_t offset[PK_MAXPASS]; };
+struct PackedPeers { int n = 0; int row0[9]; const char* ws[8]; };      // last pass: split-step rows by owner
 static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istride, long ibatch, bool is_signed,
                                   void* outp, long ostride, long obatch, long ntime, long nbatch, char* ws,
                                   std::vector<PackedGeom> const& geom, int k0, int k1, PackedProgList const* lists,
-                                  PackedTileRange const* range = nullptr, PackedRings const* ring = nullptr) {
+                                  PackedTileRange const* range = nullptr, PackedRings const* ring = nullptr,
+                                  PackedPeers const* peers = nullptr) {
 	cudaStream_t cst = plan->get_stream();
 	const int npass = (int)plan->packed.size();
 	for( int k=k0; k<k1; ++k ) {
@@ -979,6 +981,11 @@ static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istri
 		q.src_rl = k > 0 ? (ring ? ring->ring[k-1] : geom[k-1].stride) : 1;
 		q.dst_rl = k == npass - 1 ? (1L << 62) : (ring ? ring->ring[k] : geom[k].stride);
 		q.plist = lists ? lists[k].d : nullptr;
+		if( peers && peers->n > 0 && k == npass - 1 && k > 0 ) {
+			q.npeer = peers->n;
+			for( int g=0; g<=peers->n; ++g ) q.peer_row0[g] = peers->row0[g];
+			for( int g=0; g<peers->n; ++g ) q.peer[g] = peers->ws[g] + geom[k-1].offset;
+		}
 		BFstatus ls = launch_packed_pass(cp, q, nbatch, cst, lists ? lists[k].n : -1);
 		if( ls != BF_STATUS_SUCCESS ) return ls;
 	}
@@ -1347,6 +1354,46 @@ BFstatus bfFdmtShardExecute(BFfdmt plan, int phase, BFarray const* in, BFarray c
 	const int k0 = phase == 0 ? 0 : npass - 1, k1 = phase == 0 ? npass - 1 : npass;
 	return run_packed_passes(plan, raw, istride, 0, in->dtype == BF_DTYPE_I8, out->data, ostride, 0,
 	                         ntime, 1, (char*)exec_storage, geom, k0, k1, lists.data());
+}
+
+// Phase 1 without an exchange: the rows of the split step are staged (TMA bulk
+// copies) straight from the workspace of the rank that produced them --
+// peer_storage[g] is rank g's exec_storage as mapped into THIS process (CUDA
+// IPC / peer access over NVLink; peer_storage[own rank] = exec_storage).  The
+// caller makes sure every rank has finished phase 0 before, and keeps its
+// workspace untouched until every rank has finished this call.
+BFstatus bfFdmtShardExecutePeers(BFfdmt plan, BFarray const* in, BFarray const* out,
+                                 void* exec_storage, BFsize* exec_storage_size,
+                                 void const* const* peer_storage, int npeer) {
+	BFB_ASSERT(plan, BF_STATUS_INVALID_HANDLE);
+	BFB_ASSERT(in && out && exec_storage && exec_storage_size && peer_storage, BF_STATUS_INVALID_POINTER);
+	BFB_ASSERT(plan->planned && plan->shard_nrank >= 2 && npeer == plan->shard_nrank, BF_STATUS_INVALID_STATE);
+	FdmtPlan const& P = plan->plan;
+	const int cpr = P.nchan / plan->shard_nrank;
+	BFB_ASSERT(in->ndim == 2 && out->ndim == 2, BF_STATUS_UNSUPPORTED_SHAPE);
+	BFB_ASSERT(in->shape[0] == cpr && out->shape[0] == P.max_delay && in->shape[1] == out->shape[1], BF_STATUS_INVALID_SHAPE);
+	BFB_ASSERT(out->dtype == BF_DTYPE_F32 && (in->dtype == BF_DTYPE_I8 || in->dtype == BF_DTYPE_U8), BF_STATUS_UNSUPPORTED_DTYPE);
+	const long ntime = in->shape[1];
+	std::vector<PackedGeom> geom;
+	size_t need = 0;
+	BFB_TRY(need = packed_geometry(plan->packed, ntime, 1, &geom));
+	BFB_ASSERT(*exec_storage_size >= need, BF_STATUS_INSUFFICIENT_STORAGE);
+	BFB_ASSERT(space_on_device(out->space), BF_STATUS_UNSUPPORTED_SPACE);
+	BFB_ASSERT(out->strides[1] == 4 && out->strides[0] > 0 && out->strides[0] % 4 == 0, BF_STATUS_UNSUPPORTED_STRIDE);
+	if( ntime == 0 ) return BF_STATUS_SUCCESS;
+	const int npass = (int)plan->packed.size();
+	PackedPass const& sp = plan->packed[plan->shard_split];
+	PackedPeers peers;
+	peers.n = npeer;
+	for( int g=0; g<=npeer; ++g ) {
+		const int r0 = g < npeer ? P.bands[plan->shard_step][g].row0 : P.nrow(plan->shard_step);
+		peers.row0[g] = (int)(std::lower_bound(sp.out_rows.begin(), sp.out_rows.end(), r0) - sp.out_rows.begin());
+	}
+	for( int g=0; g<npeer; ++g ) { BFB_ASSERT(peer_storage[g], BF_STATUS_INVALID_POINTER); peers.ws[g] = (const char*)peer_storage[g]; }
+	std::vector<PackedProgList> lists(npass);
+	for( int k=0; k<npass; ++k ) { lists[k].d = plan->d_shard_progs[k]; lists[k].n = (int)plan->shard_progs[k].size(); }
+	return run_packed_passes(plan, in->data, in->strides[0], 0, in->dtype == BF_DTYPE_I8, out->data, out->strides[0] / 4, 0,
+	                         ntime, 1, (char*)exec_storage, geom, npass - 1, npass, lists.data(), nullptr, nullptr, &peers);
 }
 
 // Layout of the exchange and of the output for a gulp of `ntime` samples:

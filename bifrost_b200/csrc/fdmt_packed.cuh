@@ -431,6 +431,11 @@ struct PackedParams {
 	int  early;                                      // else: request the next tile's rows before the last level
 	long src_rl, dst_rl;                             // ring lengths (columns) of the workspaces; >= width: linear
 	const int* plist;                                // programs to run (grid.y entries), NULL: all of them
+	// sharded execution over peer memory: source row r lives in the workspace of
+	// the rank g with peer_row0[g] <= r < peer_row0[g+1] (same layout everywhere)
+	int  npeer;
+	int  peer_row0[9];
+	const void* peer[8];
 };
 
 // Per (CTA, tile) values.
@@ -546,7 +551,14 @@ __device__ __forceinline__ void pk_stage_issue(const PackedSmem& S, const Packed
 		for( int k=lane; k<hdr.y; k+=32 ) {
 			const int4 e = S.ssrc[k];
 			const long c0 = (t0 + e.y - P.src_tb) % P.src_rl;
-			const unsigned char* g = src + (long)e.x * P.sstride * ESZ;
+			const unsigned char* base = src;
+			if( P.npeer ) {
+				// the row's owner: its HBM is read directly (NVLink peer access)
+				int g = 0;
+				while( g + 1 < P.npeer && e.x >= P.peer_row0[g + 1] ) ++g;
+				base = (const unsigned char*)P.peer[g] + soff * ESZ;
+			}
+			const unsigned char* g = base + (long)e.x * P.sstride * ESZ;
 			unsigned char* d = S.dbase + e.z + flip;
 			const long n1 = min((long)e.w, P.src_rl - c0);
 			bulk_g2s(d, g + c0 * ESZ, (uint32_t)n1 * ESZ, S.mbar);

@@ -56,6 +56,15 @@ class Fdmt(BifrostObject):
                                       workspace_ptr, ctypes.byref(size)))
         return odata
 
+    def shard_execute_peers(self, idata, odata, workspace_ptr, workspace_size, peer_ptrs):
+        """Phase 1 reading the split-step rows straight from every rank's
+        workspace (peer_ptrs[g] = rank g's workspace as mapped here)."""
+        size = _bf.BFsize(workspace_size)
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+        _check(_bf.bfFdmtShardExecutePeers(self.obj, asarray(idata).as_BFarray(), asarray(odata).as_BFarray(),
+                                           workspace_ptr, ctypes.byref(size), arr, len(peer_ptrs)))
+        return odata
+
     def shard_layout(self, ntime):
         """Exchange / output layout for a gulp of `ntime` samples: dict with the
         byte offset and pitch of the split-step rows in the workspace, every

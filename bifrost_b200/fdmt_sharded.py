@@ -17,6 +17,13 @@ at the step that has `world` sub-bands,
 and the rows written by the ranks are, together, bit for bit the output of
 bfFdmtExecute on one GPU.  One process per GPU; kernels and collectives are
 ordered on the calling thread's current torch stream.
+
+`execute(..., peer=True)` drops the exchange: the ranks map each other's
+workspaces (CUDA IPC, set up once) and phase 1 stages every cut-step row with
+a TMA bulk copy straight from the HBM of the GPU that produced it, over NVLink,
+tile by tile while the previous tile is being merged (bfFdmtShardExecutePeers).
+NCCL then only carries two barriers per gulp (phase 0 done everywhere / phase
+1 done everywhere) and the optional gather.
 """
 import numpy as np
 
@@ -35,6 +42,8 @@ class ShardedFdmt(object):
         self.plan = Fdmt()
         self._ws = None
         self._layout = {}
+        self._peer_ptrs = None
+        self._peer_keep = []
 
     def init(self, nchan, max_delay, f0, df, exponent=-2.0):
         """Same arguments on every rank: the FULL band."""
@@ -84,19 +93,48 @@ class ShardedFdmt(object):
     def _global_rank(self, g):
         return g if self.group is None else self._dist.get_global_rank(self.group, g)
 
-    def execute(self, x_local, out, gather_to=None):
+    def map_peers(self, ws):
+        """Maps every rank's workspace into this process (CUDA IPC through
+        torch's own storage sharing; peer access over NVLink is enabled when
+        the handle is opened).  Collective; once per workspace."""
+        import torch
+        dist = self._dist
+        handle = ws.untyped_storage()._share_cuda_()
+        offset = ws.storage_offset() * ws.element_size()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (handle, offset), group=self.group)
+        ptrs, keep = [], []
+        for g, (h, off) in enumerate(handles):
+            if g == self.rank:
+                ptrs.append(ws.data_ptr())
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(*h)
+            keep.append(st)
+            ptrs.append(st.data_ptr() + off)
+        self._peer_ptrs, self._peer_keep, self._peer_ws = ptrs, keep, ws
+        return ptrs
+
+    def execute(self, x_local, out, gather_to=None, peer=False):
         """x_local: torch int8/uint8 CUDA tensor [nchan/world, ntime] (this rank's
         channels); out: torch float32 CUDA tensor [max_delay, ntime].  After
         the call `out` holds this rank's delay blocks (see layout()['blocks']);
-        with gather_to=r rank r's `out` holds the whole bank."""
+        with gather_to=r rank r's `out` holds the whole bank.  peer=True: no
+        exchange, phase 1 reads the other ranks' rows in place over NVLink."""
         import torch
         _device.set_stream(torch.cuda.current_stream().cuda_stream)
         a_in, a_out = _ndarray(base=x_local), _ndarray(base=out)
         ntime = int(x_local.shape[-1])
         ws, need = self._workspace(a_in, a_out)
+        if peer and (self._peer_ptrs is None or self._peer_ws is not ws):
+            self.map_peers(ws)
         self.plan.shard_execute(0, a_in, a_out, ws.data_ptr(), need)
-        self.exchange(ws, ntime)
-        self.plan.shard_execute(1, a_in, a_out, ws.data_ptr(), need)
+        if peer:
+            self._dist.barrier(group=self.group)          # every rank's rows are in its HBM
+            self.plan.shard_execute_peers(a_in, a_out, ws.data_ptr(), need, self._peer_ptrs)
+            self._dist.barrier(group=self.group)          # nobody reads my workspace any more
+        else:
+            self.exchange(ws, ntime)
+            self.plan.shard_execute(1, a_in, a_out, ws.data_ptr(), need)
         if gather_to is not None:
             self.gather(out, ntime, gather_to)
         return out

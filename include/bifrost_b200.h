@@ -377,6 +377,14 @@ BFstatus bfMapCompile(int ndim, long const* shape, char const* const* axis_names
 BFstatus bfFdmtShardInit(BFfdmt plan, int rank, int nrank);
 BFstatus bfFdmtShardExecute(BFfdmt plan, int phase, BFarray const* in, BFarray const* out,
                             void* exec_storage, BFsize* exec_storage_size);
+/* Phase 1 without an exchange: the split-step rows are staged by TMA straight
+ * from the workspace of the rank that produced them.  peer_storage[g] = rank g's
+ * exec_storage as mapped into this process (CUDA IPC / NVLink peer access;
+ * the own rank's entry is exec_storage).  The caller orders it after every
+ * rank's phase 0 and keeps the workspaces untouched until every rank is done. */
+BFstatus bfFdmtShardExecutePeers(BFfdmt plan, BFarray const* in, BFarray const* out,
+                                 void* exec_storage, BFsize* exec_storage_size,
+                                 void const* const* peer_storage, int npeer);
 /* info: [0] byte offset of the split-step rows in the workspace, [1] row pitch
  * (bytes), [2] rows, [3] bytes per element, [4] nrank, [5] split step,
  * [6 .. 6+nrank] first row of each rank's block and the end; then n and n

@@ -95,6 +95,21 @@ def test_sharded_plans_assemble_the_full_band_bank(nchan, md, f0, df, ntime, nra
         written += mine
     assert (written == 1).all(), "the delay blocks of the ranks must tile the bank exactly once"
     assert same_bits(t_out.cpu().numpy(), gold)
+    # ---- the same without an exchange: every "rank" keeps its own workspace and
+    # phase 1 fetches each cut-step row from the workspace of its owner
+    # (bfFdmtShardExecutePeers; on several GPUs those are peer mappings)
+    wss = []
+    for g, p in enumerate(plans):
+        w = torch.empty((need,), dtype=torch.uint8, device='cuda')
+        w.fill_(0xFF)
+        p.shard_execute(0, subs[g], a_out, w.data_ptr(), need)
+        wss.append(w)
+    t_out.fill_(-999.0)
+    ptrs = [w.data_ptr() for w in wss]
+    for g, p in enumerate(plans):
+        p.shard_execute_peers(subs[g], a_out, wss[g].data_ptr(), need, ptrs)
+    torch.cuda.synchronize()
+    assert same_bits(t_out.cpu().numpy(), gold)
 
 
 @pytest.mark.gpu
