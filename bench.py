@@ -381,6 +381,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-chain', action='store_true')
     ap.add_argument('--no-fullband', action='store_true', help='N > 1: skip the cross-GPU full-band transform')
+    ap.add_argument('--fullband-peer', action='store_true',
+                    help='N > 1: also time the full-band transform with phase 1 reading peer memory (CUDA IPC)')
     ap.add_argument('--no-traffic', action='store_true')
     ap.add_argument('--no-gpu-reference', action='store_true')
     ap.add_argument('--dry-run', action='store_true')
@@ -829,16 +831,21 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
                 fb_par = oracle_window_check(x_full, lambda a, n: t_fb[:, a:a + n].cpu().numpy(), full, wins)
             # the same with phase 1 reading the peers' rows in place over NVLink (no exchange)
             peer = None
-            try:
+            if not args.fullband_peer:
+                peer_ok = -1
+            else:
+              try:
                 t_fb.zero_()
                 sf.execute(x_loc, t_fb, gather_to=0, peer=True)
                 torch.cuda.synchronize()
                 peer_ok = 1
-            except Exception as e:
+              except Exception as e:
                 peer_ok, peer_err = 0, str(e)
             agree = torch.tensor([peer_ok], device='cuda')
             dist.all_reduce(agree, op=dist.ReduceOp.MIN)
-            if int(agree.item()) == 1:
+            if int(agree.item()) == -1:
+                peer = dict(available=None, note='not requested (--fullband-peer); see profiles/r02_sharded_2gpu.txt')
+            elif int(agree.item()) == 1:
                 peer_par = oracle_window_check(x_full, lambda a, n: t_fb[:, a:a + n].cpu().numpy(), full, wins) if rank == 0 else None
                 ms_peer = timed(lambda: sf.execute(x_loc, t_fb, peer=True), 2, 5)[0] / 5
                 peer = dict(what='phase 1 stages every cut-step row by TMA straight from the HBM of the rank that produced it '

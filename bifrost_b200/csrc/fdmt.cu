@@ -944,7 +944,7 @@ static BFstatus launch_packed_pass(PackedPass const& cp, PackedParams const& q, 
 struct PackedProgList { const int* d = nullptr; int n = -1; };
 struct PackedTileRange { long first = 0, count = -1; };
 struct PackedRings { long ring[PK_MAXPASS]; size_t offset[PK_MAXPASS]; };
-struct PackedPeers { int n = 0; int row0[9]; const char* ws[8]; };      // last pass: split-step rows by owner
+struct PackedPeers { int n = 0, self = 0, ldg = 1; int row0[9]; const char* ws[8]; };      // last pass: split-step rows by owner
 static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istride, long ibatch, bool is_signed,
                                   void* outp, long ostride, long obatch, long ntime, long nbatch, char* ws,
                                   std::vector<PackedGeom> const& geom, int k0, int k1, PackedProgList const* lists,
@@ -982,7 +982,7 @@ static BFstatus run_packed_passes(BFfdmt_impl* plan, const void* raw, long istri
 		q.dst_rl = k == npass - 1 ? (1L << 62) : (ring ? ring->ring[k] : geom[k].stride);
 		q.plist = lists ? lists[k].d : nullptr;
 		if( peers && peers->n > 0 && k == npass - 1 && k > 0 ) {
-			q.npeer = peers->n;
+			q.npeer = peers->n; q.peer_self = peers->self; q.peer_ldg = peers->ldg;
 			for( int g=0; g<=peers->n; ++g ) q.peer_row0[g] = peers->row0[g];
 			for( int g=0; g<peers->n; ++g ) q.peer[g] = peers->ws[g] + geom[k-1].offset;
 		}
@@ -1384,7 +1384,9 @@ BFstatus bfFdmtShardExecutePeers(BFfdmt plan, BFarray const* in, BFarray const* 
 	const int npass = (int)plan->packed.size();
 	PackedPass const& sp = plan->packed[plan->shard_split];
 	PackedPeers peers;
-	peers.n = npeer;
+	peers.n = npeer; peers.self = plan->shard_rank;
+	// remote rows: plain 16-byte loads by default; BFB_FDMT_PEER_TMA=1 stages them with cp.async.bulk like the local ones
+	peers.ldg = env_int("BFB_FDMT_PEER_TMA", 0) ? 0 : 1;
 	for( int g=0; g<=npeer; ++g ) {
 		const int r0 = g < npeer ? P.bands[plan->shard_step][g].row0 : P.nrow(plan->shard_step);
 		peers.row0[g] = (int)(std::lower_bound(sp.out_rows.begin(), sp.out_rows.end(), r0) - sp.out_rows.begin());

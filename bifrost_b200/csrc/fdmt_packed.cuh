@@ -434,6 +434,8 @@ struct PackedParams {
 	// sharded execution over peer memory: source row r lives in the workspace of
 	// the rank g with peer_row0[g] <= r < peer_row0[g+1] (same layout everywhere)
 	int  npeer;
+	int  peer_self;                                  // this rank
+	int  peer_ldg;                                   // 1: remote rows by plain vector loads (all warps), 0: by TMA
 	int  peer_row0[9];
 	const void* peer[8];
 };
@@ -545,9 +547,21 @@ __device__ __forceinline__ void pk_stage_issue(const PackedSmem& S, const Packed
 				bulk_g2s(S.dbase + e.z, g - mis, (mis + e.w + 15) & ~15u, S.mbar);
 		}
 	} else {
-		if( lane == 0 ) mbar_expect_tx(S.mbar, (uint32_t)hdr.z);
-		__syncwarp();
 		const unsigned char* src = (const unsigned char*)P.src + soff * ESZ;
+		if( P.npeer && P.peer_ldg ) {
+			// rows of other ranks are fetched by pk_stage_finish: expect the local bytes only
+			uint32_t mine = 0;
+			for( int k=lane; k<hdr.y; k+=32 ) {
+				const int4 e = S.ssrc[k];
+				int g = 0;
+				while( g + 1 < P.npeer && e.x >= P.peer_row0[g + 1] ) ++g;
+				if( g == P.peer_self ) mine += (uint32_t)e.w * ESZ;
+			}
+#pragma unroll
+			for( int o=16; o>0; o>>=1 ) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+			if( lane == 0 ) mbar_expect_tx(S.mbar, mine);
+		} else if( lane == 0 ) mbar_expect_tx(S.mbar, (uint32_t)hdr.z);
+		__syncwarp();
 		for( int k=lane; k<hdr.y; k+=32 ) {
 			const int4 e = S.ssrc[k];
 			const long c0 = (t0 + e.y - P.src_tb) % P.src_rl;
@@ -556,6 +570,7 @@ __device__ __forceinline__ void pk_stage_issue(const PackedSmem& S, const Packed
 				// the row's owner: its HBM is read directly (NVLink peer access)
 				int g = 0;
 				while( g + 1 < P.npeer && e.x >= P.peer_row0[g + 1] ) ++g;
+				if( P.peer_ldg && g != P.peer_self ) continue;
 				base = (const unsigned char*)P.peer[g] + soff * ESZ;
 			}
 			const unsigned char* g = base + (long)e.x * P.sstride * ESZ;
@@ -568,7 +583,24 @@ __device__ __forceinline__ void pk_stage_issue(const PackedSmem& S, const Packed
 }
 template<int ESZ, int SRCK>
 __device__ __forceinline__ void pk_stage_finish(const PackedSmem& S, const PackedParams& P, long t0, long roff,
-                                                uint32_t& parity, int lane, int warp, int nwarp) {
+                                                uint32_t& parity, int lane, int warp, int nwarp,
+                                                long soff = 0, int flip = 0) {
+	if( SRCK == PK_SRC_SAME ) if( P.npeer && P.peer_ldg ) {
+		// rows owned by other ranks: 16-byte loads straight from their HBM (NVLink
+		// peer access; workspace rows and windows are 16-byte aligned, linear)
+		const int4 hdr = S.shdr[0];
+		for( int k=warp; k<hdr.y; k+=nwarp ) {
+			const int4 e = S.ssrc[k];
+			int g = 0;
+			while( g + 1 < P.npeer && e.x >= P.peer_row0[g + 1] ) ++g;
+			if( g == P.peer_self ) continue;
+			const long c0 = (t0 + e.y - P.src_tb) % P.src_rl;
+			const uint4* sp = (const uint4*)((const unsigned char*)P.peer[g] + (soff + (long)e.x * P.sstride + c0) * ESZ);
+			uint4* dp = (uint4*)(S.dbase + e.z + flip);
+			const int nv = e.w * ESZ / 16;
+			for( int j=lane; j<nv; j+=32 ) dp[j] = __ldcs(sp + j);
+		}
+	}
 	if( SRCK == PK_SRC_BYTES ) {
 		// rows at the ends of the gulp: every warp writes its share by hand
 		const int4 hdr = S.shdr[0];
@@ -913,7 +945,7 @@ __device__ __forceinline__ void pk_tiles(const PackedSmem& S, const PackedParams
 	for( long n=0; n<count; ++n ) {
 		const long t0 = P.t_begin + (first + n * stride) * P.T;
 		__syncthreads();                               // smis / staged rows of this tile were requested by warp 0
-		pk_stage_finish<ESZ, SRCK>(S, P, t0, roff, parity, lane, warp, nwarp);
+		pk_stage_finish<ESZ, SRCK>(S, P, t0, roff, parity, lane, warp, nwarp, soff, flip);
 		__syncthreads();
 		PackedTile tl;
 		tl.t0 = t0; tl.dcol = (t0 - P.dst_tb) % P.dst_rl; tl.doff = doff;

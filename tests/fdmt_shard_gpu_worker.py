@@ -20,6 +20,7 @@ from oracle import fdmt as ofdmt  # noqa: E402
 
 
 def main():
+    with_peer = '--peer' in sys.argv
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     bf.device.set_device(local)
@@ -57,26 +58,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # the same without an exchange: phase 1 reads the peers' rows in place (NVLink)
         out_p = torch.full((md, ntime), -999.0, dtype=torch.float32, device='cuda')
-        sf.execute(x_local, out_p, gather_to=0, peer=True)
-        torch.cuda.synchronize()
-        evp = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        dist.barrier()
-        torch.cuda.synchronize()
-        evp[0].record()
-        sf.execute(x_local, out_p, peer=True)
-        evp[1].record()
-        torch.cuda.synchronize()
-        tp = torch.tensor([evp[0].elapsed_time(evp[1])], device='cuda')
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        tp = torch.zeros(1, device='cuda')
+        if with_peer:
+            sf.execute(x_local, out_p, gather_to=0, peer=True)
+            torch.cuda.synchronize()
+            evp = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            dist.barrier()
+            torch.cuda.synchronize()
+            evp[0].record()
+            sf.execute(x_local, out_p, peer=True)
+            evp[1].record()
+            torch.cuda.synchronize()
+            tp = torch.tensor([evp[0].elapsed_time(evp[1])], device='cuda')
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
         if rank == 0:
             gold = np.full((md, ntime), -999.0, np.float32)
             ofdmt.fdmt(x, md, f0, df, out=gold)
             got = out.cpu().numpy()
             same = np.array_equal(got.view(np.uint32), gold.view(np.uint32))
-            same_peer = np.array_equal(out_p.cpu().numpy().view(np.uint32), gold.view(np.uint32))
+            same_peer = (not with_peer) or np.array_equal(out_p.cpu().numpy().view(np.uint32), gold.view(np.uint32))
             ok = ok and same and same_peer
             report.append(dict(nchan=nchan, max_delay=md, ntime=ntime, world=world, same_bits=bool(same),
-                               same_bits_peer_access=bool(same_peer), ms_whole_gulp_peer_access=float(tp[0]),
+                               same_bits_peer_access=bool(same_peer) if with_peer else None,
+                               peer_mode=('tma' if os.environ.get('BFB_FDMT_PEER_TMA') == '1' else 'ldg') if with_peer else None,
+                               ms_whole_gulp_peer_access=float(tp[0]) if with_peer else None,
                                exchange_bytes_received_per_rank=int(nbytes),
                                ms_phase0=float(t[0]), ms_exchange=float(t[1]), ms_phase1=float(t[2])))
     if rank == 0:

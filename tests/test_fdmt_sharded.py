@@ -104,12 +104,17 @@ def test_sharded_plans_assemble_the_full_band_bank(nchan, md, f0, df, ntime, nra
         w.fill_(0xFF)
         p.shard_execute(0, subs[g], a_out, w.data_ptr(), need)
         wss.append(w)
-    t_out.fill_(-999.0)
     ptrs = [w.data_ptr() for w in wss]
-    for g, p in enumerate(plans):
-        p.shard_execute_peers(subs[g], a_out, wss[g].data_ptr(), need, ptrs)
-    torch.cuda.synchronize()
-    assert same_bits(t_out.cpu().numpy(), gold)
+    for tma in ('0', '1'):                 # remote rows by plain loads (default) / by TMA like the local ones
+        os.environ['BFB_FDMT_PEER_TMA'] = tma
+        try:
+            t_out.fill_(-999.0)
+            for g, p in enumerate(plans):
+                p.shard_execute_peers(subs[g], a_out, wss[g].data_ptr(), need, ptrs)
+            torch.cuda.synchronize()
+        finally:
+            del os.environ['BFB_FDMT_PEER_TMA']
+        assert same_bits(t_out.cpu().numpy(), gold), tma
 
 
 @pytest.mark.gpu
