@@ -110,6 +110,30 @@ const char* bfGetSpaceString(BFspace space) {
 	}
 }
 
+// B200 extension: CUDA IPC for device allocations of bfMalloc (space 'cuda'), so
+// that cooperating processes -- one per GPU -- can map each other's buffers
+// (peer access over NVLink is enabled when the handle is opened).  The handle is
+// the 64-byte cudaIpcMemHandle_t; `ptr` must be the start of the allocation.
+BFstatus bfIpcGetHandle(void* ptr, void* handle64) {
+	BFB_ASSERT(ptr && handle64, BF_STATUS_INVALID_POINTER);
+	cudaIpcMemHandle_t h;
+	BFB_CUDA(cudaIpcGetMemHandle(&h, ptr), BF_STATUS_DEVICE_ERROR);
+	memcpy(handle64, &h, sizeof(h));
+	return BF_STATUS_SUCCESS;
+}
+BFstatus bfIpcOpenHandle(void const* handle64, void** ptr) {
+	BFB_ASSERT(ptr && handle64, BF_STATUS_INVALID_POINTER);
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	BFB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), BF_STATUS_DEVICE_ERROR);
+	return BF_STATUS_SUCCESS;
+}
+BFstatus bfIpcCloseHandle(void* ptr) {
+	BFB_ASSERT(ptr, BF_STATUS_INVALID_POINTER);
+	BFB_CUDA(cudaIpcCloseMemHandle(ptr), BF_STATUS_DEVICE_ERROR);
+	return BF_STATUS_SUCCESS;
+}
+
 BFstatus bfMalloc(void** ptr, BFsize size, BFspace space) {
 	BFB_ASSERT(ptr, BF_STATUS_INVALID_POINTER);
 	void* data = nullptr;

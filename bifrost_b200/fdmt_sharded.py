@@ -43,7 +43,7 @@ class ShardedFdmt(object):
         self._ws = None
         self._layout = {}
         self._peer_ptrs = None
-        self._peer_keep = []
+        self._peer_need = 0
 
     def init(self, nchan, max_delay, f0, df, exponent=-2.0):
         """Same arguments on every rank: the FULL band."""
@@ -93,25 +93,30 @@ class ShardedFdmt(object):
     def _global_rank(self, g):
         return g if self.group is None else self._dist.get_global_rank(self.group, g)
 
-    def map_peers(self, ws):
-        """Maps every rank's workspace into this process (CUDA IPC through
-        torch's own storage sharing; peer access over NVLink is enabled when
-        the handle is opened).  Collective; once per workspace."""
-        import torch
+    def map_peers(self, need):
+        """Allocates this rank's peer-visible workspace (bfMalloc, i.e. its own
+        cudaMalloc block) and maps every other rank's into this process (CUDA IPC;
+        peer access over NVLink is enabled when a handle is opened).
+        Collective; once per workspace size."""
+        import ctypes
+        from bifrost_b200.libbifrost import _bf, _check
+        from bifrost_b200.ndarray import empty
         dist = self._dist
-        handle = ws.untyped_storage()._share_cuda_()
-        offset = ws.storage_offset() * ws.element_size()
+        self._peer_buf = empty((need,), dtype='u8', space='cuda')           # keeps the allocation alive
+        mine = self._peer_buf.ctypes.data
+        h = ctypes.create_string_buffer(64)
+        _check(_bf.bfIpcGetHandle(mine, h))
         handles = [None] * self.world
-        dist.all_gather_object(handles, (handle, offset), group=self.group)
-        ptrs, keep = [], []
-        for g, (h, off) in enumerate(handles):
+        dist.all_gather_object(handles, bytes(h.raw), group=self.group)
+        ptrs = []
+        for g, hb in enumerate(handles):
             if g == self.rank:
-                ptrs.append(ws.data_ptr())
+                ptrs.append(mine)
                 continue
-            st = torch.UntypedStorage._new_shared_cuda(*h)
-            keep.append(st)
-            ptrs.append(st.data_ptr() + off)
-        self._peer_ptrs, self._peer_keep, self._peer_ws = ptrs, keep, ws
+            p = ctypes.c_void_p()
+            _check(_bf.bfIpcOpenHandle(ctypes.create_string_buffer(hb, 64), ctypes.byref(p)))
+            ptrs.append(p.value)
+        self._peer_ptrs, self._peer_need = ptrs, need
         return ptrs
 
     def execute(self, x_local, out, gather_to=None, peer=False):
@@ -124,15 +129,18 @@ class ShardedFdmt(object):
         _device.set_stream(torch.cuda.current_stream().cuda_stream)
         a_in, a_out = _ndarray(base=x_local), _ndarray(base=out)
         ntime = int(x_local.shape[-1])
-        ws, need = self._workspace(a_in, a_out)
-        if peer and (self._peer_ptrs is None or self._peer_ws is not ws):
-            self.map_peers(ws)
-        self.plan.shard_execute(0, a_in, a_out, ws.data_ptr(), need)
         if peer:
+            need = self.plan.shard_workspace_size(a_in, a_out)
+            if self._peer_ptrs is None or self._peer_need < need:
+                self.map_peers(need)
+            mine = self._peer_ptrs[self.rank]
+            self.plan.shard_execute(0, a_in, a_out, mine, need)
             self._dist.barrier(group=self.group)          # every rank's rows are in its HBM
-            self.plan.shard_execute_peers(a_in, a_out, ws.data_ptr(), need, self._peer_ptrs)
+            self.plan.shard_execute_peers(a_in, a_out, mine, need, self._peer_ptrs)
             self._dist.barrier(group=self.group)          # nobody reads my workspace any more
         else:
+            ws, need = self._workspace(a_in, a_out)
+            self.plan.shard_execute(0, a_in, a_out, ws.data_ptr(), need)
             self.exchange(ws, ntime)
             self.plan.shard_execute(1, a_in, a_out, ws.data_ptr(), need)
         if gather_to is not None:

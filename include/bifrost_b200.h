@@ -392,6 +392,13 @@ BFstatus bfFdmtShardExecutePeers(BFfdmt plan, BFarray const* in, BFarray const* 
  * *ninfo: capacity (longs) in, used out. */
 BFstatus bfFdmtShardQuery(BFfdmt plan, long ntime, long* info, int* ninfo);
 
+/* B200 extension: CUDA IPC for bfMalloc'ed device buffers (one process per GPU
+ * mapping each other's buffers; used by the sharded FDMT's peer-access phase).
+ * handle64: the 64 bytes of a cudaIpcMemHandle_t; ptr: start of the allocation. */
+BFstatus bfIpcGetHandle(void* ptr, void* handle64);
+BFstatus bfIpcOpenHandle(void const* handle64, void** ptr);
+BFstatus bfIpcCloseHandle(void* ptr);
+
 /* Number of kernels this library has launched since load (all threads). */
 BFstatus bfGetLaunchCount(unsigned long long* count);
 
