@@ -848,8 +848,9 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
             elif int(agree.item()) == 1:
                 peer_par = oracle_window_check(x_full, lambda a, n: t_fb[:, a:a + n].cpu().numpy(), full, wins) if rank == 0 else None
                 ms_peer = timed(lambda: sf.execute(x_loc, t_fb, peer=True), 2, 5)[0] / 5
-                peer = dict(what='phase 1 stages every cut-step row by TMA straight from the HBM of the rank that produced it '
-                                 '(CUDA IPC mappings, NVLink peer access); NCCL carries two barriers per gulp, no data',
+                peer = dict(what='phase 1 fetches every cut-step row straight from the HBM of the rank that produced it '
+                                 '(CUDA IPC mappings, NVLink peer access; ' + ('cp.async.bulk' if os.environ.get('BFB_FDMT_PEER_TMA') == '1' else '16-byte loads') +
+                                 '); NCCL carries two barriers per gulp, no data',
                             ms_per_step_without_gather=ms_peer, parity=peer_par)
             else:
                 peer = dict(available=False, note=peer_err if not peer_ok else 'another rank failed')

@@ -1385,10 +1385,11 @@ BFstatus bfFdmtShardExecutePeers(BFfdmt plan, BFarray const* in, BFarray const* 
 	PackedPass const& sp = plan->packed[plan->shard_split];
 	PackedPeers peers;
 	peers.n = npeer; peers.self = plan->shard_rank;
-	// remote rows are staged with cp.async.bulk like the local ones (the copy engine
-	// reads peer memory over NVLink while the previous tile is merged);
-	// BFB_FDMT_PEER_TMA=0 fetches them with plain 16-byte loads instead
-	peers.ldg = env_int("BFB_FDMT_PEER_TMA", 1) ? 0 : 1;
+	// remote rows: plain 16-byte loads by all warps (measured on 2 B200s, config 2's
+	// gulp: 0.84 ms per gulp); BFB_FDMT_PEER_TMA=1 stages them with cp.async.bulk
+	// like the local ones (works, 0.99 ms: a bulk copy over NVLink completes late
+	// and the tile waits for the slowest one)
+	peers.ldg = env_int("BFB_FDMT_PEER_TMA", 0) ? 0 : 1;
 	for( int g=0; g<=npeer; ++g ) {
 		const int r0 = g < npeer ? P.bands[plan->shard_step][g].row0 : P.nrow(plan->shard_step);
 		peers.row0[g] = (int)(std::lower_bound(sp.out_rows.begin(), sp.out_rows.end(), r0) - sp.out_rows.begin());

@@ -80,7 +80,7 @@ def main():
             ok = ok and same and same_peer
             report.append(dict(nchan=nchan, max_delay=md, ntime=ntime, world=world, same_bits=bool(same),
                                same_bits_peer_access=bool(same_peer) if with_peer else None,
-                               peer_mode=('ldg' if os.environ.get('BFB_FDMT_PEER_TMA') == '0' else 'tma') if with_peer else None,
+                               peer_mode=('tma' if os.environ.get('BFB_FDMT_PEER_TMA') == '1' else 'ldg') if with_peer else None,
                                ms_whole_gulp_peer_access=float(tp[0]) if with_peer else None,
                                exchange_bytes_received_per_rank=int(nbytes),
                                ms_phase0=float(t[0]), ms_exchange=float(t[1]), ms_phase1=float(t[2])))

@@ -105,7 +105,7 @@ def test_sharded_plans_assemble_the_full_band_bank(nchan, md, f0, df, ntime, nra
         p.shard_execute(0, subs[g], a_out, w.data_ptr(), need)
         wss.append(w)
     ptrs = [w.data_ptr() for w in wss]
-    for tma in ('1', '0'):                 # remote rows by TMA like the local ones (default) / by plain loads
+    for tma in ('0', '1'):                 # remote rows by plain loads (default) / by TMA like the local ones
         os.environ['BFB_FDMT_PEER_TMA'] = tma
         try:
             t_out.fill_(-999.0)
