@@ -105,6 +105,12 @@ class Pipeline(object):
             ring.set_abort_event(self._abort)
         for b in self.blocks:                  # readers exist before any writer starts
             b._readers = [r.open_reader(b) for r in b.irings]
+        # a block without gpu= works on the device that is current where run() is
+        # called (a new thread would otherwise start on device 0)
+        try:
+            self._default_gpu = int(device.get_device())
+        except Exception:
+            self._default_gpu = None            # no CUDA device: system-space pipelines
         threads = [threading.Thread(target=self._run_block, args=(b,), name=b.name, daemon=True) for b in self.blocks]
         for t in threads:
             t.start()
@@ -122,6 +128,8 @@ class Pipeline(object):
                     pass
             if block.gpu is not None:
                 device.set_device(block.gpu)
+            elif getattr(self, '_default_gpu', None) is not None:
+                device.set_device(self._default_gpu)
             block.main()
         except PipelineAborted:
             pass
