@@ -40,6 +40,7 @@ CASES = [
     (64, 50, 1200.0, -3.0, 1777, 4, np.int8),               # reversed band: rank 0 holds the LAST input channels
     (4096, 794, 1000.0, 400. / 4096, 2600, 8, np.int8),     # BASELINE config 2's plan, config 5's rank count
     (4096, 794, 1000.0, 400. / 4096, 2600, 2, np.int8),
+    (4096, 794, 1000.0, 400. / 4096, 2600, 4, np.int8),     # cut at step 10: passes (1-5)(6-9)(10)(11-12)
 ]
 
 
