@@ -1,0 +1,4 @@
+/* Source-compatibility forwarder: the reference's <bifrost/proclog.h>.
+ * All declarations live in the consolidated <bifrost_b200.h>. */
+#pragma once
+#include "../bifrost_b200.h"

@@ -399,6 +399,116 @@ BFstatus bfIpcGetHandle(void* ptr, void* handle64);
 BFstatus bfIpcOpenHandle(void const* handle64, void** ptr);
 BFstatus bfIpcCloseHandle(void* ptr);
 
+/* ------------------------------------------------------------------ *
+ * Rings                               (ref: src/bifrost/ring.h:60-227)
+ * Byte-addressed circular buffers between blocks, in any memory space, with
+ * a ghost region that makes every span contiguous (device-to-device ghost
+ * copies on the caller's stream for rings in CUDA space).  One writer stream
+ * of sequences (name, time tag, header) and spans; readers open sequences by
+ * name / time tag / earliest / latest, optionally *guaranteed* (the writer
+ * blocks instead of overwriting what they still hold).  Blocking calls
+ * return BF_STATUS_END_OF_DATA when the data they wait for can no longer
+ * come, non-blocking reservations BF_STATUS_WOULD_BLOCK.
+ * BFrsequence / BFwsequence handles are valid BFsequence handles, BFrspan /
+ * BFwspan handles valid BFspan handles.
+ * ------------------------------------------------------------------ */
+typedef struct BFring_impl*        BFring;
+typedef struct BFsequence_wrapper* BFsequence;
+typedef struct BFrsequence_impl*   BFrsequence;
+typedef struct BFwsequence_impl*   BFwsequence;
+typedef struct BFspan_impl*        BFspan;
+typedef struct BFrspan_impl*       BFrspan;
+typedef struct BFwspan_impl*       BFwspan;
+
+BFstatus bfRingCreate(BFring* ring, const char* name, BFspace space);
+BFstatus bfRingDestroy(BFring ring);
+/* grow-only: at least `contiguous_bytes` per span, `capacity_bytes` buffered
+ * (rounded up to a power of two), `nringlet` ringlets; contents are kept */
+BFstatus bfRingResize(BFring ring, BFsize contiguous_bytes, BFsize capacity_bytes, BFsize nringlet);
+BFstatus bfRingGetName(BFring ring, const char** name);
+BFstatus bfRingGetSpace(BFring ring, BFspace* space);
+/* later (re)allocations of a host-space ring come from the NUMA node of
+ * `core` (-1: no preference).  The reference needs hwloc for this. */
+BFstatus bfRingSetAffinity(BFring ring, int core);
+BFstatus bfRingGetAffinity(BFring ring, int* core);
+BFstatus bfRingLock(BFring ring);
+BFstatus bfRingUnlock(BFring ring);
+BFstatus bfRingLockedGetData(BFring ring, void** data);
+BFstatus bfRingLockedGetContiguousSpan(BFring ring, BFsize* val);
+BFstatus bfRingLockedGetTotalSpan(BFring ring, BFsize* val);
+BFstatus bfRingLockedGetNRinglet(BFring ring, BFsize* val);
+BFstatus bfRingLockedGetStride(BFring ring, BFsize* val);
+BFstatus bfRingBeginWriting(BFring ring);
+BFstatus bfRingEndWriting(BFring ring);
+BFstatus bfRingWritingEnded(BFring ring, BFbool* writing_ended);
+/* name: unique among the sequences in the ring, or ""; time_tag: unique, or
+ * BFoffset(-1) */
+BFstatus bfRingSequenceBegin(BFwsequence* sequence, BFring ring, const char* name,
+                             BFoffset time_tag, BFsize header_size, const void* header,
+                             BFsize nringlet, BFoffset offset_from_head);
+BFstatus bfRingSequenceEnd(BFwsequence sequence, BFoffset offset_from_head);
+BFstatus bfRingSequenceOpen(BFrsequence* sequence, BFring ring, const char* name, BFbool guarantee);
+BFstatus bfRingSequenceOpenAt(BFrsequence* sequence, BFring ring, BFoffset time_tag, BFbool guarantee);
+BFstatus bfRingSequenceOpenLatest(BFrsequence* sequence, BFring ring, BFbool guarantee);
+BFstatus bfRingSequenceOpenEarliest(BFrsequence* sequence, BFring ring, BFbool guarantee);
+BFstatus bfRingSequenceNext(BFrsequence sequence);
+BFstatus bfRingSequenceClose(BFrsequence sequence);
+BFstatus bfRingSequenceGetRing(BFsequence sequence, BFring* ring);
+BFstatus bfRingSequenceGetName(BFsequence sequence, const char** name);
+BFstatus bfRingSequenceGetTimeTag(BFsequence sequence, BFoffset* time_tag);
+BFstatus bfRingSequenceGetHeader(BFsequence sequence, const void** hdr);
+BFstatus bfRingSequenceGetHeaderSize(BFsequence sequence, BFsize* size);
+BFstatus bfRingSequenceGetNRinglet(BFsequence sequence, BFsize* nringlet);
+typedef struct BFsequence_info_ {
+	BFring      ring;
+	const char* name;
+	BFoffset    time_tag;
+	const void* header;
+	BFsize      header_size;
+	BFsize      nringlet;
+} BFsequence_info;
+BFstatus bfRingSequenceGetInfo(BFsequence sequence, BFsequence_info* sequence_info);
+BFstatus bfRingSpanReserve(BFwspan* span, BFring ring, BFsize size, BFbool nonblocking);
+BFstatus bfRingSpanCommit(BFwspan span, BFsize size);
+BFstatus bfRingSpanAcquire(BFrspan* span, BFrsequence sequence, BFoffset offset, BFsize size);
+BFstatus bfRingSpanRelease(BFrspan span);
+BFstatus bfRingSpanGetSizeOverwritten(BFrspan span, BFsize* val);
+BFstatus bfRingSpanGetRing(BFspan span, BFring* ring);
+BFstatus bfRingSpanGetData(BFspan span, void** data);
+BFstatus bfRingSpanGetSize(BFspan span, BFsize* val);
+BFstatus bfRingSpanGetStride(BFspan span, BFsize* val);
+BFstatus bfRingSpanGetOffset(BFspan span, BFsize* val);
+BFstatus bfRingSpanGetNRinglet(BFspan span, BFsize* val);
+typedef struct BFspan_info_ {
+	BFring      ring;
+	void*       data;
+	BFsize      size;
+	BFsize      stride;
+	BFsize      offset;
+	BFsize      nringlet;
+} BFspan_info;
+BFstatus bfRingSpanGetInfo(BFspan span, BFspan_info* span_info);
+
+/* ------------------------------------------------------------------ *
+ * Process log                        (ref: src/bifrost/proclog.h:41-48)
+ * One text file per log under BF_PROCLOG_DIR/<pid>/<name> ("block/quantity"),
+ * rewritten on every update, removed with the handle / the process.
+ * The directory can be moved with $BIFROST_B200_PROCLOG_DIR.
+ * ------------------------------------------------------------------ */
+#define BFB_PROCLOG_DIR "/dev/shm/bifrost"
+typedef struct BFproclog_impl* BFproclog;
+BFstatus bfProcLogCreate(BFproclog* log_ptr, const char* name);
+BFstatus bfProcLogDestroy(BFproclog log);
+BFstatus bfProcLogUpdate(BFproclog log, const char* str);
+
+/* ------------------------------------------------------------------ *
+ * Thread placement                  (ref: src/bifrost/affinity.h:41-46)
+ * core = -1 unbinds; GetCore gives -1 for a thread that may run on several.
+ * ------------------------------------------------------------------ */
+BFstatus bfAffinitySetCore(int core);
+BFstatus bfAffinityGetCore(int* core);
+BFstatus bfAffinitySetOpenMPCores(BFsize nthread, const int* thread_cores);
+
 /* Number of kernels this library has launched since load (all threads). */
 BFstatus bfGetLaunchCount(unsigned long long* count);
 

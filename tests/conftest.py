@@ -13,6 +13,11 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# bfProcLog* / ring status files of the test processes go to a scratch directory
+# (read by the library on first use; default /dev/shm/bifrost as in the reference)
+if 'BIFROST_B200_PROCLOG_DIR' not in os.environ:
+    import tempfile
+    os.environ['BIFROST_B200_PROCLOG_DIR'] = tempfile.mkdtemp(prefix='bfb_proclog_')
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
