@@ -21,6 +21,7 @@ from bifrost_b200.quantize import quantize
 from bifrost_b200.map import map, detect, accumulate, clear_map_cache
 from bifrost_b200.spectrometer import spectrometer
 from bifrost_b200 import views
+from bifrost_b200 import affinity, proclog
 from bifrost_b200 import blocks
 from bifrost_b200.pipeline import Pipeline, get_default_pipeline, block_scope, block_view
 

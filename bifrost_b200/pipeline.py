@@ -22,12 +22,14 @@ An exception in any block stops the pipeline and is re-raised by ``run()``.
 """
 import os
 import threading
+import time
 from copy import deepcopy
 
 import numpy as np
 
-from bifrost_b200 import device
+from bifrost_b200 import affinity, device
 from bifrost_b200.ndarray import memset_array
+from bifrost_b200.proclog import ProcLog
 from bifrost_b200.memory import space_accessible
 from bifrost_b200.ring import (Ring, ViewRing, Span, Sequence, PipelineAborted,      # noqa: F401
                                frame_axis as _frame_axis, slice_frames as _slice_frames)
@@ -121,11 +123,18 @@ class Pipeline(object):
 
     def _run_block(self, block):
         try:
-            if block.core is not None and hasattr(os, 'sched_setaffinity'):
+            if block.core is not None:
+                core = block.core if isinstance(block.core, int) else block.core[0]
                 try:
-                    os.sched_setaffinity(0, {int(block.core)})
-                except OSError:
+                    affinity.set_core(int(core))
+                except RuntimeError:            # a core this machine does not have
                     pass
+            # the status logs the reference's executor keeps per block (pipeline.py:346-364,445-451)
+            block._log('bind', {'ncore': 1, 'core0': affinity.get_core()})
+            block._log('in', dict([('nring', len(block.irings))] +
+                                  [(f'ring{i}', r.name) for i, r in enumerate(block.irings)]))
+            block._log('out', dict([('nring', len(block.orings))] +
+                                   [(f'ring{i}', r.name) for i, r in enumerate(block.orings)]))
             if block.gpu is not None:
                 device.set_device(block.gpu)
             elif getattr(self, '_default_gpu', None) is not None:
@@ -230,6 +239,18 @@ class Block(object):
             r.consumers.append(self)
         self.orings = []
         self._readers = []
+        self._proclogs = {}
+
+    def _log(self, kind, contents):
+        """Rewrites the block's status log `<name>/<kind>` (created on first use;
+        a log that cannot be written never stops the block)."""
+        try:
+            log = self._proclogs.get(kind)
+            if log is None:
+                log = self._proclogs[kind] = ProcLog(f"{self.name}/{kind}")
+            log.update(contents)
+        except Exception:                       # noqa: BLE001
+            pass
 
     def create_ring(self, space):
         ring = Ring(space, self)
@@ -272,10 +293,15 @@ class SourceBlock(Block):
                     self._seq_count += 1
                     st = ring.begin_sequence(ohdrs[0], self.gulp_nframe)
                     try:
+                        self._log('sequence0', ohdrs[0])
                         while True:
+                            t0 = time.time()
                             ospan = ring.reserve(st, self.gulp_nframe)
+                            t1 = time.time()
                             n = self.on_data(reader, [ospan])[0]
                             ring.commit(st, n)
+                            self._log('perf', {'acquire_time': -1, 'reserve_time': t1 - t0,
+                                               'process_time': time.time() - t1})
                             if n == 0 or n < ospan.nframe:
                                 break
                     finally:
@@ -306,12 +332,18 @@ class _ConsumerMixin(object):
                 reader.open(st, gulp, overlap)
                 try:
                     self._begin_outputs(iseq, gulp, overlap)
+                    self._log('sequence0', iseq.header)
                     offset = 0
                     while True:
+                        t0 = time.time()
                         ispan = reader.acquire(st, iseq, offset, gulp + overlap)
                         if ispan.nframe <= overlap:            # nothing new (or nothing at all)
                             break
+                        t1 = time.time()
+                        self._reserve_time = 0.
                         self._process(ispan, overlap)
+                        self._log('perf', {'acquire_time': t1 - t0, 'reserve_time': self._reserve_time,
+                                           'process_time': time.time() - t1 - self._reserve_time})
                         offset += gulp
                         reader.release(st, offset)
                         if ispan.nframe < gulp + overlap:      # ragged final gulp
@@ -366,7 +398,9 @@ class TransformBlock(_ConsumerMixin, Block):
         ring = self.orings[0]
         onframe = self.define_output_nframes(ispan.nframe)
         # a block that commits rarely (accumulate) is handed the same frames again
+        t0 = time.time()
         ospan = ring.reserve(self._ost, onframe)
+        self._reserve_time = time.time() - t0
         ncommit = self.on_data(ispan, ospan)
         if ncommit is None:
             ooverlap = self.define_output_nframes(overlap) if overlap else 0

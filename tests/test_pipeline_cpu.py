@@ -305,3 +305,35 @@ def test_fuse_scope_collapses_the_guppi_chain():
     p._fuse_chains()
     kinds = [type(b).__name__ for b in p.blocks]
     assert 'SpectrometerBlock' not in kinds and 'FftBlock' in kinds
+
+
+def test_blocks_keep_the_reference_status_logs():
+    """Every block writes <name>/bind, /in, /out, /sequence0 and /perf through
+    bfProcLog* (what the reference's pipeline.py:346-364,445-451,486,649 writes and
+    its like_top / like_bmon tools read); core= binds the block's thread."""
+    import os
+    from bifrost_b200 import proclog
+    data = np.arange(40 * 2, dtype=np.float32).reshape(40, 2)
+    out = Collect()
+    cores = sorted(os.sched_getaffinity(0))
+    seen = {}
+
+    def data_cb(ispan):
+        seen['core'] = bf.affinity.get_core()
+        seen['logs'] = proclog.load_by_pid(os.getpid(), include_rings=True)
+        out.data(ispan)
+
+    with Pipeline() as p:
+        src = array_source(data, header([-1, 2]), gulp_nframe=8, name='logsrc')
+        b = copy(src, gulp_nframe=8, name='logcopy')
+        callback_sink(b, out.seq, data_cb, gulp_nframe=8, name='logsink', core=cores[-1])
+        p.run()
+    np.testing.assert_array_equal(np.concatenate(out.chunks, axis=0), data)
+    assert seen['core'] == cores[-1]
+    logs = seen['logs']
+    assert logs['logsink']['bind'] == {'ncore': 1, 'core0': cores[-1]}
+    assert logs['logcopy']['in']['nring'] == 1 and logs['logcopy']['out']['nring'] == 1
+    assert logs['logcopy']['in']['ring0'] == logs['logsrc']['out']['ring0']
+    assert set(logs['logcopy']['perf']) == {'acquire_time', 'reserve_time', 'process_time'}
+    assert logs['logsrc']['perf']['acquire_time'] == -1
+    assert logs['logcopy']['sequence0']['name'] == 'test'
