@@ -110,7 +110,7 @@ class SigprocSinkBlock(SinkBlock):
 
         def refdm():
             if ihdr.get('refdm') is not None:
-                hdr['refdm'] = ihdr['refdm']           # already pc cm^-3 (the only unit used on this path)
+                hdr['refdm'] = convert_units(ihdr['refdm'], ihdr.get('refdm_units', 'pc cm^-3'), 'pc cm^-3')
 
         if ndim >= 3 and axnames[-3:] == ['time', 'pol', 'freq']:
             self.data_format = 'filterbank'
@@ -160,7 +160,7 @@ class SigprocSinkBlock(SinkBlock):
                 if axnames[-3] != 'dispersion':
                     raise ValueError("Expected first axis to be 'dispersion' got '%s'" % axnames[-3])
                 dm0, ddm = scales[-3]
-                dms = [dm0 + ddm * d for d in range(shape[-3])]
+                dms = [convert_units(dm0 + ddm * d, units[-3], 'pc cm^-3') for d in range(shape[-3])]
                 self.ofiles = [open(filename + '.%09.2f.tim' % dm, 'wb') for dm in dms]
                 for d, dm in enumerate(dms):
                     hdr['refdm'] = dm

@@ -46,6 +46,14 @@ def frame_axis(tensor):
     return tensor['shape'].index(-1)
 
 
+def _frame_nbit(tensor):
+    n = DataType(tensor['dtype']).itemsize_bits
+    for s in tensor['shape']:
+        if s != -1:
+            n *= s
+    return n
+
+
 def slice_frames(arr, axis, lo, hi):
     sl = [slice(None)] * arr.ndim
     sl[axis] = slice(lo, hi)
@@ -273,6 +281,7 @@ class Reader(object):
         self.who = who
         self.view = None
         self._next = 0
+        self._num, self._den = 1, 1      # frames of the ring per frame of this reader's view
 
     def sequences(self):
         """Yields (state, Sequence-as-this-reader-sees-it) until the writer stops."""
@@ -286,13 +295,30 @@ class Reader(object):
                 st = ring._seqs[self._next]
             self._next += 1
             hdr = deepcopy(st.seq.header)
+            self._num, self._den = 1, 1
             if self.view is not None:
                 hdr = self.view.transform_header(hdr)
+                # a view that splits or merges the frame axis (views.split_axis /
+                # merge_axes) changes what a frame is: this reader counts in its
+                # own frames, the ring in the writer's
+                mine, theirs = _frame_nbit(hdr['_tensor']), _frame_nbit(st.seq.tensor)
+                if mine != theirs:
+                    if mine % theirs and theirs % mine:
+                        raise ValueError("Header view changes the frame size by a non-integer factor")
+                    self._num, self._den = (mine // theirs, 1) if mine > theirs else (1, theirs // mine)
             yield st, Sequence(hdr, st.seq.index)
+
+    def _ring_frames(self, nframe, round_up=False):
+        """This reader's frame count in frames of the ring."""
+        n = nframe * self._num
+        if n % self._den and not round_up:
+            raise ValueError(f"{nframe} frames of the view are not a whole number of ring frames "
+                             f"(1 ring frame = {self._den} view frames): choose gulp_nframe accordingly")
+        return -(-n // self._den)
 
     def open(self, st, gulp, overlap):
         with self.ring._cond:
-            st.opened[self] = (max(1, int(gulp)), max(0, int(overlap)))
+            st.opened[self] = (max(1, self._ring_frames(int(gulp), True)), max(0, self._ring_frames(int(overlap), True)))
             st.tails[self] = 0
             self.ring._cond.notify_all()
 
@@ -300,23 +326,29 @@ class Reader(object):
         """Frames [frame_offset, frame_offset + nframe) -- fewer at the end of the
         sequence, none (nframe 0) once it is exhausted."""
         ring = self.ring
+        view_offset = frame_offset
+        frame_offset, nframe = self._ring_frames(frame_offset), self._ring_frames(nframe)
         with ring._cond:
             while st.head < frame_offset + nframe and not st.ended:
                 ring._wait()
             n = max(0, min(nframe, st.head - frame_offset))
             if st.storage is None:
                 n = 0
+            if self._num > 1:
+                n -= n % self._num                          # whole frames of the view only
         if n == 0:
             shape = list(seq.tensor['shape'])
             shape[frame_axis(seq.tensor)] = 0
-            return Span(seq, empty(shape, dtype=seq.tensor['dtype'], space='system'), frame_offset, frame_axis(seq.tensor))
+            return Span(seq, empty(shape, dtype=seq.tensor['dtype'], space='system'), view_offset, frame_axis(seq.tensor))
         b = frame_offset % st.cap
         data = slice_frames(st.storage, st.faxis, b, b + n)
+        frame_offset = view_offset
         if self.view is not None:
             data = self.view.reinterpret(seq, data)
         return Span(seq, data, frame_offset, frame_axis(seq.tensor))
 
     def release(self, st, upto_frame):
+        upto_frame = upto_frame * self._num // self._den
         with self.ring._cond:
             st.tails[self] = max(st.tails.get(self, 0), upto_frame)
             self.ring._cond.notify_all()

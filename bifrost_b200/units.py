@@ -1,5 +1,5 @@
 """Tiny unit converter for the quantities the hot-path blocks touch
-(frequency, time).  The reference uses `pint` (python/bifrost/units.py:28),
+(frequency, time, dispersion measure).  The reference uses `pint` (python/bifrost/units.py:28),
 which is not a dependency here."""
 _FACTORS = {
     'Hz': 1.0, 'kHz': 1e3, 'MHz': 1e6, 'GHz': 1e9, 'THz': 1e12,
@@ -8,6 +8,9 @@ _FACTORS = {
 }
 _KIND = {'Hz': 'f', 'kHz': 'f', 'MHz': 'f', 'GHz': 'f', 'THz': 'f', '1/s': 'f', 's^-1': 'f',
          's': 't', 'ms': 't', 'us': 't', 'ns': 't'}
+# dispersion measure (blocks/fdmt.py and the sigproc sink): the spellings pint accepts
+for _dm in ('pc cm^-3', 'pc cm**-3', 'pc/cm^3', 'pc/cm**3', 'pc / cm ** 3', 'parsec / centimeter ** 3'):
+    _FACTORS[_dm], _KIND[_dm] = 1.0, 'dm'
 _INV = {'s': 'Hz', 'ms': 'kHz', 'us': 'MHz', 'ns': 'GHz', 'Hz': 's', 'kHz': 'ms', 'MHz': 'us', 'GHz': 'ns'}
 
 

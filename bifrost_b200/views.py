@@ -98,10 +98,13 @@ def split_axis(block, axis, n, label=None):
         ax = _axis(t, axis)
         shape = t['shape']
         if shape[ax] == -1:
-            raise NotImplementedError("split_axis on the frame axis")
-        if shape[ax] % n:
-            raise ValueError(f"Split does not evenly divide axis ({shape[ax]} // {n})")
-        shape[ax] //= n
+            # n frames become one (basic_views.py:154-158 of the reference); the
+            # reader of this view counts in the new frames (ring.Reader)
+            hdr['gulp_nframe'] = (hdr.get('gulp_nframe', 1) - 1) // n + 1
+        else:
+            if shape[ax] % n:
+                raise ValueError(f"Split does not evenly divide axis ({shape[ax]} // {n})")
+            shape[ax] //= n
         shape.insert(ax + 1, n)
         if 'units' in t:
             t['units'].insert(ax + 1, t['units'][ax])
@@ -121,9 +124,12 @@ def merge_axes(block, axis1, axis2, label=None):
         if a2 != a1 + 1:
             raise ValueError("Merge axes must be adjacent")
         n = t['shape'][a2]
-        if n == -1 or t['shape'][a1] == -1:
-            raise NotImplementedError("merge_axes involving the frame axis")
-        t['shape'][a1] *= n
+        if n == -1:
+            raise ValueError("Second merge axis cannot be frame axis")
+        if t['shape'][a1] == -1:
+            hdr['gulp_nframe'] = hdr.get('gulp_nframe', 1) * n      # one frame becomes n
+        else:
+            t['shape'][a1] *= n
         del t['shape'][a2]
         if 'scales' in t and 'units' in t:
             s1, s2 = t['scales'][a1][1], t['scales'][a2][1]

@@ -337,3 +337,52 @@ def test_blocks_keep_the_reference_status_logs():
     assert set(logs['logcopy']['perf']) == {'acquire_time', 'reserve_time', 'process_time'}
     assert logs['logsrc']['perf']['acquire_time'] == -1
     assert logs['logcopy']['sequence0']['name'] == 'test'
+
+
+def test_views_that_split_or_merge_the_frame_axis():
+    """views.split_axis / merge_axes on the frame axis (basic_views.py:154-158,
+    191-193 of the reference): no data moves, the reader of the view counts in
+    the new frames and gulp_nframe is rescaled."""
+    data = np.arange(40 * 6, dtype=np.float32).reshape(40, 6)
+    out = Collect()
+    hdr = header([-1, 6])
+    hdr['gulp_nframe'] = 8
+    with Pipeline() as p:
+        src = array_source(data, hdr, gulp_nframe=8)
+        v = bf.views.split_axis(src, 'time', 4, label='fine')
+        callback_sink(v, out.seq, out.data)                    # gulp from the header: 8 -> 2 new frames
+        p.run()
+    t = out.headers[0]['_tensor']
+    assert t['shape'] == [-1, 4, 6] and t['labels'][:2] == ['time', 'fine']
+    assert t['scales'][0][1] == 4.0 and t['scales'][1] == [0, 1.0]
+    assert out.headers[0]['gulp_nframe'] == 2
+    assert all(c.shape == (2, 4, 6) for c in out.chunks)
+    np.testing.assert_array_equal(np.concatenate(out.chunks, axis=0), data.reshape(10, 4, 6))
+
+    # and back: [-1, 4, 6] frames of 4 fine samples -> 40 frames of one
+    hdr = header([-1, 4, 6], labels=['time', 'fine', 'chan'])
+    hdr['_tensor']['units'] = ['s', 's', None]
+    hdr['_tensor']['scales'] = [[0, 4.0], [0, 1.0], [0, 1.0]]
+    hdr['gulp_nframe'] = 3
+    out = Collect()
+    with Pipeline() as p:
+        src = array_source(data.reshape(10, 4, 6), hdr, gulp_nframe=3)
+        v = bf.views.merge_axes(src, 'time', 'fine')
+        callback_sink(v, out.seq, out.data)                    # gulp 3 -> 12 new frames
+        p.run()
+    t = out.headers[0]['_tensor']
+    assert t['shape'] == [-1, 6] and t['labels'] == ['time', 'chan'] and t['scales'][0] == [0, 1.0]
+    assert out.headers[0]['gulp_nframe'] == 12
+    assert [c.shape[0] for c in out.chunks] == [12, 12, 12, 4]
+    np.testing.assert_array_equal(np.concatenate(out.chunks, axis=0), data)
+
+    # a gulp of the view that is not a whole number of ring frames is refused
+    with Pipeline() as p:
+        src = array_source(data.reshape(10, 4, 6), hdr, gulp_nframe=3)
+        v = bf.views.merge_axes(src, 'time', 'fine')
+        callback_sink(v, out.seq, out.data, gulp_nframe=6)
+        try:
+            p.run()
+            raise AssertionError('expected a ValueError')
+        except ValueError as e:
+            assert 'whole number of ring frames' in str(e)
