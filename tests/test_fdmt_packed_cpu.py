@@ -440,3 +440,24 @@ def test_persistent_schedule_is_deadlock_free_and_exact(nchan, md, f0, df, ntime
     if len(passes) > 1:
         assert any(mg['per'][k]['ring'] < geometry(passes, ntime)[k]['te'] - geometry(passes, ntime)[k]['tb']
                    for k in range(len(passes) - 1))
+
+
+@pytest.mark.parametrize("nrank", [2, 4, 8])
+def test_packed_tables_of_the_config5_subband_plans(nrank):
+    """The per-GPU plans `bench.py --gpus N` builds for BASELINE config 5
+    (nchan/N channels, f0_g, max_delay_g): every one of them takes the integer
+    schedule and its tables reproduce the oracle."""
+    import bench
+    for g in range(nrank):
+        sb = bench.subband(g, nrank)
+        nchan, md, f0, df = sb['nchan'], sb['max_delay'], sb['f0'], sb['df']
+        passes = query(nchan, md, f0, df)
+        assert passes, (nrank, g)
+        ntime = md + 700
+        rng = np.random.default_rng(100 * nrank + g)
+        x = rng.integers(-128, 128, size=(nchan, ntime)).astype(np.int8)
+        gold = np.zeros((md, ntime), np.float32)
+        ofdmt.fdmt(x, md, f0, df, out=gold)
+        got = np.zeros((md, ntime), np.float32)
+        run_schedule(x, passes, got)
+        assert np.array_equal(got.view(np.uint32), gold.view(np.uint32)), (nrank, g)
