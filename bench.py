@@ -44,8 +44,10 @@ sys.path.insert(0, ROOT)
 
 NCHAN = 4096
 NTIME_OUT = 131072
-# bounded CPU sample: 1/4 of the gulp's time span, all 4096 channels (env override: tests only)
-CPU_SAMPLE_NTIME = int(os.environ.get('BENCH_CPU_SAMPLE_NTIME', 32768))
+# bounded CPU sample, all 4096 channels: the whole gulp where the host has the cores to finish it
+# in well under a second (the B200 boxes: 128), else 1/4 of its time span (env override: tests only)
+CPU_SAMPLE_NTIME = int(os.environ.get('BENCH_CPU_SAMPLE_NTIME',
+                                      NTIME_OUT if (os.cpu_count() or 1) >= 64 else NTIME_OUT // 4))
 F0_MHZ = 1000.0
 BW_MHZ = 400.0
 DT_S = 256e-6
@@ -76,6 +78,29 @@ def subband(g, n):
     f0 = w['f0'] + g * nc * w['df']
     md = max_delay_for(f0, w['df'], nc, DT_S, MAX_DM)
     return dict(nchan=nc, chan0=g * nc, ntime=w['ntime'], max_delay=md, f0=f0, df=w['df'])
+
+
+def bench_config(world):
+    """The `config` object of the JSON line -- the same for the GPU arm and for
+    `--impl reference` (the driver compares them)."""
+    full = workload(0)
+    md = full['max_delay']
+    if world == 1:
+        return dict(workload='BASELINE config 2: bfFdmtExecute, max_dm=100 '
+                             f'(max_delay={md}) on {NCHAN}-chan x {NTIME_OUT}(+{md})-sample '
+                             'int8 filterbank; f0=1000 MHz, bw=400 MHz, dt=256 us',
+                    sharding='single GPU',
+                    l2='input 540 MB + output 419 MB per step exceed the 126 MB L2')
+    subs = [subband(g, world) for g in range(world)]
+    nc = subs[0]['nchan']
+    return dict(workload=f'BASELINE config 5: the one {NCHAN}-chan x {NTIME_OUT}(+{md})-sample int8 '
+                         f'gulp of config 2 split into {world} sub-bands of {nc} channels',
+                sharding=f'NCCL grouped send/recv scatter of the sub-bands from rank 0 -> per-GPU '
+                         f'bfFdmtInit({nc}, max_delay_g, f0_g, df) + bfFdmtExecute -> NCCL grouped '
+                         'send/recv gather of the [max_delay_g, ntime] f32 banks to rank 0',
+                subband_max_delay=[s['max_delay'] for s in subs],
+                subband_f0_mhz=[s['f0'] for s in subs],
+                l2='per-GPU inputs and banks exceed L2 for N <= 4; the collectives stream through HBM')
 
 
 def make_input(w, seed, ntime=None):
@@ -182,6 +207,7 @@ def bind_to_gpu_numa_node(index):
             cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
         if cpus:
+            _ORIGINAL_AFFINITY.append(os.sched_getaffinity(0))
             os.sched_setaffinity(0, cpus)
             return dict(numa_node=node, cpus=len(cpus))
     except Exception:
@@ -189,36 +215,56 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+_ORIGINAL_AFFINITY = []      # what bind_to_gpu_numa_node narrowed (the CPU baseline leg widens it again)
+
+
 # --------------------------------------------------------------------------- CPU arm
-def cpu_fdmt_sample(w, ntime_sample, threads=None):
-    """Times the oracle (CPU restatement of the reference algorithm) on a
-    bounded sample: the full 4096 channels, `ntime_sample` time samples.
-    Returns (Msamples/s, kind, cores, seconds)."""
-    try:
-        from oracle import fdmt_c
-        have_c = fdmt_c.available()
-    except Exception:
-        have_c = False
-    if not have_c:
-        ntime_sample = min(ntime_sample, 8192)        # the numpy port is ~10x slower
-    x = make_input(w, 4321, ntime=ntime_sample + w['max_delay'])
-    nsamp = w['nchan'] * ntime_sample
-    if have_c:
-        from oracle import fdmt_c
-        cores = threads or os.cpu_count()
-        plan = fdmt_c.Plan(w['nchan'], w['max_delay'], w['f0'], w['df'])
-        out = np.zeros((w['max_delay'], x.shape[1]), np.float32)
-        plan.execute(x, out, threads=cores)            # warm (page-in, thread pool)
+class CpuFdmt(object):
+    """The oracle (CPU restatement of the reference algorithm) on a bounded
+    sample: the full 4096 channels, `ntime_sample` time samples.  Input and
+    plan are built once; run() times one transform."""
+
+    def __init__(self, w, ntime_sample, threads=None):
+        try:
+            from oracle import fdmt_c
+            self.have_c = fdmt_c.available()
+        except Exception:
+            self.have_c = False
+        if not self.have_c:
+            ntime_sample = min(ntime_sample, 8192)        # the numpy port is ~10x slower
+        self.w, self.ntime_sample = w, ntime_sample
+        self.x = make_input(w, 4321, ntime=ntime_sample + w['max_delay'])
+        self.nsamp = w['nchan'] * ntime_sample
+        self.kind = 'port'
+        if self.have_c:
+            self.cores = threads or len(os.sched_getaffinity(0))
+            self.plan = fdmt_c.Plan(w['nchan'], w['max_delay'], w['f0'], w['df'])
+            self.out = np.zeros((w['max_delay'], self.x.shape[1]), np.float32)
+            self.plan.execute(self.x, self.out, threads=self.cores)       # warm (page-in, thread pool)
+        else:
+            from oracle import fdmt as ofdmt
+            self.cores = 1
+            self.plan = ofdmt.FdmtPlan(w['nchan'], w['max_delay'], w['f0'], w['df'])
+
+    def run(self):
+        """Seconds of one transform of the sample."""
         t0 = time.perf_counter()
-        plan.execute(x, out, threads=cores)
-        dt = time.perf_counter() - t0
-        return nsamp / dt / 1e6, 'port', cores, dt
-    from oracle import fdmt as ofdmt
-    plan = ofdmt.FdmtPlan(w['nchan'], w['max_delay'], w['f0'], w['df'])
-    t0 = time.perf_counter()
-    ofdmt.fdmt(x, w['max_delay'], w['f0'], w['df'], plan=plan)
-    dt = time.perf_counter() - t0
-    return nsamp / dt / 1e6, 'port', 1, dt
+        if self.have_c:
+            self.plan.execute(self.x, self.out, threads=self.cores)
+        else:
+            from oracle import fdmt as ofdmt
+            ofdmt.fdmt(self.x, self.w['max_delay'], self.w['f0'], self.w['df'], plan=self.plan)
+        return time.perf_counter() - t0
+
+    def msamples_per_s(self, dt):
+        return self.nsamp / dt / 1e6
+
+
+def cpu_fdmt_sample(w, ntime_sample, threads=None):
+    """One timed transform: (Msamples/s, kind, cores, seconds)."""
+    c = CpuFdmt(w, ntime_sample, threads)
+    dt = c.run()
+    return c.msamples_per_s(dt), c.kind, c.cores, dt
 
 
 def run_reference_arm(args, rank, world):
@@ -229,13 +275,13 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     w = workload(0)
-    ntime_sample = CPU_SAMPLE_NTIME
+    cpu = CpuFdmt(w, CPU_SAMPLE_NTIME)
+    ntime_sample, cores = cpu.ntime_sample, cpu.cores
     vals, secs = [], []
-    cores = 1
     for i in range(args.warmup + args.steps):
-        v, kind, cores, dt = cpu_fdmt_sample(w, ntime_sample)
+        dt = cpu.run()
         if i >= args.warmup:
-            vals.append(v)
+            vals.append(cpu.msamples_per_s(dt))
             secs.append(dt)
     value = float(np.mean(vals))
     sample = (f"oracle CPU FDMT (oracle/fdmt_c.c, pthreads) on {w['nchan']} chan x {ntime_sample} samples "
@@ -244,9 +290,9 @@ def run_reference_arm(args, rank, world):
                 steps=args.steps, warmup=args.warmup, ms_per_step=float(np.mean(secs) * 1e3),
                 higher_is_better=True, scaling='strong' if args.gpus > 1 else 'weak', vs_baseline=None,
                 dtype='f32', data='synthetic',
-                config=dict(workload='BASELINE config 2: FDMT max_dm=100 on 4096-chan x 128k-sample '
-                                     'int8 filterbank (bounded sample, see cpu_baseline.sample); the same one '
-                                     'gulp at every N (the GPU arm scales strongly), CPU threads do not grow with N'),
+                # the GPU arm's config; what the CPU ran of it per step is cpu_baseline.sample
+                # (the same one gulp at every N: the GPU arm scales strongly, CPU threads do not grow with N)
+                config=bench_config(max(1, args.gpus)),
                 cpu_baseline=dict(value=value, unit='Msamples/s', cores=cores, kind='port',
                                   sample=sample),
                 e2e=dict(value=value, unit='Msamples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -284,6 +330,7 @@ def run_dry(args, rank, world):
             dist.isend(mine, 0).wait()
     if rank == 0:
         print(json.dumps(dict(dry_run=True, n_gpus=world, ms_per_step=ms, scaling='strong' if world > 1 else 'weak',
+                              config=bench_config(world),
                               value=NCHAN * NTIME_OUT / (ms * 1e-3) / 1e6,
                               subband_f0_mhz=[s['f0'] for s in subs], subband_nchan=[s['nchan'] for s in subs],
                               subband_max_delay=[s['max_delay'] for s in subs], bank_offsets=[int(o) for o in offs],
@@ -617,6 +664,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
+        if _ORIGINAL_AFFINITY:                       # the CPU leg gets every host core back
+            os.sched_setaffinity(0, _ORIGINAL_AFFINITY[0])
         v, kind, cores, dt = cpu_fdmt_sample(w, CPU_SAMPLE_NTIME)
         cpu = dict(value=v, unit='Msamples/s', cores=cores, kind=kind,
                    sample=f"oracle CPU FDMT: {nchan} chan x {CPU_SAMPLE_NTIME} samples "
@@ -627,12 +676,7 @@ def main():
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='u16/f32 (exact integers; bit-identical to the reference\'s f32)',
                 data='synthetic',
-                config=dict(workload='BASELINE config 2: bfFdmtExecute, max_dm=100 '
-                                     f'(max_delay={md}) on {nchan}-chan x {NTIME_OUT}(+{md})-sample '
-                                     'int8 filterbank; f0=1000 MHz, bw=400 MHz, dt=256 us',
-                            sharding='single GPU',
-                            l2='input 540 MB + output 419 MB per step exceed the 126 MB L2',
-                            host_numa=numa),
+                config=bench_config(1), host_numa=numa,
                 roofline=roofline, cpu_baseline=cpu, gpu_reference=gpu_reference, parity=parity,
                 e2e=dict(value=e2e_value, unit='Msamples/s', ms_per_step=ms_e2e,
                          ms_per_step_serial=ms_e2e_serial, ms_per_step_pipelined=ms_pipe,
@@ -887,14 +931,7 @@ def run_multi(args, rank, local_rank, world, bf, Fdmt, torch, dist, stream, time
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
                 scaling='strong', vs_baseline=None,
                 dtype='u16/f32 (exact integers; bit-identical to the reference\'s f32)', data='synthetic',
-                config=dict(workload=f'BASELINE config 5: the one {NCHAN}-chan x {NTIME_OUT}(+{full["max_delay"]})-sample int8 '
-                                     f'gulp of config 2 split into {world} sub-bands of {nc} channels',
-                            sharding=f'NCCL grouped send/recv scatter of the sub-bands from rank 0 -> per-GPU '
-                                     f'bfFdmtInit({nc}, max_delay_g, f0_g, df) + bfFdmtExecute -> NCCL grouped '
-                                     'send/recv gather of the [max_delay_g, ntime] f32 banks to rank 0',
-                            subband_max_delay=[s['max_delay'] for s in subs],
-                            subband_f0_mhz=[s['f0'] for s in subs], host_numa=numa,
-                            l2='per-GPU inputs and banks exceed L2 for N <= 4; the collectives stream through HBM'),
+                config=bench_config(world), host_numa=numa,
                 comm=dict(collective='ncclSend/ncclRecv groups (torch.distributed.batch_isend_irecv)',
                           nvlink_bytes_per_step=int(nvlink_scatter + nvlink_gather),
                           scatter_bytes=int(nvlink_scatter), gather_bytes=int(nvlink_gather),

@@ -83,6 +83,7 @@ def test_dry_run_single():
                          capture_output=True, text=True, timeout=300, check=True)
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['n_gpus'] == 1 and line['ms_per_step'] == 1.0
+    assert line['config'] == bench.bench_config(1) and 'config 2' in line['config']['workload']
 
 
 def test_dry_run_world_size_2_gloo():
@@ -95,6 +96,8 @@ def test_dry_run_world_size_2_gloo():
     assert len(lines) == 1                       # rank 0 alone prints
     line = json.loads(lines[0])
     assert line['n_gpus'] == 2 and line['scaling'] == 'strong'
+    assert line['config'] == bench.bench_config(2) and 'config 5' in line['config']['workload']
+    assert line['config']['subband_max_delay'] == line['subband_max_delay']
     assert line['ms_per_step'] == 1.5            # max over ranks, not mean / rank 0
     assert line['subband_f0_mhz'] == [1000.0, 1200.0] and line['subband_nchan'] == [2048, 2048]
     # one gulp whatever N is: the value is that gulp's samples over the slowest rank's time
@@ -114,6 +117,8 @@ def test_reference_arm_line(monkeypatch):
                          capture_output=True, text=True, timeout=600, env=env, check=True)
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['unit'] == 'Msamples/s'
+    assert line['config'] == bench.bench_config(1)          # the GPU arm's config, verbatim
+    assert line['metric'] == bench.METRIC and line['higher_is_better'] is True
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['value'] == line['value']
     assert line['value'] > 0
