@@ -46,8 +46,20 @@ NCHAN = 4096
 NTIME_OUT = 131072
 # bounded CPU sample, all 4096 channels: the whole gulp where the host has the cores to finish it
 # in well under a second (the B200 boxes: 128), else 1/4 of its time span (env override: tests only)
+def _mem_available_gb():
+    try:
+        for line in open('/proc/meminfo'):
+            if line.startswith('MemAvailable:'):
+                return int(line.split()[1]) / 2 ** 20
+    except Exception:
+        pass
+    return 0.
+
+
+# (the step-by-step oracle keeps two buffers of 8192 rows: 8.7 GB for the whole gulp)
 CPU_SAMPLE_NTIME = int(os.environ.get('BENCH_CPU_SAMPLE_NTIME',
-                                      NTIME_OUT if (os.cpu_count() or 1) >= 64 else NTIME_OUT // 4))
+                                      NTIME_OUT if ((os.cpu_count() or 1) >= 64 and _mem_available_gb() >= 48)
+                                      else NTIME_OUT // 4))
 F0_MHZ = 1000.0
 BW_MHZ = 400.0
 DT_S = 256e-6
