@@ -60,6 +60,38 @@ def test_c2c_nd_reference_shapes():
     c2c_case((33, 31, 65, 16), [0, 2], rng)
 
 
+@pytest.mark.parametrize("shape,axes_list", [
+    ((16777216,), [[0]]),                                                     # shape1D
+    ((2048, 2048), [[0], [1], [0, 1]]),                                       # shape2D
+    ((128, 128, 128), [[0], [1], [2], [0, 1], [0, 2], [1, 2], [0, 1, 2]]),    # shape3D
+    ((32, 32, 32, 32), [[0, 1], [0, 3], [1, 2], [2, 3], [0, 1, 2], [0, 2, 3], [1, 2, 3]]),   # shape4D
+])
+def test_c2c_at_the_reference_sizes(shape, axes_list):
+    """The shapes test/test_fft.py:57-66 itself runs (its 1-D case is 2^24
+    points), forward and inverse + fftshift."""
+    rng = np.random.default_rng(len(shape))
+    x = rng.normal(size=shape + (2,)).astype(np.float32).view(np.complex64)[..., 0]
+    xd = x.astype(np.complex128)
+    for axes in axes_list:
+        for inverse, shift in ((False, False), (True, True)):
+            got = run(x, shape, 'cf32', axes, inverse, shift)
+            compare(got, offt.fft(xd, axes, inverse=inverse, fftshift=shift))
+
+
+def test_r2c_and_c2r_at_the_reference_sizes():
+    """test/test_fft.py:193-204: real transforms of shape2D and shape3D."""
+    rng = np.random.default_rng(6)
+    for shape, axes in (((2048, 2048), [0, 1]), ((128, 128, 128), [0, 1, 2])):
+        x = rng.normal(size=shape).astype(np.float32)
+        oshape = list(shape)
+        oshape[-1] = shape[-1] // 2 + 1
+        gold = np.fft.rfftn(x.astype(np.float64), axes=axes)
+        compare(run(x, oshape, 'cf32', axes), gold)
+        spec = gold.astype(np.complex64)
+        back = run(spec, shape, 'f32', axes)
+        compare(back, np.fft.irfftn(spec.astype(np.complex128), s=list(shape), axes=axes) * np.prod(shape))
+
+
 @pytest.mark.parametrize("n", [1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 20])
 def test_c2c_large_four_step(n):
     """Lengths above the single-pass limit (8192): n = n1 * n2 with n2 = min(4096, n/16);
