@@ -1,0 +1,41 @@
+"""Race detection for the native ring: csrc/ring.cpp is compiled with
+-fsanitize=thread together with host-only stand-ins for the runtime calls it
+makes (tests/cabi/runtime_host_stub.cpp) and stressed by
+tests/cabi/ring_stress.cpp -- a writer with short commits, two guaranteed
+readers, an unguaranteed one, a thread that keeps growing the ring while spans
+are in flight and one that polls the locked getters; every byte read is
+checked.  The run must finish without a ThreadSanitizer report."""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope='module')
+def stress_binary(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp('tsan') / 'ring_stress_tsan')
+    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fsanitize=thread',
+           '-I' + os.path.join(ROOT, 'include'), '-I' + os.path.join(ROOT, 'bifrost_b200', 'csrc'),
+           '-I/usr/local/cuda/include',
+           os.path.join(ROOT, 'bifrost_b200', 'csrc', 'ring.cpp'),
+           os.path.join(HERE, 'cabi', 'runtime_host_stub.cpp'),
+           os.path.join(HERE, 'cabi', 'ring_stress.cpp'), '-o', exe, '-lpthread']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        if 'tsan' in res.stderr or 'sanitize' in res.stderr:
+            pytest.skip('this toolchain has no ThreadSanitizer runtime')
+        raise AssertionError(res.stderr[-3000:])
+    return exe
+
+
+@pytest.mark.timeout(300)
+def test_ring_is_race_free_under_thread_sanitizer(stress_binary, tmp_path):
+    env = dict(os.environ, BIFROST_B200_PROCLOG_DIR=str(tmp_path / 'proclog'),
+               TSAN_OPTIONS='halt_on_error=0 exitcode=66')
+    res = subprocess.run([stress_binary], capture_output=True, text=True, timeout=280, env=env)
+    assert 'ThreadSanitizer' not in res.stderr, res.stderr[-4000:]
+    assert res.returncode == 0, (res.returncode, res.stderr[-2000:])
+    assert res.stdout.startswith('OK ')
