@@ -216,6 +216,9 @@ def _sync(*spaces):
         device.stream_synchronize()
 
 
+PERF_LOG_PERIOD = 0.05
+
+
 class Block(object):
     instance_counts = {}
 
@@ -240,14 +243,23 @@ class Block(object):
         self.orings = []
         self._readers = []
         self._proclogs = {}
+        self._perf_logged = 0.
 
     def _log(self, kind, contents):
         """Rewrites the block's status log `<name>/<kind>` (created on first use;
-        a log that cannot be written never stops the block)."""
+        a log that cannot be written never stops the block).  The per-gulp
+        'perf' log is rewritten at most every PERF_LOG_PERIOD seconds: gulps
+        take well under a millisecond here, the tools that read the logs poll
+        about once a second."""
         try:
             log = self._proclogs.get(kind)
             if log is None:
                 log = self._proclogs[kind] = ProcLog(f"{self.name}/{kind}")
+            elif kind == 'perf':
+                now = time.time()
+                if now - self._perf_logged < PERF_LOG_PERIOD:
+                    return
+                self._perf_logged = now
             log.update(contents)
         except Exception:                       # noqa: BLE001
             pass
