@@ -18,7 +18,14 @@ As in the reference (pipeline.py:249-261, 558-650):
   * ``define_input_overlap_nframe`` re-presents the tail of each gulp to the
     next one (blocks/fdmt.py:112-115); ``on_data`` may return the number of
     frames to commit (blocks/accumulate.py:63-74).
-An exception in any block stops the pipeline and is re-raised by ``run()``.
+An exception in any block stops the pipeline and is re-raised by ``run()``;
+``shutdown()`` / ``shutdown_on_signals()`` stop it from outside.
+
+Not carried over: unguaranteed readers (``guarantee=False`` on a block,
+pipeline.py:518-537,590-643 of the reference -- a reader the writer may lap,
+with ``on_skip`` zero-filling what was lost).  The keyword is accepted and the
+reader is guaranteed: a slow block holds its producer back instead of losing
+data.  (The C rings, csrc/ring.cpp, do implement both kinds.)
 """
 import os
 import threading
@@ -204,9 +211,26 @@ class Pipeline(object):
                 self.blocks.remove(b)
 
     def shutdown(self):
+        """Stops every block at its next ring call; run() then returns."""
         self._abort.set()
         for ring in self._rings():
             ring.wake()
+
+    def shutdown_on_signals(self, signals=None):
+        """Installs handlers that shut the pipeline down (pipeline.py:271-286 of
+        the reference; default SIGHUP, SIGINT, SIGQUIT, SIGTERM, SIGTSTP).  Call
+        from the main thread, before run()."""
+        import signal
+        import warnings
+        if signals is None:
+            signals = [signal.SIGHUP, signal.SIGINT, signal.SIGQUIT, signal.SIGTERM, signal.SIGTSTP]
+
+        def handler(signum, frame):
+            warnings.warn(f"Received signal {signum} {signal.Signals(signum).name}, shutting down pipeline",
+                          RuntimeWarning)
+            self.shutdown()
+        for sig in signals:
+            signal.signal(sig, handler)
 
 
 def _sync(*spaces):

@@ -175,6 +175,7 @@ class Ring(object):
     def reserve(self, st, nframe):
         """A writable span of `nframe` frames following the committed ones."""
         with self._cond:
+            self._check_abort()                               # Pipeline.shutdown() stops writers that never wait
             while len(st.opened) < len(self._readers):       # every reader has seen the header
                 self._wait()
             if st.storage is None:

@@ -386,3 +386,44 @@ def test_views_that_split_or_merge_the_frame_axis():
             raise AssertionError('expected a ValueError')
         except ValueError as e:
             assert 'whole number of ring frames' in str(e)
+
+
+def test_a_signal_shuts_a_running_pipeline_down():
+    """Pipeline.shutdown_on_signals (pipeline.py:271-286 of the reference): an
+    endless source and its consumers stop at their next ring call and run()
+    returns."""
+    import os
+    import signal
+    import threading
+    import time
+    import warnings
+    from bifrost_b200.blocks.testing import NumpySourceBlock
+
+    class Endless(NumpySourceBlock):
+        def on_data(self, reader, ospans):
+            reader.pos = 0                                   # never runs out
+            return super(Endless, self).on_data(reader, ospans)
+
+    seen = [0]
+
+    def count(ispan):
+        seen[0] += ispan.nframe
+
+    data = np.arange(8 * 2, dtype=np.float32).reshape(8, 2)
+    old = signal.getsignal(signal.SIGUSR1)
+    try:
+        with Pipeline() as p:
+            src = Endless(data, header([-1, 2]), 4)
+            b = copy(src, gulp_nframe=4)
+            callback_sink(b, None, count, gulp_nframe=4)
+            p.shutdown_on_signals([signal.SIGUSR1])
+            threading.Timer(0.3, os.kill, (os.getpid(), signal.SIGUSR1)).start()
+            t0 = time.time()
+            with warnings.catch_warnings(record=True) as caught:
+                warnings.simplefilter('always')
+                p.run()
+        assert time.time() - t0 < 20
+        assert seen[0] > 0
+        assert any('shutting down pipeline' in str(w.message) for w in caught)
+    finally:
+        signal.signal(signal.SIGUSR1, old)
