@@ -21,11 +21,13 @@ As in the reference (pipeline.py:249-261, 558-650):
 An exception in any block stops the pipeline and is re-raised by ``run()``;
 ``shutdown()`` / ``shutdown_on_signals()`` stop it from outside.
 
-Not carried over: unguaranteed readers (``guarantee=False`` on a block,
-pipeline.py:518-537,590-643 of the reference -- a reader the writer may lap,
-with ``on_skip`` zero-filling what was lost).  The keyword is accepted and the
-reader is guaranteed: a slow block holds its producer back instead of losing
-data.  (The C rings, csrc/ring.cpp, do implement both kinds.)
+``guarantee=False`` on a block (pipeline.py:518-537,590-643 of the reference)
+makes its reader one the writer may lap: a gulp any frame of which was
+overwritten -- before it was acquired or while ``on_data`` worked on it -- is
+dropped as a whole, ``on_skip`` fills the corresponding output frames (zeros
+by default) so the output keeps its cadence, and one more gulp is dropped
+after an overwrite so that the block can catch up.  (Coarser than the
+reference, which hands out the surviving part of a span.)
 """
 import os
 import threading
@@ -259,6 +261,7 @@ class Block(object):
         self.core = scope.get('core')
         self.gpu = scope.get('gpu')
         self.fuse = scope.get('fuse', False)
+        self.guarantee = scope.get('guarantee', True)
         self.pipeline = get_default_pipeline()
         self.pipeline.blocks.append(self)
         self.irings = [r.orings[0] if hasattr(r, 'orings') else r for r in irings]
@@ -365,24 +368,35 @@ class _ConsumerMixin(object):
                 self._check_space()
                 overlap = self._open_sequence(iseq)
                 gulp = self._gulp(iseq)
+                self._ist = st
                 reader.open(st, gulp, overlap)
                 try:
                     self._begin_outputs(iseq, gulp, overlap)
                     self._log('sequence0', iseq.header)
                     offset = 0
+                    force_skip = False
                     while True:
                         t0 = time.time()
                         ispan = reader.acquire(st, iseq, offset, gulp + overlap)
-                        if ispan.nframe <= overlap:            # nothing new (or nothing at all)
+                        # (an unguaranteed reader that was lapped gets an empty span
+                        # and the number of frames it lost)
+                        nframe = ispan.nframe + ispan.nframe_skipped
+                        if nframe <= overlap:                  # nothing new (or nothing at all)
                             break
                         t1 = time.time()
                         self._reserve_time = 0.
-                        self._process(ispan, overlap)
+                        skip = force_skip or ispan.nframe_skipped > 0
+                        self._process(ispan, overlap, nframe, skip)
+                        if not reader.guarantee:
+                            # frames that were overwritten while on_data worked on them are
+                            # void too; one more gulp is then dropped so that a block that
+                            # fell behind can catch up (pipeline.py:630-643 of the reference)
+                            force_skip = (not skip) and ispan.nframe_overwritten > 0
                         self._log('perf', {'acquire_time': t1 - t0, 'reserve_time': self._reserve_time,
                                            'process_time': time.time() - t1 - self._reserve_time})
                         offset += gulp
                         reader.release(st, offset)
-                        if ispan.nframe < gulp + overlap:      # ragged final gulp
+                        if nframe < gulp + overlap:            # ragged final gulp
                             break
                     self.on_sequence_end(iseq)
                 finally:
@@ -430,14 +444,26 @@ class TransformBlock(_ConsumerMixin, Block):
     def _begin_outputs(self, iseq, gulp, overlap):
         self._ost = self.orings[0].begin_sequence(self._ohdr, self.define_output_nframes(gulp + overlap))
 
-    def _process(self, ispan, overlap):
+    def _process(self, ispan, overlap, nframe=None, skip=False):
         ring = self.orings[0]
-        onframe = self.define_output_nframes(ispan.nframe)
+        onframe = self.define_output_nframes(ispan.nframe if nframe is None else nframe)
         # a block that commits rarely (accumulate) is handed the same frames again
         t0 = time.time()
         ospan = ring.reserve(self._ost, onframe)
         self._reserve_time = time.time() - t0
-        ncommit = self.on_data(ispan, ospan)
+        ncommit = None
+        if not skip:
+            ncommit = self.on_data(ispan, ospan)
+            if not self._readers[0].guarantee:
+                _sync(self.irings[0].space, ring.space)        # the kernels have read what they will read
+                if ispan.nframe_overwritten:
+                    skip = True
+        if skip:
+            # the frames were lost to the writer: the output keeps its cadence, with
+            # whatever on_skip puts there (zeros)
+            lost = ispan.nframe if nframe is None else nframe
+            self.on_skip(slice(ispan.frame_offset, ispan.frame_offset + lost), ospan)
+            ncommit = None
         if ncommit is None:
             ooverlap = self.define_output_nframes(overlap) if overlap else 0
             ncommit = max(onframe - ooverlap, 0)
@@ -474,6 +500,10 @@ class SinkBlock(_ConsumerMixin, Block):
     def on_data(self, ispan):
         raise NotImplementedError
 
+    def on_skip(self, islice):
+        """Frames `islice` of the sequence were lost (unguaranteed readers only)."""
+        pass
+
     def _open_sequence(self, iseq):
         self.on_sequence(iseq)
         return self.define_input_overlap_nframe(iseq)
@@ -481,7 +511,10 @@ class SinkBlock(_ConsumerMixin, Block):
     def _begin_outputs(self, iseq, gulp, overlap):
         pass
 
-    def _process(self, ispan, overlap):
+    def _process(self, ispan, overlap, nframe=None, skip=False):
+        if skip:
+            self.on_skip(slice(ispan.frame_offset, ispan.frame_offset + (nframe or 0)))
+            return
         self.on_data(ispan)
         _sync(self.irings[0].space)
 

@@ -13,10 +13,14 @@ same machine, frame-addressed, for the blocks of the hot path:
   * the tensor's frame axis is the circular axis; axes in front of it are
     the reference's "ringlets" (ring2.py:87-107): a span is then a strided
     view, which is what the kernels take (DESIGN.md section 3);
-  * one writer, any number of guaranteed readers, each with its own cursor;
-    the writer blocks when it would overwrite frames a reader has not
+  * one writer, any number of readers, each with its own cursor; the writer
+    blocks when it would overwrite frames a *guaranteed* reader has not
     released, a reader blocks until the frames it wants are committed or the
-    sequence ends (ring_impl.cpp:open_read_at / reserve_span);
+    sequence ends (ring_impl.cpp:open_read_at / reserve_span).  A reader opened
+    with guarantee=False never holds the writer back: a span any frame of
+    which has been overwritten comes back empty with `nframe_skipped` set, and
+    `Reader.overwritten()` tells after the fact whether the writer got there
+    while the span was in use (ring.h:bfRingSpanGetSizeOverwritten);
   * storage is sized when the sequence starts, from the spans the writer and
     every reader declare (gulp + overlap), `buffer_nframe` / `buffer_factor`
     of the block scope (pipeline.py:84-134 of the reference).
@@ -80,8 +84,18 @@ class Span(object):
         self.frame_axis = faxis
         self.nframe = data.shape[faxis]
         self.nframe_skipped = 0
-        self.nframe_overwritten = 0
+        self._lost_query = None     # set for spans of unguaranteed readers
         self.frame_nbyte = 0 if self.nframe == 0 else data.nbytes // max(self.nframe, 1)
+
+
+def _nframe_overwritten(span):
+    """Frames of the span the writer has taken back since it was acquired (all of
+    them or none; always 0 for guaranteed readers) -- asked when read, like
+    ring2.py:ReadSpan.nframe_overwritten of the reference."""
+    return span.nframe if (span._lost_query is not None and span._lost_query()) else 0
+
+
+Span.nframe_overwritten = property(_nframe_overwritten)
 
 
 class _SeqState(object):
@@ -95,6 +109,7 @@ class _SeqState(object):
         self.cap = 0
         self.ghost = 0
         self.head = 0               # frames committed
+        self.reserved = 0           # frames of the open write span (the writer may scribble on them)
         self.ended = False
         self.opened = {}            # reader -> (gulp, overlap) once it has seen the header
         self.tails = {}             # reader -> frames released
@@ -151,7 +166,7 @@ class Ring(object):
         reserve(), once every reader has declared its span."""
         with self._cond:
             # readers must be done with the previous sequence before its storage goes away
-            while self._seqs and len(self._seqs[-1].closed) < len(self._readers):
+            while self._seqs and any(r.guarantee and r not in self._seqs[-1].closed for r in self._readers):
                 self._wait()
             if self._seqs:
                 self._seqs[-1].storage = None
@@ -181,8 +196,12 @@ class Ring(object):
             if st.storage is None:
                 self._allocate(st)
             assert nframe <= st.ghost, "write span longer than declared"
-            while st.tails and st.head + nframe - st.cap > min(st.tails.values()):
+            while True:
+                held = [t for r, t in st.tails.items() if r.guarantee]
+                if not held or st.head + nframe - st.cap <= min(held):
+                    break
                 self._wait()
+            st.reserved = nframe
             b = st.head % st.cap
             return Span(st.seq, slice_frames(st.storage, st.faxis, b, b + nframe), st.head, st.faxis)
 
@@ -203,6 +222,7 @@ class Ring(object):
             device.stream_synchronize()
         with self._cond:
             st.head += nframe
+            st.reserved = 0
             self._cond.notify_all()
 
     def _ghost_copy(self, st, lo, hi, dst_lo):
@@ -224,8 +244,10 @@ class Ring(object):
             self._cond.notify_all()
 
     # --------------------------------------------------------------- readers
-    def open_reader(self, who=None):
-        r = Reader(self, who)
+    def open_reader(self, who=None, guarantee=None):
+        if guarantee is None:
+            guarantee = getattr(who, 'guarantee', True)
+        r = Reader(self, who, bool(guarantee))
         with self._cond:
             self._readers.append(r)
         return r
@@ -253,8 +275,8 @@ class ViewRing(object):
             raise ValueError("Header transform returned None")
         return out
 
-    def open_reader(self, who=None):
-        r = self.root().open_reader(who)
+    def open_reader(self, who=None, guarantee=None):
+        r = self.root().open_reader(who, guarantee)
         r.view = self
         return r
 
@@ -277,9 +299,10 @@ class ViewRing(object):
 class Reader(object):
     """One consumer's cursor into a ring."""
 
-    def __init__(self, ring, who=None):
+    def __init__(self, ring, who=None, guarantee=True):
         self.ring = ring
         self.who = who
+        self.guarantee = guarantee
         self.view = None
         self._next = 0
         self._num, self._den = 1, 1      # frames of the ring per frame of this reader's view
@@ -333,20 +356,41 @@ class Reader(object):
             while st.head < frame_offset + nframe and not st.ended:
                 ring._wait()
             n = max(0, min(nframe, st.head - frame_offset))
-            if st.storage is None:
+            storage = st.storage            # (the writer drops it when the next sequence begins)
+            if storage is None:
                 n = 0
             if self._num > 1:
                 n -= n % self._num                          # whole frames of the view only
-        if n == 0:
+            # an unguaranteed reader that was lapped: the span is void as a whole
+            lost = (not self.guarantee) and n > 0 and frame_offset < st.head + st.reserved - st.cap
+        if n == 0 or lost:
             shape = list(seq.tensor['shape'])
             shape[frame_axis(seq.tensor)] = 0
-            return Span(seq, empty(shape, dtype=seq.tensor['dtype'], space='system'), view_offset, frame_axis(seq.tensor))
+            span = Span(seq, empty(shape, dtype=seq.tensor['dtype'], space='system'), view_offset, frame_axis(seq.tensor))
+            if lost:
+                span.nframe_skipped = n * self._den // self._num
+            return span
         b = frame_offset % st.cap
-        data = slice_frames(st.storage, st.faxis, b, b + n)
+        data = slice_frames(storage, st.faxis, b, b + n)
         frame_offset = view_offset
+        if not self.guarantee:
+            span = Span(seq, self.view.reinterpret(seq, data) if self.view is not None else data,
+                        frame_offset, frame_axis(seq.tensor))
+            span._lost_query = lambda: self.overwritten(st, view_offset)
+            return span
         if self.view is not None:
             data = self.view.reinterpret(seq, data)
         return Span(seq, data, frame_offset, frame_axis(seq.tensor))
+
+    def overwritten(self, st, frame_offset):
+        """True if the writer has (or may have) written over frames at or after
+        `frame_offset` (this reader's frames) since they were acquired -- only an
+        unguaranteed reader can see that happen."""
+        if self.guarantee:
+            return False
+        first = frame_offset * self._num // self._den
+        with self.ring._cond:
+            return first < st.head + st.reserved - st.cap
 
     def release(self, st, upto_frame):
         upto_frame = upto_frame * self._num // self._den

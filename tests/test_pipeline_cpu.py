@@ -427,3 +427,68 @@ def test_a_signal_shuts_a_running_pipeline_down():
         assert any('shutting down pipeline' in str(w.message) for w in caught)
     finally:
         signal.signal(signal.SIGUSR1, old)
+
+
+def test_unguaranteed_readers_are_lapped_instead_of_holding_the_writer_back():
+    """guarantee=False (pipeline.py:518-537,590-643 of the reference): a slow
+    sink loses whole gulps, never sees a torn one, and does not slow the source
+    or the guaranteed sink next to it down; a transform behind an unguaranteed
+    reader keeps its output cadence with on_skip's zeros for what was lost."""
+    import time
+    nframe, gulp = 4000, 8
+    data = (np.arange(nframe * 3, dtype=np.float32).reshape(nframe, 3) + 1)       # no zeros in the data
+    fast, slow, behind = Collect(), Collect(), Collect()
+    slow.offsets, slow.skipped = [], []
+    t_fast = [0.]
+
+    def fast_data(ispan):
+        fast.data(ispan)
+        t_fast[0] = time.time()
+
+    def slow_data(ispan):
+        chunk = np.array(ispan.data.copy('system'))
+        time.sleep(0.002)
+        if ispan.nframe_overwritten:           # the writer came by meanwhile: the copy may be torn
+            slow.skipped.append((ispan.frame_offset, ispan.frame_offset + ispan.nframe))
+        else:
+            slow.offsets.append(ispan.frame_offset)
+            slow.chunks.append(chunk)
+
+    class SlowSink(bf.blocks.testing.CallbackSinkBlock):
+        def on_skip(self, islice):
+            slow.skipped.append((islice.start, islice.stop))
+
+    class SlowCopy(TransformBlock):
+        def on_sequence(self, iseq):
+            return deepcopy(iseq.header)
+
+        def on_data(self, ispan, ospan):
+            time.sleep(0.002)
+            bf.copy_array(ospan.data, ispan.data)
+
+    with Pipeline() as p:
+        with bf.block_scope(buffer_nframe=4 * gulp):
+            src = array_source(data, header([-1, 3]), gulp_nframe=gulp)
+        callback_sink(src, None, fast_data, gulp_nframe=gulp)
+        SlowSink(src, None, slow_data, gulp_nframe=gulp, guarantee=False)
+        callback_sink(SlowCopy(src, gulp_nframe=gulp, guarantee=False), None, behind.data, gulp_nframe=gulp)
+        t0 = time.time()
+        p.run()
+        t_all = time.time() - t0
+    # the guaranteed sink got everything, and nobody waited for the slow ones: had they
+    # held the source back the run would have taken 500 gulps x 2 ms
+    np.testing.assert_array_equal(np.concatenate(fast.chunks, axis=0), data)
+    assert t_all < 0.5 * (nframe // gulp) * 0.002
+    # the slow sink: whole gulps, each intact, the rest reported lost, nothing twice
+    assert slow.skipped and len(slow.chunks) < nframe // gulp
+    for off, chunk in zip(slow.offsets, slow.chunks):
+        np.testing.assert_array_equal(chunk, data[off:off + gulp])
+    seen = sorted([(o, o + gulp) for o in slow.offsets] + slow.skipped)
+    assert seen[0][0] == 0 and all(a[1] == b[0] for a, b in zip(seen[:-1], seen[1:]))
+    # the transform: every frame accounted for, lost gulps are zeros, the others the data
+    out = np.concatenate(behind.chunks, axis=0)
+    assert out.shape == data.shape
+    blocks = out.reshape(-1, gulp, 3)
+    zero = ~blocks.reshape(len(blocks), -1).any(axis=1)
+    assert zero.any() and not zero.all()
+    np.testing.assert_array_equal(blocks[~zero], data.reshape(-1, gulp, 3)[~zero])
