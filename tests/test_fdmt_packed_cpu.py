@@ -461,3 +461,37 @@ def test_packed_tables_of_the_config5_subband_plans(nrank):
         got = np.zeros((md, ntime), np.float32)
         run_schedule(x, passes, got)
         assert np.array_equal(got.view(np.uint32), gold.view(np.uint32)), (nrank, g)
+
+
+def test_packed_tables_of_random_plans():
+    """Forty random geometries (odd channel counts, reversed and narrow bands,
+    bank depths from 1 to a few hundred, low frequencies where the delays pile
+    up in the first channels): whenever bfFdmtInit would take the integer
+    schedule its tables must be the transform."""
+    rng = np.random.default_rng(20240923)
+    ran = 0
+    for case in range(40):
+        nchan = int(rng.integers(2, 400))
+        md = int(rng.integers(1, 260))
+        f0 = float(rng.choice([40.0, 150.0, 400.0, 1000.0, 1400.0, 4000.0]))
+        frac = float(rng.uniform(0.02, 0.6))                 # bandwidth as a fraction of f0
+        df = f0 * frac / nchan * (1 if rng.random() < 0.7 else -1)
+        if df < 0:
+            f0 = f0 * (1 + frac)                             # keep every channel above zero
+        ntime = md + int(rng.integers(40, 500))
+        dtype = np.int8 if rng.random() < 0.6 else np.uint8
+        try:
+            passes = query(nchan, md, f0, df)
+        except Exception:
+            passes = None                                    # a plan the reference would refuse as well
+        if not passes:
+            continue
+        info = np.iinfo(dtype)
+        x = rng.integers(info.min, info.max + 1, size=(nchan, ntime)).astype(dtype)
+        gold = np.full((md, ntime), -7.0, np.float32)
+        ofdmt.fdmt(x, md, f0, df, out=gold)
+        got = np.full((md, ntime), -7.0, np.float32)
+        run_schedule(x, passes, got)
+        assert np.array_equal(got.view(np.uint32), gold.view(np.uint32)), (case, nchan, md, f0, df, ntime, dtype)
+        ran += 1
+    assert ran >= 25
