@@ -36,6 +36,10 @@ def test_ring_is_race_free_under_thread_sanitizer(stress_binary, tmp_path):
     env = dict(os.environ, BIFROST_B200_PROCLOG_DIR=str(tmp_path / 'proclog'),
                TSAN_OPTIONS='halt_on_error=0 exitcode=66')
     res = subprocess.run([stress_binary], capture_output=True, text=True, timeout=280, env=env)
+    if 'FATAL: ThreadSanitizer' in res.stderr:
+        # the sanitizer runtime could not start (e.g. an address-space layout it
+        # does not support on this kernel): nothing was tested
+        pytest.skip(res.stderr.strip().splitlines()[0][:200])
     assert 'ThreadSanitizer' not in res.stderr, res.stderr[-4000:]
     assert res.returncode == 0, (res.returncode, res.stderr[-2000:])
     assert res.stdout.startswith('OK ')
