@@ -64,38 +64,60 @@ def test_live_differential_against_the_reference_ring(seed):
 
 
 # --------------------------------------------------------------------------
-# small binding for the threaded tests
+# small binding for the threaded tests; `L` is the library under test -- ours,
+# or (fixture `lib`) the reference's own ring, so that what these tests expect
+# is checked to be the reference's behaviour too
 # --------------------------------------------------------------------------
+class _Lib(object):
+    target = OURS
+
+    def __getattr__(self, name):
+        return getattr(_Lib.target, name)
+
+
+L = _Lib()
+
+
+@pytest.fixture(params=['ours', 'reference'])
+def lib(request):
+    if request.param == 'reference':
+        if REF is None:
+            pytest.skip('oracle/_ref/libbifrost_ref_ring.so not built')
+        _Lib.target = REF
+    yield request.param
+    _Lib.target = OURS
+
+
 class Ring(object):
     def __init__(self, name, space='system'):
         self.obj = ctypes.c_void_p()
         self.space = _bf.BF_SPACE_CUDA if space == 'cuda' else _bf.BF_SPACE_SYSTEM
-        _check(_bf.bfRingCreate(ctypes.byref(self.obj), name.encode(), self.space))
+        _check(L.bfRingCreate(ctypes.byref(self.obj), name.encode(), self.space))
 
     def destroy(self):
-        _check(_bf.bfRingDestroy(self.obj))
+        _check(L.bfRingDestroy(self.obj))
 
     def reserve(self, nbyte, nonblocking=False):
         h = ctypes.c_void_p()
-        _check(_bf.bfRingSpanReserve(ctypes.byref(h), self.obj, nbyte, nonblocking))
+        _check(L.bfRingSpanReserve(ctypes.byref(h), self.obj, nbyte, nonblocking))
         return h
 
     @staticmethod
     def info(span):
         inf = BFspan_info()
-        _check(_bf.bfRingSpanGetInfo(span, ctypes.byref(inf)))
+        _check(L.bfRingSpanGetInfo(span, ctypes.byref(inf)))
         return inf
 
     def begin_sequence(self, name, time_tag, header=b'', nringlet=1):
         h = ctypes.c_void_p()
         buf = ctypes.create_string_buffer(header, len(header))
-        _check(_bf.bfRingSequenceBegin(ctypes.byref(h), self.obj, name.encode(), time_tag, len(header),
+        _check(L.bfRingSequenceBegin(ctypes.byref(h), self.obj, name.encode(), time_tag, len(header),
                                        ctypes.cast(buf, ctypes.c_void_p), nringlet, 0))
         return h
 
     def open_earliest(self, guarantee=True):
         h = ctypes.c_void_p()
-        _check(_bf.bfRingSequenceOpenEarliest(ctypes.byref(h), self.obj, guarantee))
+        _check(L.bfRingSequenceOpenEarliest(ctypes.byref(h), self.obj, guarantee))
         return h
 
 
@@ -110,19 +132,19 @@ def span_view(inf, r):
 
 
 @pytest.mark.timeout(120)
-def test_writer_and_guaranteed_readers_stream_through_a_small_ring():
+def test_writer_and_guaranteed_readers_stream_through_a_small_ring(lib):
     """200 gulps through a ring that holds 4: the writer blocks on the slowest
     guaranteed reader, readers block on the writer, spans wrap through the ghost
     region, two sequences, every byte of both ringlets arrives in order."""
     gulp, ngulp, nringlet = 1000, 200, 2
     ring = Ring('threaded')
-    _check(_bf.bfRingResize(ring.obj, gulp, 4 * gulp, nringlet))
+    _check(L.bfRingResize(ring.obj, gulp, 4 * gulp, nringlet))
     errors = []
     opened = threading.Semaphore(0)
 
     def writer():
         try:
-            _check(_bf.bfRingBeginWriting(ring.obj))
+            _check(L.bfRingBeginWriting(ring.obj))
             i = 0
             for s in range(2):
                 seq = ring.begin_sequence('obs%d' % s, 100 + s, b'hdr%d' % s, nringlet)
@@ -135,10 +157,10 @@ def test_writer_and_guaranteed_readers_stream_through_a_small_ring():
                     assert inf.size == gulp and inf.nringlet == nringlet
                     for r in range(nringlet):
                         span_view(inf, r)[:] = payload(i, r, gulp)
-                    _check(_bf.bfRingSpanCommit(span, gulp))
+                    _check(L.bfRingSpanCommit(span, gulp))
                     i += 1
-                _check(_bf.bfRingSequenceEnd(seq, 0))
-            _check(_bf.bfRingEndWriting(ring.obj))
+                _check(L.bfRingSequenceEnd(seq, 0))
+            _check(L.bfRingEndWriting(ring.obj))
         except Exception as e:      # pragma: no cover
             errors.append(e)
 
@@ -148,33 +170,35 @@ def test_writer_and_guaranteed_readers_stream_through_a_small_ring():
             opened.release()
             i = 0
             for s in range(2):
-                assert _get(_bf.bfRingSequenceGetName, seq) == b'obs%d' % s
-                sinf = BFsequence_info()
-                _check(_bf.bfRingSequenceGetInfo(seq, ctypes.byref(sinf)))
-                assert ctypes.string_at(sinf.header, sinf.header_size) == b'hdr%d' % s and sinf.time_tag == 100 + s
+                assert _get(L.bfRingSequenceGetName, seq) == b'obs%d' % s
+                if hasattr(_Lib.target, 'bfRingSequenceGetInfo'):      # (declared but not defined by the reference)
+                    sinf = BFsequence_info()
+                    _check(L.bfRingSequenceGetInfo(seq, ctypes.byref(sinf)))
+                    assert ctypes.string_at(sinf.header, sinf.header_size) == b'hdr%d' % s and sinf.time_tag == 100 + s
+                assert _get(L.bfRingSequenceGetTimeTag, seq) == 100 + s
                 offset = 0
                 while True:
                     span = ctypes.c_void_p()
                     try:
-                        _check(_bf.bfRingSpanAcquire(ctypes.byref(span), seq, offset, read_size))
+                        _check(L.bfRingSpanAcquire(ctypes.byref(span), seq, offset, read_size))
                     except EndOfDataStop:
                         break
                     inf = ring.info(span)
                     assert inf.offset == offset and 0 < inf.size <= read_size
-                    assert _get(_bf.bfRingSpanGetSizeOverwritten, span) == 0
+                    assert _get(L.bfRingSpanGetSizeOverwritten, span) == 0
                     for r in range(nringlet):
                         got = span_view(inf, r)
                         for j in range(0, inf.size, gulp):
                             np.testing.assert_array_equal(got[j:j + gulp], payload(i + j // gulp, r, gulp)[:inf.size - j])
-                    _check(_bf.bfRingSpanRelease(span))
+                    _check(L.bfRingSpanRelease(span))
                     offset += inf.size
                     i += inf.size // gulp
                 assert offset == (ngulp // 2) * gulp
                 if s == 0:
-                    _check(_bf.bfRingSequenceNext(seq))
+                    _check(L.bfRingSequenceNext(seq))
             with pytest.raises(EndOfDataStop):
-                _check(_bf.bfRingSequenceNext(seq))
-            _check(_bf.bfRingSequenceClose(seq))
+                _check(L.bfRingSequenceNext(seq))
+            _check(L.bfRingSequenceClose(seq))
         except Exception as e:      # pragma: no cover
             errors.append(e)
 
@@ -190,15 +214,15 @@ def test_writer_and_guaranteed_readers_stream_through_a_small_ring():
 
 
 @pytest.mark.timeout(60)
-def test_blocking_reserve_waits_for_the_guaranteed_reader():
+def test_blocking_reserve_waits_for_the_guaranteed_reader(lib):
     gulp = 4096
     ring = Ring('blocking')
-    _check(_bf.bfRingResize(ring.obj, gulp, 2 * gulp, 1))
-    _check(_bf.bfRingBeginWriting(ring.obj))
+    _check(L.bfRingResize(ring.obj, gulp, 2 * gulp, 1))
+    _check(L.bfRingBeginWriting(ring.obj))
     ring.begin_sequence('s', 1)
     reader = ring.open_earliest(guarantee=True)
     for _ in range(2):
-        _check(_bf.bfRingSpanCommit(ring.reserve(gulp), gulp))
+        _check(L.bfRingSpanCommit(ring.reserve(gulp), gulp))
     # the ring is full of data the reader still holds: non-blocking says so ...
     with pytest.raises(IOError):
         ring.reserve(gulp, nonblocking=True)
@@ -206,116 +230,116 @@ def test_blocking_reserve_waits_for_the_guaranteed_reader():
     done = threading.Event()
 
     def blocked():
-        _check(_bf.bfRingSpanCommit(ring.reserve(gulp), gulp))
+        _check(L.bfRingSpanCommit(ring.reserve(gulp), gulp))
         done.set()
     t = threading.Thread(target=blocked)
     t.start()
     assert not done.wait(0.3)
     span = ctypes.c_void_p()
-    _check(_bf.bfRingSpanAcquire(ctypes.byref(span), reader, gulp, gulp))      # lets go of the first gulp
+    _check(L.bfRingSpanAcquire(ctypes.byref(span), reader, gulp, gulp))      # lets go of the first gulp
     assert done.wait(10)
     t.join()
-    _check(_bf.bfRingSpanRelease(span))
-    _check(_bf.bfRingSequenceClose(reader))
+    _check(L.bfRingSpanRelease(span))
+    _check(L.bfRingSequenceClose(reader))
     ring.destroy()
 
 
-def test_unguaranteed_reader_sees_what_was_overwritten():
+def test_unguaranteed_reader_sees_what_was_overwritten(lib):
     gulp = 4096
     ring = Ring('lossy')
-    _check(_bf.bfRingResize(ring.obj, gulp, 2 * gulp, 1))
-    _check(_bf.bfRingBeginWriting(ring.obj))
+    _check(L.bfRingResize(ring.obj, gulp, 2 * gulp, 1))
+    _check(L.bfRingBeginWriting(ring.obj))
     ring.begin_sequence('s', 1)
-    _check(_bf.bfRingSpanCommit(ring.reserve(gulp), gulp))
+    _check(L.bfRingSpanCommit(ring.reserve(gulp), gulp))
     reader = ring.open_earliest(guarantee=False)
     span = ctypes.c_void_p()
-    _check(_bf.bfRingSpanAcquire(ctypes.byref(span), reader, 0, gulp))
-    assert _get(_bf.bfRingSpanGetSizeOverwritten, span) == 0
-    _check(_bf.bfRingSpanCommit(ring.reserve(gulp), gulp))          # the ring is full now ...
+    _check(L.bfRingSpanAcquire(ctypes.byref(span), reader, 0, gulp))
+    assert _get(L.bfRingSpanGetSizeOverwritten, span) == 0
+    _check(L.bfRingSpanCommit(ring.reserve(gulp), gulp))          # the ring is full now ...
     half = ring.reserve(gulp // 2)                                   # ... and this laps the reader by half a gulp
-    assert _get(_bf.bfRingSpanGetSizeOverwritten, span) == gulp // 2
-    _check(_bf.bfRingSpanCommit(half, gulp // 2))
-    _check(_bf.bfRingSpanRelease(span))
+    assert _get(L.bfRingSpanGetSizeOverwritten, span) == gulp // 2
+    _check(L.bfRingSpanCommit(half, gulp // 2))
+    _check(L.bfRingSpanRelease(span))
     # asking again for the start of the sequence gives what is left of it
-    _check(_bf.bfRingSpanAcquire(ctypes.byref(span), reader, 0, gulp))
+    _check(L.bfRingSpanAcquire(ctypes.byref(span), reader, 0, gulp))
     inf = ring.info(span)
     assert (inf.offset, inf.size) == (gulp // 2, gulp // 2)
-    _check(_bf.bfRingSpanRelease(span))
-    _check(_bf.bfRingSequenceClose(reader))
+    _check(L.bfRingSpanRelease(span))
+    _check(L.bfRingSequenceClose(reader))
     ring.destroy()
 
 
 def test_status_codes_of_misuse():
     ring = Ring('misuse')
     h = ctypes.c_void_p()
-    assert _bf.bfRingSpanReserve(ctypes.byref(h), ring.obj, 16, 1) == _bf.BF_STATUS_INVALID_ARGUMENT   # > contiguous span (0)
-    assert _bf.bfRingSpanReserve(ctypes.byref(h), ring.obj, 0, 1) == _bf.BF_STATUS_INVALID_STATE       # never sized
-    _check(_bf.bfRingResize(ring.obj, 100, 400, 2))
-    assert _get(_bf.bfRingGetName, ring.obj) == b'misuse'
-    assert _get(_bf.bfRingGetSpace, ring.obj) == _bf.BF_SPACE_SYSTEM
-    _check(_bf.bfRingLock(ring.obj))
-    assert _get(_bf.bfRingLockedGetContiguousSpan, ring.obj) == 4096       # rounded up to the alignment
-    assert _get(_bf.bfRingLockedGetTotalSpan, ring.obj) == 4096           # power of two >= alignment
-    assert _get(_bf.bfRingLockedGetStride, ring.obj) == 8192
-    assert _get(_bf.bfRingLockedGetNRinglet, ring.obj) == 2
-    assert _get(_bf.bfRingLockedGetData, ring.obj) % 4096 == 0
-    _check(_bf.bfRingUnlock(ring.obj))
-    assert _bf.bfRingEndWriting(ring.obj) == _bf.BF_STATUS_INVALID_STATE       # before begin
-    _check(_bf.bfRingBeginWriting(ring.obj))
-    assert _bf.bfRingBeginWriting(ring.obj) == _bf.BF_STATUS_INVALID_STATE
-    assert _bf.bfRingSpanReserve(ctypes.byref(h), ring.obj, 4097, 1) == _bf.BF_STATUS_INVALID_ARGUMENT
-    assert _bf.bfRingSequenceBegin(ctypes.byref(h), ring.obj, b's', 1, 0, None, 3, 0) == _bf.BF_STATUS_INVALID_ARGUMENT
-    assert _bf.bfRingSequenceBegin(ctypes.byref(h), ring.obj, b's', 1, 4, None, 1, 0) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert L.bfRingSpanReserve(ctypes.byref(h), ring.obj, 16, 1) == _bf.BF_STATUS_INVALID_ARGUMENT   # > contiguous span (0)
+    assert L.bfRingSpanReserve(ctypes.byref(h), ring.obj, 0, 1) == _bf.BF_STATUS_INVALID_STATE       # never sized
+    _check(L.bfRingResize(ring.obj, 100, 400, 2))
+    assert _get(L.bfRingGetName, ring.obj) == b'misuse'
+    assert _get(L.bfRingGetSpace, ring.obj) == _bf.BF_SPACE_SYSTEM
+    _check(L.bfRingLock(ring.obj))
+    assert _get(L.bfRingLockedGetContiguousSpan, ring.obj) == 4096       # rounded up to the alignment
+    assert _get(L.bfRingLockedGetTotalSpan, ring.obj) == 4096           # power of two >= alignment
+    assert _get(L.bfRingLockedGetStride, ring.obj) == 8192
+    assert _get(L.bfRingLockedGetNRinglet, ring.obj) == 2
+    assert _get(L.bfRingLockedGetData, ring.obj) % 4096 == 0
+    _check(L.bfRingUnlock(ring.obj))
+    assert L.bfRingEndWriting(ring.obj) == _bf.BF_STATUS_INVALID_STATE       # before begin
+    _check(L.bfRingBeginWriting(ring.obj))
+    assert L.bfRingBeginWriting(ring.obj) == _bf.BF_STATUS_INVALID_STATE
+    assert L.bfRingSpanReserve(ctypes.byref(h), ring.obj, 4097, 1) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert L.bfRingSequenceBegin(ctypes.byref(h), ring.obj, b's', 1, 0, None, 3, 0) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert L.bfRingSequenceBegin(ctypes.byref(h), ring.obj, b's', 1, 4, None, 1, 0) == _bf.BF_STATUS_INVALID_ARGUMENT
     seq = ring.begin_sequence('s', 1, b'abc', 2)
-    assert _bf.bfRingSequenceBegin(ctypes.byref(h), ring.obj, b't', 2, 0, None, 1, 0) == _bf.BF_STATUS_INVALID_STATE
-    assert _bf.bfRingSequenceOpen(ctypes.byref(h), ring.obj, b'nope', 1) == _bf.BF_STATUS_INVALID_ARGUMENT
-    assert _bf.bfRingSequenceOpenAt(ctypes.byref(h), ring.obj, 0, 1) == _bf.BF_STATUS_INVALID_ARGUMENT
-    assert _bf.bfRingSequenceOpenAt(ctypes.byref(h), ring.obj, 2 ** 64 - 1, 1) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert L.bfRingSequenceBegin(ctypes.byref(h), ring.obj, b't', 2, 0, None, 1, 0) == _bf.BF_STATUS_INVALID_STATE
+    assert L.bfRingSequenceOpen(ctypes.byref(h), ring.obj, b'nope', 1) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert L.bfRingSequenceOpenAt(ctypes.byref(h), ring.obj, 0, 1) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert L.bfRingSequenceOpenAt(ctypes.byref(h), ring.obj, 2 ** 64 - 1, 1) == _bf.BF_STATUS_INVALID_ARGUMENT
     w = ring.reserve(64)
-    assert _bf.bfRingEndWriting(ring.obj) == _bf.BF_STATUS_INVALID_STATE       # a span is open
-    assert _bf.bfRingSpanCommit(w, 65) == _bf.BF_STATUS_INVALID_ARGUMENT
-    _check(_bf.bfRingSpanCommit(w, 64))
-    _check(_bf.bfRingSequenceEnd(seq, 0))
-    _check(_bf.bfRingEndWriting(ring.obj))
-    assert _get(_bf.bfRingWritingEnded, ring.obj) == 1
-    _check(_bf.bfRingSequenceOpen(ctypes.byref(h), ring.obj, b's', 0))
+    assert L.bfRingEndWriting(ring.obj) == _bf.BF_STATUS_INVALID_STATE       # a span is open
+    assert L.bfRingSpanCommit(w, 65) == _bf.BF_STATUS_INVALID_ARGUMENT
+    _check(L.bfRingSpanCommit(w, 64))
+    _check(L.bfRingSequenceEnd(seq, 0))
+    _check(L.bfRingEndWriting(ring.obj))
+    assert _get(L.bfRingWritingEnded, ring.obj) == 1
+    _check(L.bfRingSequenceOpen(ctypes.byref(h), ring.obj, b's', 0))
     span = ctypes.c_void_p()
-    assert _bf.bfRingSpanAcquire(ctypes.byref(span), h, 64, 8) == _bf.BF_STATUS_END_OF_DATA
-    _check(_bf.bfRingSpanAcquire(ctypes.byref(span), h, 60, 8))
+    assert L.bfRingSpanAcquire(ctypes.byref(span), h, 64, 8) == _bf.BF_STATUS_END_OF_DATA
+    _check(L.bfRingSpanAcquire(ctypes.byref(span), h, 60, 8))
     assert ring.info(span).size == 4                                           # cut at the end of the sequence
-    _check(_bf.bfRingSpanRelease(span))
-    assert _bf.bfRingSequenceNext(h) == _bf.BF_STATUS_END_OF_DATA
-    _check(_bf.bfRingSequenceClose(h))
-    for fn, args in ((_bf.bfRingDestroy, (None,)), (_bf.bfRingSpanRelease, (None,)), (_bf.bfRingSequenceClose, (None,)),
-                     (_bf.bfRingResize, (None, 1, 1, 1))):
+    _check(L.bfRingSpanRelease(span))
+    assert L.bfRingSequenceNext(h) == _bf.BF_STATUS_END_OF_DATA
+    _check(L.bfRingSequenceClose(h))
+    for fn, args in ((L.bfRingDestroy, (None,)), (L.bfRingSpanRelease, (None,)), (L.bfRingSequenceClose, (None,)),
+                     (L.bfRingResize, (None, 1, 1, 1))):
         assert fn(*args) == _bf.BF_STATUS_INVALID_HANDLE
-    assert _bf.bfRingCreate(None, b'x', 1) == _bf.BF_STATUS_INVALID_POINTER
-    assert _bf.bfRingCreate(ctypes.byref(h), b'x', 77) == _bf.BF_STATUS_INVALID_ARGUMENT
+    assert L.bfRingCreate(None, b'x', 1) == _bf.BF_STATUS_INVALID_POINTER
+    assert L.bfRingCreate(ctypes.byref(h), b'x', 77) == _bf.BF_STATUS_INVALID_ARGUMENT
     ring.destroy()
 
 
-def test_opening_on_an_ended_empty_ring_is_end_of_data():
+def test_opening_on_an_ended_empty_ring_is_end_of_data(lib):
     ring = Ring('empty')
-    _check(_bf.bfRingResize(ring.obj, 64, 256, 1))
-    _check(_bf.bfRingBeginWriting(ring.obj))
-    _check(_bf.bfRingEndWriting(ring.obj))
+    _check(L.bfRingResize(ring.obj, 64, 256, 1))
+    _check(L.bfRingBeginWriting(ring.obj))
+    _check(L.bfRingEndWriting(ring.obj))
     h = ctypes.c_void_p()
-    assert _bf.bfRingSequenceOpenEarliest(ctypes.byref(h), ring.obj, 1) == _bf.BF_STATUS_END_OF_DATA
-    assert _bf.bfRingSequenceOpenLatest(ctypes.byref(h), ring.obj, 0) == _bf.BF_STATUS_END_OF_DATA
+    assert L.bfRingSequenceOpenEarliest(ctypes.byref(h), ring.obj, 1) == _bf.BF_STATUS_END_OF_DATA
+    assert L.bfRingSequenceOpenLatest(ctypes.byref(h), ring.obj, 0) == _bf.BF_STATUS_END_OF_DATA
     # the failed guaranteed open left nothing pinned: the writer side would not block
     ring.destroy()
 
 
 def test_ring_memory_placement_request_is_honoured_or_harmless():
     ring = Ring('numa')
-    assert _get(_bf.bfRingGetAffinity, ring.obj) == -1
-    _check(_bf.bfRingSetAffinity(ring.obj, 0))
-    assert _get(_bf.bfRingGetAffinity, ring.obj) == 0
-    assert _bf.bfRingSetAffinity(ring.obj, -2) == _bf.BF_STATUS_INVALID_ARGUMENT
-    _check(_bf.bfRingResize(ring.obj, 1 << 16, 1 << 18, 1))       # allocates under the node preference
+    assert _get(L.bfRingGetAffinity, ring.obj) == -1
+    _check(L.bfRingSetAffinity(ring.obj, 0))
+    assert _get(L.bfRingGetAffinity, ring.obj) == 0
+    assert L.bfRingSetAffinity(ring.obj, -2) == _bf.BF_STATUS_INVALID_ARGUMENT
+    _check(L.bfRingResize(ring.obj, 1 << 16, 1 << 18, 1))       # allocates under the node preference
     w = ring.reserve(1 << 16)
     span_view(ring.info(w), 0)[:] = 5
-    _check(_bf.bfRingSpanCommit(w, 1 << 16))
+    _check(L.bfRingSpanCommit(w, 1 << 16))
     ring.destroy()
 
 
@@ -343,7 +367,7 @@ def test_proclog_files():
     assert _bf.bfProcLogUpdate(None, b'') == _bf.BF_STATUS_INVALID_HANDLE
     # every ring describes itself under rings/<name>
     ring = Ring('logged')
-    _check(_bf.bfRingResize(ring.obj, 100, 1000, 3))
+    _check(L.bfRingResize(ring.obj, 100, 1000, 3))
     text = open(os.path.join(proclog_root(), 'rings', 'logged')).read()
     fields = dict(line.split(':') for line in text.strip().splitlines())
     fields = {k.strip(): v.strip() for k, v in fields.items()}
@@ -388,9 +412,9 @@ def test_thread_affinity():
 def test_cuda_space_ring_round_trip():
     gulp, ngulp, nringlet = 3000, 40, 2
     ring = Ring('device', space='cuda')
-    _check(_bf.bfRingResize(ring.obj, gulp, 4 * gulp, nringlet))
-    assert _get(_bf.bfRingGetSpace, ring.obj) == _bf.BF_SPACE_CUDA
-    _check(_bf.bfRingBeginWriting(ring.obj))
+    _check(L.bfRingResize(ring.obj, gulp, 4 * gulp, nringlet))
+    assert _get(L.bfRingGetSpace, ring.obj) == _bf.BF_SPACE_CUDA
+    _check(L.bfRingBeginWriting(ring.obj))
     seq = ring.begin_sequence('dev', 7, b'{}', nringlet)
     reader = ring.open_earliest(guarantee=True)
     for i in range(ngulp):
@@ -401,13 +425,13 @@ def test_cuda_space_ring_round_trip():
         _check(_bf.bfMemcpy2D(inf.data, inf.stride, _bf.BF_SPACE_CUDA, src.ctypes.data, gulp, _bf.BF_SPACE_SYSTEM,
                               gulp, nringlet))
         _check(_bf.bfStreamSynchronize())
-        _check(_bf.bfRingSpanCommit(w, gulp))
+        _check(L.bfRingSpanCommit(w, gulp))
         # read it back half a gulp late, so that read spans straddle the write
         # spans and both kinds of ghost copy (write ran over the end / read
         # runs over the end) happen on the device
         if i >= 1:
             span = ctypes.c_void_p()
-            _check(_bf.bfRingSpanAcquire(ctypes.byref(span), reader, (i - 1) * gulp + gulp // 2, gulp))
+            _check(L.bfRingSpanAcquire(ctypes.byref(span), reader, (i - 1) * gulp + gulp // 2, gulp))
             rinf = ring.info(span)
             assert rinf.size == gulp
             got = np.zeros((nringlet, gulp), np.uint8)
@@ -417,11 +441,11 @@ def test_cuda_space_ring_round_trip():
             for r in range(nringlet):
                 want = np.concatenate([payload(i - 1, r, gulp)[gulp // 2:], payload(i, r, gulp)[:gulp // 2]])
                 np.testing.assert_array_equal(got[r], want)
-            _check(_bf.bfRingSpanRelease(span))
+            _check(L.bfRingSpanRelease(span))
     # growing a device ring keeps its contents
-    _check(_bf.bfRingResize(ring.obj, 2 * gulp, 16 * gulp, nringlet))
+    _check(L.bfRingResize(ring.obj, 2 * gulp, 16 * gulp, nringlet))
     span = ctypes.c_void_p()
-    _check(_bf.bfRingSpanAcquire(ctypes.byref(span), reader, (ngulp - 2) * gulp, 2 * gulp))
+    _check(L.bfRingSpanAcquire(ctypes.byref(span), reader, (ngulp - 2) * gulp, 2 * gulp))
     rinf = ring.info(span)
     got = np.zeros((nringlet, 2 * gulp), np.uint8)
     _check(_bf.bfMemcpy2D(got.ctypes.data, 2 * gulp, _bf.BF_SPACE_SYSTEM, rinf.data, rinf.stride, _bf.BF_SPACE_CUDA,
@@ -429,8 +453,8 @@ def test_cuda_space_ring_round_trip():
     _check(_bf.bfStreamSynchronize())
     for r in range(nringlet):
         np.testing.assert_array_equal(got[r], np.concatenate([payload(ngulp - 2, r, gulp), payload(ngulp - 1, r, gulp)]))
-    _check(_bf.bfRingSpanRelease(span))
-    _check(_bf.bfRingSequenceEnd(seq, 0))
-    _check(_bf.bfRingSequenceClose(reader))
-    _check(_bf.bfRingEndWriting(ring.obj))
+    _check(L.bfRingSpanRelease(span))
+    _check(L.bfRingSequenceEnd(seq, 0))
+    _check(L.bfRingSequenceClose(reader))
+    _check(L.bfRingEndWriting(ring.obj))
     ring.destroy()
