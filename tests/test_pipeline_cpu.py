@@ -478,7 +478,7 @@ def test_unguaranteed_readers_are_lapped_instead_of_holding_the_writer_back():
     # the guaranteed sink got everything, and nobody waited for the slow ones: had they
     # held the source back the run would have taken 500 gulps x 2 ms
     np.testing.assert_array_equal(np.concatenate(fast.chunks, axis=0), data)
-    assert t_all < 0.5 * (nframe // gulp) * 0.002
+    assert t_all < 0.8 * (nframe // gulp) * 0.002
     # the slow sink: whole gulps, each intact, the rest reported lost, nothing twice
     assert slow.skipped and len(slow.chunks) < nframe // gulp
     for off, chunk in zip(slow.offsets, slow.chunks):
